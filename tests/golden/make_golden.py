@@ -1,0 +1,145 @@
+"""Generate the committed golden fixtures under tests/golden/.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+
+Fixtures written
+  ref_glue_reim.npz   LIVE REFERENCE: BRNNmultiCH.forward (model.py:169-200) run unmodified on
+                      CPU (only ``.cuda()`` in its ctor, model.py:167, is shimmed to a no-op);
+                      the masks it multiplies by are captured with forward hooks; output and
+                      autograd gradients w.r.t. both masks are stored.
+  ref_collate.npz     LIVE REFERENCE: _collate_fn / _collate_fn_paired outputs
+                      (loader_functions.py:47-105) for a seeded ragged batch.
+  ref_ctc_sizes.npz   LIVE torch semantics of trainer_AAS.py:165-167 on a grid of (T, Tmax, T').
+  oracle_lmfb_*.npz   float64 ORACLE outputs (parity unpinned at the STFT/CMVN boundary, see
+                      oracle/lmfb_oracle.py) for seeded inputs from tests/_synth.py.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF = "/root/reference/Speech_enhancement_by_AAS"
+
+from oracle import lmfb_oracle as orc   # noqa: E402
+import _synth                            # noqa: E402
+
+
+def make_ref_glue():
+    sys.path.insert(0, REF)
+    import model as ref_model            # the reference's own model.py
+
+    torch.manual_seed(123)
+    f, t, n, h = 161, 9, 2, 16
+    mel = orc.mel_filterbank().astype(np.float32)
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self          # shim for model.py:167 only
+    try:
+        net = ref_model.BRNNmultiCH(I=2 * f, H=h, L=2, nCH=1, mel_basis=mel)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    net = net.float()
+    captured = {}
+
+    def hook(name):
+        def fn(_m, _i, out):
+            out.retain_grad()
+            captured[name] = out
+        return fn
+
+    net.final_linear_real.register_forward_hook(hook("mr"))
+    net.final_linear_imag.register_forward_hook(hook("mi"))
+    rs = np.random.RandomState(123)
+    x = torch.from_numpy(rs.randn(n, 2 * f, t).astype(np.float32) * 3.0)
+    out = net(x)
+    g = torch.from_numpy(rs.randn(*out.shape).astype(np.float32))
+    out.backward(g)
+    np.savez_compressed(
+        os.path.join(HERE, "ref_glue_reim.npz"),
+        stft_real=x[:, :f].numpy(), stft_imag=x[:, f:].numpy(),
+        mask_real=captured["mr"].detach().numpy(), mask_imag=captured["mi"].detach().numpy(),
+        mel_basis=mel, output=out.detach().numpy(), grad_out=g.numpy(),
+        grad_mask_real=captured["mr"].grad.numpy(), grad_mask_imag=captured["mi"].grad.numpy())
+    sys.path.remove(REF)
+
+
+def make_ref_collate():
+    sys.path.insert(0, REF)
+    import loader_functions as lf
+
+    rs = np.random.RandomState(7)
+    lens = [37, 52, 52, 11, 29, 52, 1]
+    batch, paired = [], []
+    for i, t in enumerate(lens):
+        feat = torch.from_numpy(rs.randn(40, t).astype(np.float32))
+        clean = torch.from_numpy(rs.randn(40, t).astype(np.float32))
+        txt = [int(v) for v in rs.randint(1, 29, size=3 + i)]
+        batch.append((feat, txt))
+        paired.append((feat, txt, clean))
+    inputs, targets, pct, tsz, mask = lf._collate_fn(list(batch))
+    pi, po, pm, pt, ppct, ptsz = lf._collate_fn_paired(list(paired))
+    np.savez_compressed(
+        os.path.join(HERE, "ref_collate.npz"),
+        lens=np.asarray(lens), seed=7,
+        inputs=inputs.numpy(), targets=targets.numpy(), pct=pct.numpy(), tsz=tsz.numpy(),
+        mask=mask.numpy(),
+        p_inputs=pi.numpy(), p_outputs=po.numpy(), p_mask=pm.numpy(), p_targets=pt.numpy(),
+        p_pct=ppct.numpy(), p_tsz=ptsz.numpy())
+    sys.path.remove(REF)
+
+
+def make_ref_ctc_sizes():
+    rows = []
+    for tmax in (101, 200, 401, 435, 601, 1234, 3001):
+        t_out = orc.conv_out_frames(tmax)
+        for t in sorted(set([1, 2, 57, 100, 135, tmax // 3, tmax // 2, tmax - 1, tmax])):
+            if t > tmax:
+                continue
+            pct = torch.FloatTensor(1)
+            pct[0] = t / float(tmax)                          # loader_functions.py:57
+            sizes = pct.mul_(int(t_out)).int()                # trainer_AAS.py:165-167
+            rows.append((t, tmax, t_out, int(sizes[0])))
+    np.savez_compressed(os.path.join(HERE, "ref_ctc_sizes.npz"), rows=np.asarray(rows, dtype=np.int64))
+
+
+def make_oracle_cases():
+    cases = {
+        "a": dict(n=3, max_len=4000, ragged=True, seed=123, mask_mode="reim", cmvn="per_bin"),
+        "b": dict(n=2, max_len=2777, ragged=True, seed=5, tonal=True, mask_mode="power", cmvn="global"),
+        "c": dict(n=2, max_len=1600, ragged=False, seed=9, mask_mode="none", cmvn="none"),
+        "d": dict(n=2, max_len=3333, ragged=True, seed=11, tonal=True, mask_mode="reim", cmvn="none"),
+    }
+    for name, c in cases.items():
+        b = _synth.make_batch(c["n"], c["max_len"], seed=c["seed"], ragged=c["ragged"],
+                              tonal=c.get("tonal", False))
+        mr = b["mask_r"] if c["mask_mode"] in ("reim", "power") else None
+        mi = b["mask_i"] if c["mask_mode"] == "reim" else None
+        z, fl = orc.lmfb_forward(b["wave"], b["lengths"], mr, mi, mask_mode=c["mask_mode"],
+                                 cmvn_mode=c["cmvn"])
+        out = dict(z=z, frame_lens=fl, mask_mode=c["mask_mode"], cmvn=c["cmvn"],
+                   n=c["n"], max_len=c["max_len"], ragged=c["ragged"], seed=c["seed"],
+                   tonal=c.get("tonal", False))
+        if c["mask_mode"] != "none":
+            g = orc.lmfb_grads(b["wave"], b["lengths"], mr, mi, b["grad_out"],
+                               mask_mode=c["mask_mode"], cmvn_mode=c["cmvn"])
+            out["grad_mask_r"] = g["grad_mask_r"]
+            if "grad_mask_i" in g:
+                out["grad_mask_i"] = g["grad_mask_i"]
+        np.savez_compressed(os.path.join(HERE, f"oracle_lmfb_{name}.npz"), **out)
+
+
+if __name__ == "__main__":
+    make_ref_glue()
+    make_ref_collate()
+    make_ref_ctc_sizes()
+    make_oracle_cases()
+    for fn in sorted(os.listdir(HERE)):
+        if fn.endswith(".npz"):
+            print(fn, os.path.getsize(os.path.join(HERE, fn)))
