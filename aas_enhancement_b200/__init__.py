@@ -1,0 +1,14 @@
+"""aas_enhancement_b200 -- B200-native LMFB front-end for lifelongeek/AAS_enhancement.
+
+Only the data-parallel hot path lives here: waveform -> STFT(320/160, Hamming) -> mask ->
+40-band mel -> log1p -> CMVN, forward and backward, as hand-written sm_100a kernels behind a
+C ABI (``include/aas_lmfb.h``), plus the host-side mirror of the reference's batch layout.
+"""
+from .lmfb import (LMFB, LMFBFrontEnd, MelPlan, hamming_window, slaney_mel_basis,
+                   N_FFT, HOP, N_BINS)
+from .collate import (collate_wave, collate_wave_paired, ctc_sizes, frame_count,
+                      shard_utterances, get_variable_nograd)
+
+__all__ = ["LMFB", "LMFBFrontEnd", "MelPlan", "hamming_window", "slaney_mel_basis",
+           "collate_wave", "collate_wave_paired", "ctc_sizes", "frame_count",
+           "shard_utterances", "get_variable_nograd", "N_FFT", "HOP", "N_BINS"]

@@ -1,0 +1,66 @@
+"""ctypes binding of libaas_lmfb.so (the C ABI declared in include/aas_lmfb.h).
+
+There is deliberately no fallback: if the CUDA library is missing, loading fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libaas_lmfb.so")
+
+ABI_VERSION = 1
+N_FFT, HOP, N_BINS = 320, 160, 161
+
+MASK_MODES = {"none": 0, "reim": 1, "power": 2}
+CMVN_MODES = {"none": 0 << 2, "per_bin": 1 << 2, "global": 2 << 2}
+
+EXPORTS = ("aas_lmfb_abi_version", "aas_lmfb_strerror", "aas_lmfb_plan_create",
+           "aas_lmfb_plan_destroy", "aas_lmfb_workspace_bytes", "aas_lmfb_forward",
+           "aas_lmfb_backward")
+
+_lock = threading.Lock()
+_lib = None
+
+_vp, _i32, _i64, _u32, _f32 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32,
+                               ctypes.c_float)
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m aas_enhancement_b200.build` "
+                "(the LMFB front-end is CUDA-only; there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.aas_lmfb_abi_version.restype = _i32
+        lib.aas_lmfb_strerror.restype = ctypes.c_char_p
+        lib.aas_lmfb_strerror.argtypes = [_i32]
+        lib.aas_lmfb_plan_create.restype = _vp
+        lib.aas_lmfb_plan_create.argtypes = [_vp, _i32, _i32, ctypes.POINTER(_i32)]
+        lib.aas_lmfb_plan_destroy.restype = None
+        lib.aas_lmfb_plan_destroy.argtypes = [_vp]
+        lib.aas_lmfb_workspace_bytes.restype = ctypes.c_size_t
+        lib.aas_lmfb_workspace_bytes.argtypes = [_i32, _i32, _i32, _u32]
+        lib.aas_lmfb_forward.restype = _i32
+        lib.aas_lmfb_forward.argtypes = [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _i64, _vp,
+                                         _vp, _vp, _i32, _u32, _f32, _vp, _vp]
+        lib.aas_lmfb_backward.restype = _i32
+        lib.aas_lmfb_backward.argtypes = [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _i64, _vp,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, _i32, _u32, _f32, _vp, _vp]
+        if lib.aas_lmfb_abi_version() != ABI_VERSION:
+            raise RuntimeError("libaas_lmfb.so ABI version mismatch; rebuild it")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(load().aas_lmfb_strerror(rc).decode() + f" (code {rc})")

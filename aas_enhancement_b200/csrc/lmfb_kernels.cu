@@ -1,0 +1,402 @@
+// B200 (sm_100a) kernels and C ABI of the LMFB front-end.  See include/aas_lmfb.h for the
+// contract and lmfb_core.cuh for the per-thread algorithm.
+//
+//   K1  lmfb_k1<MASK, BWD>   one warp per tile of 32 frames: stage wave -> 320-pt real FFT
+//                            (lane = frame) -> mask -> banded mel -> log1p   (forward)
+//                            or -> d mask from dE                            (backward)
+//   K2  cmvn_fwd / cmvn_bwd  per-utterance mean/variance normalisation of the (M, T) rows
+//                            and its gradient folded with d log1p.
+//
+// No cuFFT, no library calls, no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include <mutex>
+#include <set>
+#include <utility>
+
+#include "../../include/aas_lmfb.h"
+#include "lmfb_core.cuh"
+#include "mel_band.hpp"
+
+namespace aas_lmfb {
+
+struct K1Args {
+    const float*   wave;
+    const int32_t* lengths;
+    long long      wave_stride;
+    const float*   mask_r;
+    const float*   mask_i;
+    long long      msn, msf;
+    const float*   window;
+    float*         out;        // forward: (N, M, Tmax), receives log1p(E)
+    const float*   dE;         // backward: (N, M, Tmax)
+    float*         gr;
+    float*         gi;
+    int            tmax;
+    int            tiles_per_utt;
+    int            vec_ok;
+};
+
+template <int MASK, bool BWD>
+__global__ void __launch_bounds__(kTile)
+lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
+    extern __shared__ __align__(16) float2 S[];
+    const int lane = threadIdx.x;
+    const int n    = blockIdx.x / a.tiles_per_utt;
+    const int t0   = (blockIdx.x - n * a.tiles_per_utt) * kTile;
+    const int t    = t0 + lane;
+    const int len  = a.lengths[n];
+    int T = len >= 1 ? 1 + len / kHop : 0;
+    T = T < a.tmax ? T : a.tmax;
+    const bool inrow = t < a.tmax;
+    const bool valid = t < T;
+    const int  n_mels = mb.n_mels;
+    const long long som = a.tmax;
+    const long long row_nm = (long long)n * n_mels * som + t;
+
+    if (t0 >= T) {                                  // tile lies entirely in the zero padding
+        if (inrow) {
+            if (!BWD) {
+                for (int m = 0; m < n_mels; ++m) a.out[row_nm + m * som] = 0.0f;
+            } else if (MASK != kMaskNone) {
+                const long long g = (long long)n * a.msn + t;
+                for (int f = 0; f < kBins; ++f) {
+                    a.gr[g + f * a.msf] = 0.0f;
+                    if (MASK == kMaskReim) a.gi[g + f * a.msf] = 0.0f;
+                }
+            }
+        }
+        return;
+    }
+
+    stage_tile(lane, a.wave + (long long)n * a.wave_stride, len, t0, a.window, S, a.vec_ok != 0);
+    __syncwarp();
+    float2* col = S + lane;
+    fft_pass1(col);
+    fft_pass2(col);
+
+    const long long moff = (long long)n * a.msn + t;
+    if (!BWD) {
+        phase3_fwd<MASK>(col, mb, a.mask_r + moff, a.mask_i + moff, a.msf,
+                         a.out + row_nm, som, inrow, valid);
+    } else {
+        phase3_bwd<MASK>(col, mb, a.mask_r + moff, a.mask_i + moff, a.msf,
+                         a.dE + row_nm, som, a.gr + moff, a.gi + moff, a.msf, inrow);
+    }
+}
+
+// ------------------------------------------------------------------------------------ K2
+constexpr int kRowThreads = 128;
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();                       // protect red[] from the previous use
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s += red[i];
+    return s;
+}
+
+__device__ __forceinline__ int frames_of(const int32_t* lengths, int n, int tmax) {
+    const int len = lengths[n];
+    int T = len >= 1 ? 1 + len / kHop : 0;
+    return T < tmax ? T : tmax;
+}
+
+// mode: 1 = per mel bin (grid.x = M rows), 2 = global (grid.x = 1, block walks all M rows)
+__global__ void __launch_bounds__(kRowThreads)
+cmvn_fwd(float* __restrict__ out, float* __restrict__ stats, const int32_t* __restrict__ lengths,
+         int n_mels, int tmax, float eps, int mode) {
+    __shared__ double red[kRowThreads / 32];
+    const int n = blockIdx.y;
+    const int T = frames_of(lengths, n, tmax);
+    const int m0 = mode == 1 ? blockIdx.x : 0;
+    const int m1 = mode == 1 ? m0 + 1 : n_mels;
+    float* base = out + (long long)n * n_mels * tmax;
+    const long long cnt = (long long)(m1 - m0) * T;
+    if (T == 0) {                                   // empty utterance: rows are already zero
+        for (int m = m0 + threadIdx.x; m < m1; m += kRowThreads) {
+            stats[((long long)n * n_mels + m) * 2 + 0] = 0.0f;
+            stats[((long long)n * n_mels + m) * 2 + 1] = 1.0f;
+        }
+        return;
+    }
+    float s = 0.0f;
+    for (int m = m0; m < m1; ++m)
+        for (int t = threadIdx.x; t < T; t += kRowThreads) s += base[(long long)m * tmax + t];
+    const double mean_d = block_sum((double)s, red) / (double)cnt;
+    const float mean = (float)mean_d;
+    float v = 0.0f;
+    for (int m = m0; m < m1; ++m)
+        for (int t = threadIdx.x; t < T; t += kRowThreads) {
+            const float d = base[(long long)m * tmax + t] - mean;
+            v = fmaf(d, d, v);
+        }
+    const double var = block_sum((double)v, red) / (double)(cnt - 1);
+    const float rstd = 1.0f / ((float)sqrt(var) + eps);
+    for (int m = m0; m < m1; ++m) {
+        for (int t = threadIdx.x; t < T; t += kRowThreads) {
+            const long long i = (long long)m * tmax + t;
+            base[i] = (base[i] - mean) * rstd;
+        }
+        if (threadIdx.x == 0) {
+            stats[((long long)n * n_mels + m) * 2 + 0] = mean;
+            stats[((long long)n * n_mels + m) * 2 + 1] = rstd;
+        }
+    }
+}
+
+// dE = dY / (1 + E) with dY the CMVN gradient; mode 0 = no CMVN.
+__global__ void __launch_bounds__(kRowThreads)
+cmvn_bwd(const float* __restrict__ z, const float* __restrict__ stats,
+         const float* __restrict__ grad_out, float* __restrict__ dE,
+         const int32_t* __restrict__ lengths, int n_mels, int tmax, float eps, int mode) {
+    __shared__ double red[kRowThreads / 32];
+    const int n = blockIdx.y;
+    const int T = frames_of(lengths, n, tmax);
+    const int m0 = mode == 2 ? 0 : blockIdx.x;
+    const int m1 = mode == 2 ? n_mels : m0 + 1;
+    const long long nb = (long long)n * n_mels * tmax;
+    const float* zb = z + nb;
+    const float* gb = grad_out + nb;
+    float* eb = dE + nb;
+    float c1 = 0.0f, k = 0.0f, mean = 0.0f, rstd = 1.0f;
+    if (mode != 0) {
+        const long long cnt = (long long)(m1 - m0) * T;
+        float sg = 0.0f, sgz = 0.0f;
+        for (int m = m0; m < m1; ++m)
+            for (int t = threadIdx.x; t < T; t += kRowThreads) {
+                const long long i = (long long)m * tmax + t;
+                const float g = gb[i];
+                sg += g;
+                sgz = fmaf(g, zb[i], sgz);
+            }
+        const double sg_d = block_sum((double)sg, red);
+        const double sgz_d = block_sum((double)sgz, red);
+        mean = stats[((long long)n * n_mels + m0) * 2 + 0];
+        rstd = stats[((long long)n * n_mels + m0) * 2 + 1];
+        const double sigma = 1.0 / (double)rstd - (double)eps;
+        c1 = (float)(sg_d / (double)cnt);
+        k = (float)(sgz_d / ((double)(cnt - 1) * sigma));
+    }
+    for (int m = m0; m < m1; ++m) {
+        for (int t = threadIdx.x; t < tmax; t += kRowThreads) {
+            const long long i = (long long)m * tmax + t;
+            float r = 0.0f;
+            if (t < T) {
+                const float g = gb[i], zz = zb[i];
+                if (mode != 0) {
+                    const float dy = fmaf(rstd, g - c1, -zz * k);
+                    const float y = fmaf(zz, 1.0f / rstd, mean);
+                    r = dy * expf(-y);
+                } else {
+                    r = g * expf(-zz);
+                }
+            }
+            eb[i] = r;
+        }
+    }
+}
+
+}  // namespace aas_lmfb
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+using namespace aas_lmfb;
+
+struct aas_lmfb_plan {
+    MelBand band;
+    int     n_mels;
+};
+
+extern "C" int aas_lmfb_abi_version(void) { return AAS_LMFB_ABI_VERSION; }
+
+extern "C" const char* aas_lmfb_strerror(int code) {
+    switch (code) {
+        case AAS_LMFB_OK:      return "ok";
+        case AAS_LMFB_E_NULL:  return "aas_lmfb: required pointer is NULL";
+        case AAS_LMFB_E_ALIGN: return "aas_lmfb: buffer is not sufficiently aligned";
+        case AAS_LMFB_E_SHAPE: return "aas_lmfb: unsupported shape (n_bins must be 161, 1 <= n_mels <= 128, n >= 0, tmax >= 1)";
+        case AAS_LMFB_E_FLAGS: return "aas_lmfb: invalid mask/cmvn flags";
+        case AAS_LMFB_E_MEL:   return "aas_lmfb: mel basis is not banded (each bin may feed at most two adjacent, frequency-ordered filters)";
+        case AAS_LMFB_E_NOMEM: return "aas_lmfb: host allocation failed";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "aas_lmfb: unknown error";
+}
+
+extern "C" aas_lmfb_plan* aas_lmfb_plan_create(const float* mel, int n_mels, int n_bins, int* status) {
+    int st = AAS_LMFB_OK;
+    aas_lmfb_plan* p = nullptr;
+    do {
+        if (!mel) { st = AAS_LMFB_E_NULL; break; }
+        if (n_bins != kBins || n_mels < 1 || n_mels > kMaxMels) { st = AAS_LMFB_E_SHAPE; break; }
+        p = new (std::nothrow) aas_lmfb_plan;
+        if (!p) { st = AAS_LMFB_E_NOMEM; break; }
+        memset(p, 0, sizeof(*p));
+        p->n_mels = n_mels;
+        if (build_mel_band(mel, n_mels, &p->band) != 0) st = AAS_LMFB_E_MEL;
+    } while (0);
+    if (st != AAS_LMFB_OK && p) { delete p; p = nullptr; }
+    if (status) *status = st;
+    return p;
+}
+
+extern "C" void aas_lmfb_plan_destroy(aas_lmfb_plan* plan) { delete plan; }
+
+extern "C" size_t aas_lmfb_workspace_bytes(int n, int n_mels, int tmax, uint32_t /*flags*/) {
+    if (n <= 0 || n_mels <= 0 || tmax <= 0) return 0;
+    return (size_t)n * (size_t)n_mels * (size_t)tmax * sizeof(float);
+}
+
+namespace {
+
+typedef void (*k1_fn)(const K1Args, const MelBand);
+
+k1_fn pick_k1(unsigned mask, bool bwd) {
+    switch (mask) {
+        case AAS_LMFB_MASK_NONE:  return bwd ? nullptr : (k1_fn)lmfb_k1<kMaskNone, false>;
+        case AAS_LMFB_MASK_REIM:  return bwd ? (k1_fn)lmfb_k1<kMaskReim, true>  : (k1_fn)lmfb_k1<kMaskReim, false>;
+        case AAS_LMFB_MASK_POWER: return bwd ? (k1_fn)lmfb_k1<kMaskPower, true> : (k1_fn)lmfb_k1<kMaskPower, false>;
+    }
+    return nullptr;
+}
+
+// cudaFuncSetAttribute is per (function, device); do it once each so that launches inside
+// a CUDA-graph capture are pure stream work.
+int ensure_attrs(k1_fn fn) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int> > done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lock(mu);
+    const std::pair<const void*, int> key((const void*)fn, dev);
+    if (done.count(key)) return 0;
+    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kScratchBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return (int)e;
+    done.insert(key);
+    return 0;
+}
+
+int launch_k1(k1_fn fn, const K1Args& a, const MelBand& mb, int n, cudaStream_t stream) {
+    const int rc = ensure_attrs(fn);
+    if (rc) return rc;
+    const long long blocks = (long long)n * a.tiles_per_utt;
+    if (blocks <= 0) return AAS_LMFB_OK;
+    if (blocks > 0x7fffffffLL) return AAS_LMFB_E_SHAPE;
+    fn<<<(unsigned)blocks, kTile, kScratchBytes, stream>>>(a, mb);
+    return (int)cudaPeekAtLastError();
+}
+
+int check_common(const aas_lmfb_plan* plan, const float* wave, const int32_t* lengths, int n,
+                 const float* mask_r, const float* mask_i, const float* window, int tmax,
+                 uint32_t flags) {
+    if (!plan || !window || (n > 0 && (!wave || !lengths))) return AAS_LMFB_E_NULL;
+    if (n < 0 || tmax < 1) return AAS_LMFB_E_SHAPE;
+    const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
+    if (mask > 2u || cm > 2u || (flags >> 4)) return AAS_LMFB_E_FLAGS;
+    if (mask != AAS_LMFB_MASK_NONE && !mask_r) return AAS_LMFB_E_NULL;
+    if (mask == AAS_LMFB_MASK_REIM && !mask_i) return AAS_LMFB_E_NULL;
+    const uintptr_t al = (uintptr_t)wave | (uintptr_t)mask_r | (uintptr_t)mask_i | (uintptr_t)window;
+    if (al & 3u) return AAS_LMFB_E_ALIGN;
+    return AAS_LMFB_OK;
+}
+
+void rec(void* const* prof, int i, cudaStream_t s) {
+    if (prof && prof[i]) cudaEventRecord((cudaEvent_t)prof[i], s);
+}
+
+}  // namespace
+
+extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
+                                const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                                const float* mask_r, const float* mask_i,
+                                int64_t mask_stride_n, int64_t mask_stride_f,
+                                const float* window,
+                                float* out, float* stats, int tmax,
+                                uint32_t flags, float eps, void* cuda_stream, void* const* prof) {
+    int rc = check_common(plan, wave, lengths, n, mask_r, mask_i, window, tmax, flags);
+    if (rc) return rc;
+    if (n == 0) return AAS_LMFB_OK;
+    const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
+    if (!out || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
+    if (((uintptr_t)out | (uintptr_t)stats) & 3u) return AAS_LMFB_E_ALIGN;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+
+    K1Args a;
+    memset(&a, 0, sizeof(a));
+    a.wave = wave; a.lengths = lengths; a.wave_stride = wave_stride;
+    a.mask_r = mask_r; a.mask_i = mask_i; a.msn = mask_stride_n; a.msf = mask_stride_f;
+    a.window = window; a.out = out; a.tmax = tmax;
+    a.tiles_per_utt = (tmax + kTile - 1) / kTile;
+    a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
+
+    rec(prof, 0, stream);
+    rc = launch_k1(pick_k1(mask, false), a, plan->band, n, stream);
+    rec(prof, 1, stream);
+    if (rc) return rc;
+    rec(prof, 2, stream);
+    if (cm != 0) {
+        dim3 grid(cm == 1 ? plan->n_mels : 1, n);
+        cmvn_fwd<<<grid, kRowThreads, 0, stream>>>(out, stats, lengths, plan->n_mels, tmax, eps, (int)cm);
+        rc = (int)cudaPeekAtLastError();
+    }
+    rec(prof, 3, stream);
+    return rc;
+}
+
+extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
+                                 const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                                 const float* mask_r, const float* mask_i,
+                                 int64_t mask_stride_n, int64_t mask_stride_f,
+                                 const float* window,
+                                 const float* out, const float* stats, const float* grad_out,
+                                 float* grad_mask_r, float* grad_mask_i,
+                                 void* workspace, int tmax,
+                                 uint32_t flags, float eps, void* cuda_stream, void* const* prof) {
+    int rc = check_common(plan, wave, lengths, n, mask_r, mask_i, window, tmax, flags);
+    if (rc) return rc;
+    if (n == 0) return AAS_LMFB_OK;
+    const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
+    if (mask == AAS_LMFB_MASK_NONE) return AAS_LMFB_E_FLAGS;        // nothing to differentiate into
+    if (!out || !grad_out || !workspace || !grad_mask_r || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
+    if (mask == AAS_LMFB_MASK_REIM && !grad_mask_i) return AAS_LMFB_E_NULL;
+    if (((uintptr_t)out | (uintptr_t)grad_out | (uintptr_t)workspace | (uintptr_t)grad_mask_r |
+         (uintptr_t)grad_mask_i | (uintptr_t)stats) & 3u) return AAS_LMFB_E_ALIGN;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    float* dE = (float*)workspace;
+
+    rec(prof, 2, stream);
+    {
+        dim3 grid(cm == 2 ? 1 : plan->n_mels, n);
+        cmvn_bwd<<<grid, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm);
+        rc = (int)cudaPeekAtLastError();
+    }
+    rec(prof, 3, stream);
+    if (rc) return rc;
+
+    K1Args a;
+    memset(&a, 0, sizeof(a));
+    a.wave = wave; a.lengths = lengths; a.wave_stride = wave_stride;
+    a.mask_r = mask_r; a.mask_i = mask_i; a.msn = mask_stride_n; a.msf = mask_stride_f;
+    a.window = window; a.dE = dE; a.gr = grad_mask_r; a.gi = grad_mask_i; a.tmax = tmax;
+    a.tiles_per_utt = (tmax + kTile - 1) / kTile;
+    a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
+
+    rec(prof, 0, stream);
+    rc = launch_k1(pick_k1(mask, true), a, plan->band, n, stream);
+    rec(prof, 1, stream);
+    return rc;
+}

@@ -1,0 +1,239 @@
+"""Drop-in differentiable LMFB front-end (host side of the C ABI).
+
+Mirrors the operator surface the reference exposes for this path:
+
+* ``BRNNmultiCH(..., mel_basis)`` keeps the mel basis as a module buffer and its ``forward``
+  ends in mask -> power -> mel -> log1p on ``(N, F, T)`` tensors
+  (Speech_enhancement_by_AAS/model.py:148, :167, :186-198)  ->  :class:`LMFBFrontEnd`.
+* trainers consume ``(N, 40, T)`` fp32, channel-first, time-last
+  (trainer_AAS.py:136-142, loader_functions.py:56)           ->  the output layout here.
+* front-end parameters 16 kHz / 20 ms Hamming / 10 ms stride / 40 mels
+  (AM_training/train.py:39-42, :56)                           ->  defaults below.
+
+All arithmetic runs in the hand-written sm_100a kernels behind ``libaas_lmfb.so``; torch is
+used for device memory and streams only.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+N_FFT, HOP, N_BINS = _lib.N_FFT, _lib.HOP, _lib.N_BINS
+SAMPLE_RATE = 16000
+
+
+# --------------------------------------------------------------------------- parameters
+def hamming_window(n: int = N_FFT, sym: bool = True) -> np.ndarray:
+    """'hamming' is pinned by AM_training/train.py:42; symmetric is what deepspeech.pytorch
+    hands to librosa (scipy.signal.hamming).  float64."""
+    k = np.arange(n, dtype=np.float64)
+    return 0.54 - 0.46 * np.cos(2.0 * np.pi * k / ((n - 1) if sym else n))
+
+
+def slaney_mel_basis(sr: int = SAMPLE_RATE, n_fft: int = N_FFT, n_mels: int = 40,
+                     fmin: float = 0.0, fmax: float | None = None) -> np.ndarray:
+    """Default mel basis: Slaney scale, area-normalised triangles (librosa.filters.mel
+    defaults), (n_mels, n_fft//2+1) float64.  The reference takes the basis as a constructor
+    argument (model.py:148); pass your own to :class:`LMFBFrontEnd` to override."""
+    fmax = sr / 2.0 if fmax is None else fmax
+    f_sp, min_log_hz = 200.0 / 3.0, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, math.log(6.4) / 27.0
+
+    def hz2mel(f):
+        return min_log_mel + math.log(f / min_log_hz) / logstep if f >= min_log_hz else f / f_sp
+
+    def mel2hz(m):
+        return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+    n_bins = n_fft // 2 + 1
+    freqs = np.linspace(0.0, sr / 2.0, n_bins)
+    hz = mel2hz(np.linspace(hz2mel(fmin), hz2mel(fmax), n_mels + 2))
+    fdiff = np.diff(hz)
+    ramps = hz[:, None] - freqs[None, :]
+    w = np.zeros((n_mels, n_bins))
+    for i in range(n_mels):
+        w[i] = np.maximum(0.0, np.minimum(-ramps[i] / fdiff[i], ramps[i + 2] / fdiff[i + 1]))
+    return w * (2.0 / (hz[2:] - hz[:-2]))[:, None]
+
+
+class MelPlan:
+    """Host-side plan for one mel basis (wraps ``aas_lmfb_plan_create``)."""
+
+    def __init__(self, mel_basis):
+        mel = np.ascontiguousarray(
+            mel_basis.detach().cpu().numpy() if isinstance(mel_basis, torch.Tensor) else mel_basis,
+            dtype=np.float32)
+        if mel.ndim != 2:
+            raise ValueError("mel_basis must be (n_mels, 161)")
+        lib = _lib.load()
+        status = ctypes.c_int(0)
+        self._lib = lib
+        self.n_mels = int(mel.shape[0])
+        self.handle = lib.aas_lmfb_plan_create(mel.ctypes.data, mel.shape[0], mel.shape[1],
+                                               ctypes.byref(status))
+        if not self.handle:
+            _lib.check(status.value)
+            raise RuntimeError("aas_lmfb_plan_create failed")
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self._lib.aas_lmfb_plan_destroy(h)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _check_f32_cuda(name, t, dev):
+    if t.dtype != torch.float32 or t.device != dev:
+        raise TypeError(f"{name} must be a float32 tensor on {dev}")
+
+
+class LMFB(torch.autograd.Function):
+    """``Z, frame_lens = LMFB.apply(wave, lengths, mask_r, mask_i, plan, window, mask_mode,
+    cmvn_mode, eps, tmax)``
+
+    wave (N, Lmax) f32 cuda zero-padded; lengths (N,) int32 cuda (samples); masks
+    (N, 161, Tmax) f32 or None; plan a :class:`MelPlan`; window (320,) f32 cuda.
+    Returns Z (N, M, Tmax) f32 with frames ``t >= T_i`` exactly zero, and frame_lens (N,)
+    int32 (``T_i = 1 + L_i // 160``).  Gradients flow to mask_r / mask_i.
+    """
+
+    @staticmethod
+    def forward(ctx, wave, lengths, mask_r, mask_i, plan, window, mask_mode="reim",
+                cmvn_mode="per_bin", eps=0.0, tmax=None):
+        if not wave.is_cuda:
+            raise RuntimeError("LMFB is CUDA-only (sm_100a); there is no CPU fallback")
+        dev = wave.device
+        lib = _lib.load()
+        if mask_mode not in _lib.MASK_MODES or cmvn_mode not in _lib.CMVN_MODES:
+            raise ValueError(f"bad mask_mode/cmvn_mode: {mask_mode!r}/{cmvn_mode!r}")
+        _check_f32_cuda("wave", wave, dev)
+        _check_f32_cuda("window", window, dev)
+        if wave.dim() != 2 or wave.stride(1) != 1:
+            raise ValueError("wave must be (N, Lmax) with unit sample stride")
+        if lengths.dtype != torch.int32 or lengths.device != dev:
+            lengths = lengths.to(device=dev, dtype=torch.int32)
+        lengths = lengths.contiguous()
+        window = window.contiguous()
+        n = wave.shape[0]
+        use_r = mask_mode in ("reim", "power")
+        use_i = mask_mode == "reim"
+        if (use_r and mask_r is None) or (use_i and mask_i is None):
+            raise ValueError(f"mask_mode={mask_mode!r} needs its mask tensor(s)")
+        mask_r = mask_r if use_r else None
+        mask_i = mask_i if use_i else None
+        msn = msf = 0
+        if use_r:
+            _check_f32_cuda("mask_r", mask_r, dev)
+            if mask_r.dim() != 3 or mask_r.shape[0] != n or mask_r.shape[1] != N_BINS:
+                raise ValueError("mask_r must be (N, 161, Tmax)")
+            if mask_r.stride(2) != 1:
+                mask_r = mask_r.contiguous()
+            if tmax is None:
+                tmax = mask_r.shape[2]
+            elif mask_r.shape[2] != tmax:
+                raise ValueError("mask_r.shape[2] != tmax")
+            msn, msf = mask_r.stride(0), mask_r.stride(1)
+        if use_i:
+            _check_f32_cuda("mask_i", mask_i, dev)
+            if mask_i.shape != mask_r.shape:
+                raise ValueError("mask_i must have the shape of mask_r")
+            if mask_i.stride() != mask_r.stride():
+                mask_i = mask_i.contiguous()
+                mask_r = mask_r.contiguous()
+                msn, msf = mask_r.stride(0), mask_r.stride(1)
+        if tmax is None:
+            tmax = 1 + wave.shape[1] // HOP
+        tmax = int(tmax)
+        flags = _lib.MASK_MODES[mask_mode] | _lib.CMVN_MODES[cmvn_mode]
+        out = torch.empty((n, plan.n_mels, tmax), dtype=torch.float32, device=dev)
+        stats = torch.empty((n, plan.n_mels, 2), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.aas_lmfb_forward(plan.handle, wave.data_ptr(), lengths.data_ptr(), n,
+                                      wave.stride(0), _ptr(mask_r), _ptr(mask_i), msn, msf,
+                                      window.data_ptr(), out.data_ptr(), stats.data_ptr(), tmax,
+                                      flags, float(eps), stream, None)
+        _lib.check(rc)
+        frame_lens = torch.clamp(1 + torch.div(lengths, HOP, rounding_mode="floor"), max=tmax)
+        frame_lens = torch.where(lengths >= 1, frame_lens, torch.zeros_like(frame_lens)).to(torch.int32)
+        ctx.plan, ctx.flags, ctx.eps, ctx.tmax = plan, flags, float(eps), tmax
+        ctx.strides = (msn, msf)
+        ctx.save_for_backward(wave, lengths, mask_r, mask_i, window, out, stats)
+        ctx.mark_non_differentiable(frame_lens)
+        return out, frame_lens
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_lens):
+        wave, lengths, mask_r, mask_i, window, out, stats = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("gradient w.r.t. the waveform is not implemented")
+        if mask_r is None:
+            return (None,) * 10
+        lib = _lib.load()
+        dev = wave.device
+        n, plan, tmax = wave.shape[0], ctx.plan, ctx.tmax
+        grad_out = grad_out.contiguous()
+        if grad_out.dtype != torch.float32:
+            grad_out = grad_out.float()
+        gr = torch.empty_strided(mask_r.shape, mask_r.stride(), dtype=torch.float32, device=dev)
+        gi = torch.empty_strided(mask_i.shape, mask_i.stride(), dtype=torch.float32, device=dev) \
+            if mask_i is not None else None
+        ws_bytes = lib.aas_lmfb_workspace_bytes(n, plan.n_mels, tmax, ctx.flags)
+        ws = torch.empty((max(ws_bytes, 4) + 3) // 4, dtype=torch.float32, device=dev)
+        msn, msf = ctx.strides
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.aas_lmfb_backward(plan.handle, wave.data_ptr(), lengths.data_ptr(), n,
+                                       wave.stride(0), _ptr(mask_r), _ptr(mask_i), msn, msf,
+                                       window.data_ptr(), out.data_ptr(), stats.data_ptr(),
+                                       grad_out.data_ptr(), gr.data_ptr(), _ptr(gi), ws.data_ptr(),
+                                       tmax, ctx.flags, ctx.eps, stream, None)
+        _lib.check(rc)
+        return None, None, gr, gi, None, None, None, None, None, None
+
+
+class LMFBFrontEnd(torch.nn.Module):
+    """``nn.Module`` face of :class:`LMFB`: holds ``mel_basis`` and ``window`` as buffers the
+    way ``BRNNmultiCH`` holds ``mel_basis`` (model.py:167).
+
+    ``forward(wave, lengths, mask_r=None, mask_i=None)`` -> ``(features (N, n_mels, Tmax),
+    frame_lens)``.  With ``mask_mode='reim'`` it is the tail of ``BRNNmultiCH.forward``
+    (model.py:186-198) fused with the STFT in front of it and the CMVN behind it.
+    """
+
+    def __init__(self, mel_basis=None, window=None, mask_mode="reim", cmvn_mode="per_bin",
+                 eps=0.0, n_mels=40, window_sym=True):
+        super().__init__()
+        mel = slaney_mel_basis(n_mels=n_mels) if mel_basis is None else mel_basis
+        mel = torch.as_tensor(np.asarray(mel.detach().cpu() if isinstance(mel, torch.Tensor) else mel),
+                              dtype=torch.float32)
+        win = hamming_window(N_FFT, window_sym) if window is None else window
+        win = torch.as_tensor(np.asarray(win.detach().cpu() if isinstance(win, torch.Tensor) else win),
+                              dtype=torch.float32)
+        if win.numel() != N_FFT:
+            raise ValueError("window must have 320 samples (AM_training/train.py:39-40)")
+        self.register_buffer("mel_basis", mel)
+        self.register_buffer("window", win)
+        self.mask_mode, self.cmvn_mode, self.eps = mask_mode, cmvn_mode, float(eps)
+        self.plan = MelPlan(mel)
+
+    @property
+    def audio_conf(self):
+        """The front-end configuration, to be stored next to checkpoints (cf. the unused
+        ``audio_conf`` slot of DeepSpeech.serialize, model.py:267, :432-433)."""
+        return dict(sample_rate=SAMPLE_RATE, window_size=N_FFT / SAMPLE_RATE,
+                    window_stride=HOP / SAMPLE_RATE, window="hamming",
+                    n_mels=int(self.mel_basis.shape[0]), mask_mode=self.mask_mode,
+                    cmvn_mode=self.cmvn_mode, eps=self.eps)
+
+    def forward(self, wave, lengths, mask_r=None, mask_i=None, tmax=None):
+        return LMFB.apply(wave, lengths, mask_r, mask_i, self.plan, self.window,
+                          self.mask_mode, self.cmvn_mode, self.eps, tmax)

@@ -1,0 +1,486 @@
+#!/usr/bin/env python3
+"""LMFB front-end benchmark (BASELINE.json metric: LMFB fwd+bwd audio-seconds / second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path (forward + backward into both masks, 'reim' mask mode,
+per-bin CMVN) over one synthetic batch.  Default workload = BASELINE.json configs[1]: the
+CHiME-4-shaped batch, 30 utterances x 6 s at 16 kHz (18,030 frames).  Under torchrun each rank
+owns its own batch ring (utterance-sharded, weak scaling, no data-path collective).
+
+Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM (CUDA-graph
+replay of the C-ABI calls, CUDA-event timed, max over ranks); `e2e` goes through the public
+autograd API with pinned HOST buffers and the H2D/D2H copies inside the timed region;
+`roofline` is the dominant kernel (K1 backward) timed with CUDA events recorded by the library
+around that kernel; `cpu_baseline` is the reference's CPU path (oracle/lmfb_torch_cpu.py)
+timed on this host.  `--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+HOP = 160
+SR = 16000
+B_FWD, B_BWD = 2088, 3536             # algorithmic bytes / frame, 'reim' 
+B_K1_BWD = 640 + 1288 + 1288          # K1-backward's own compulsory bytes: wave + masks + grad masks
+B_K1_FWD = 640 + 1288 + 160
+
+WORKLOADS = {
+    # name: (utterances, seconds)
+    "chime4_30x6s": (30, 6.0),        # BASELINE.json configs[1]
+    "cfg0_8x4s": (8, 4.0),            # configs[0]
+    "sweep_512x30s": (512, 30.0),     # largest single-GPU point of configs[4]
+    "sweep_256x10s": (256, 10.0),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Polls NVML for SM clock / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._in_region = False
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((self._in_region, mhz))
+                if self._in_region:
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
+
+    def region(self, on):
+        self._in_region = on
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        inside = [m for r, m in self.samples if r] or [m for _, m in self.samples]
+        return {"sm_mhz": statistics.median(inside) if inside else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples_in_region": sum(1 for r, _ in self.samples if r)}
+
+
+# ------------------------------------------------------------------------------- ours
+class Slot:
+    """One resident synthetic batch + its output buffers (device)."""
+
+    def __init__(self, n, samples, tmax, n_mels, gen, dev):
+        self.wave = (0.1 * torch.randn(n, samples, generator=gen, device=dev)).clamp_(-1, 1)
+        self.lengths = torch.full((n,), samples, dtype=torch.int32, device=dev)
+        self.mr = torch.rand(n, 161, tmax, generator=gen, device=dev)
+        self.mi = torch.rand(n, 161, tmax, generator=gen, device=dev)
+        self.gout = torch.randn(n, n_mels, tmax, generator=gen, device=dev)
+        self.out = torch.empty(n, n_mels, tmax, device=dev)
+        self.stats = torch.empty(n, n_mels, 2, device=dev)
+        self.gr = torch.empty_like(self.mr)
+        self.gi = torch.empty_like(self.mi)
+        self.ws = torch.empty(n, n_mels, tmax, device=dev)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from aas_enhancement_b200 import LMFBFrontEnd, _lib, build as _build
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the LMFB path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load()
+
+    n, secs = WORKLOADS[args.workload]
+    samples = int(secs * SR)
+    tmax = 1 + samples // HOP
+    frames = n * tmax
+    audio_s = n * secs
+    fe = LMFBFrontEnd(mask_mode="reim", cmvn_mode="per_bin").to(dev)
+    plan, window, n_mels = fe.plan, fe.window, fe.plan.n_mels
+    flags = _lib.MASK_MODES["reim"] | _lib.CMVN_MODES["per_bin"]
+
+    slot_bytes = (n * samples + 4 * n * 161 * tmax + 3 * n * n_mels * tmax) * 4
+    ring = max(2, min(16, -(-400_000_000 // slot_bytes)))          # >= ~400 MB > 126 MB L2
+    if slot_bytes * ring > 60e9:
+        ring = max(1, int(60e9 // slot_bytes))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(123 + rank)                                      # config.py:62 default seed
+    slots = [Slot(n, samples, tmax, n_mels, gen, dev) for _ in range(ring)]
+
+    def fwd(s, prof=None):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.aas_lmfb_forward(plan.handle, s.wave.data_ptr(), s.lengths.data_ptr(), n,
+                                        s.wave.stride(0), s.mr.data_ptr(), s.mi.data_ptr(),
+                                        s.mr.stride(0), s.mr.stride(1), window.data_ptr(),
+                                        s.out.data_ptr(), s.stats.data_ptr(), tmax, flags, 0.0, st, prof))
+
+    def bwd(s, prof=None):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.aas_lmfb_backward(plan.handle, s.wave.data_ptr(), s.lengths.data_ptr(), n,
+                                         s.wave.stride(0), s.mr.data_ptr(), s.mi.data_ptr(),
+                                         s.mr.stride(0), s.mr.stride(1), window.data_ptr(),
+                                         s.out.data_ptr(), s.stats.data_ptr(), s.gout.data_ptr(),
+                                         s.gr.data_ptr(), s.gi.data_ptr(), s.ws.data_ptr(), tmax,
+                                         flags, 0.0, st, prof))
+
+    def step(i):
+        s = slots[i % ring]
+        fwd(s)
+        bwd(s)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up (also sets function attributes before any capture)
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+
+    # ---- capture: one graph of `ring` consecutive steps (+ a remainder graph)
+    side = torch.cuda.Stream()
+    graphs = {}
+
+    def capture(count):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for i in range(count):
+                step(i)
+        return g
+
+    reps, rem = divmod(args.steps, ring)
+    if reps:
+        graphs["full"] = capture(ring)
+    if rem:
+        graphs["rem"] = capture(rem)
+    for g in graphs.values():                                       # warm the graphs themselves
+        g.replay()
+    sync_all()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    sampler.region(True)
+    e0.record()
+    for _ in range(reps):
+        graphs["full"].replay()
+    if rem:
+        graphs["rem"].replay()
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.region(False)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop()
+
+    # ---- dominant kernel (K1 backward) + the other three, CUDA events recorded by the library
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+    k_ms = {"k1_fwd": [], "k2_fwd": [], "k2_bwd": [], "k1_bwd": []}
+    for e in ev:
+        e.record()                                                  # materialise the handles
+    torch.cuda.synchronize()
+    prof_f = ctypes_array([e.cuda_event for e in ev[:4]])
+    prof_b = ctypes_array([e.cuda_event for e in ev[4:]])
+    n_prof = min(max(args.steps, 10), 200)
+    for i in range(n_prof):
+        s = slots[i % ring]
+        fwd(s, prof_f)
+        bwd(s, prof_b)
+        torch.cuda.synchronize()
+        k_ms["k1_fwd"].append(ev[0].elapsed_time(ev[1]))
+        k_ms["k2_fwd"].append(ev[2].elapsed_time(ev[3]))
+        k_ms["k1_bwd"].append(ev[4].elapsed_time(ev[5]))
+        k_ms["k2_bwd"].append(ev[6].elapsed_time(ev[7]))
+    k_avg = {k: sum(v) / len(v) for k, v in k_ms.items()}
+
+    # ---- e2e: public autograd API, pinned host buffers, copies inside the timed region
+    e2e = measure_e2e(fe, n, samples, tmax, n_mels, audio_s, dev, min(max(args.steps, 5), 40), world)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    ms_per_step = ms / args.steps
+    value = world * audio_s * args.steps / (ms / 1e3)
+    k1b = k_avg["k1_bwd"] / 1e3
+    achieved = frames * B_K1_BWD / k1b / 1e9
+    step_gbs = frames * (B_FWD + B_BWD) / (ms_per_step / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("k1_bwd_dram_bytes")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "LMFB fwd+bwd audio-seconds per second",
+        "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "utterances_per_gpu": n, "seconds": secs,
+                   "frames_per_step_per_gpu": frames, "mask_mode": "reim", "cmvn": "per_bin",
+                   "sharding": f"utterance-sharded x{world}, no collective",
+                   "l2": f"inputs larger than L2: ring of {ring} distinct resident batches "
+                         f"({ring * slot_bytes / 1e6:.0f} MB) cycled step by step",
+                   "launch": "CUDA graph replay of the C-ABI forward+backward calls"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": 4 * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "lmfb_k1<reim,bwd>", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": frames * B_K1_BWD,
+                     "avg_launch_ms": k_avg["k1_bwd"],
+                     "kernels_ms": k_avg,
+                     "k1_fwd_frac": frames * B_K1_FWD / (k_avg["k1_fwd"] / 1e3) / 1e9 / peak,
+                     "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak / world},
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(n, samples, budget_s=12.0)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ctypes_array(handles):
+    import ctypes
+    arr = (ctypes.c_void_p * len(handles))(*[ctypes.c_void_p(int(h)) for h in handles])
+    return arr
+
+
+def measure_e2e(fe, n, samples, tmax, n_mels, audio_s, dev, steps, world):
+    import torch.distributed as dist
+    gen = torch.Generator()
+    gen.manual_seed(123)
+    h_wave = (0.1 * torch.randn(n, samples, generator=gen)).clamp_(-1, 1).pin_memory()
+    h_len = torch.full((n,), samples, dtype=torch.int32).pin_memory()
+    h_mr = torch.rand(n, 161, tmax, generator=gen).pin_memory()
+    h_mi = torch.rand(n, 161, tmax, generator=gen).pin_memory()
+    h_g = torch.randn(n, n_mels, tmax, generator=gen).pin_memory()
+    h_z = torch.empty(n, n_mels, tmax).pin_memory()
+    h_gr = torch.empty(n, 161, tmax).pin_memory()
+    h_gi = torch.empty(n, 161, tmax).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in (h_wave, h_len, h_mr, h_mi, h_g))
+    d2h = sum(t.numel() * t.element_size() for t in (h_z, h_gr, h_gi))
+
+    def one():
+        wave = h_wave.to(dev, non_blocking=True)
+        lens = h_len.to(dev, non_blocking=True)
+        mr = h_mr.to(dev, non_blocking=True).requires_grad_(True)
+        mi = h_mi.to(dev, non_blocking=True).requires_grad_(True)
+        g = h_g.to(dev, non_blocking=True)
+        z, _ = fe(wave, lens, mr, mi)
+        z.backward(g)
+        h_z.copy_(z.detach(), non_blocking=True)
+        h_gr.copy_(mr.grad, non_blocking=True)
+        h_gi.copy_(mi.grad, non_blocking=True)
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": world * audio_s * steps / (ms / 1e3), "unit": "audio-s/s",
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+            "api": "LMFBFrontEnd.forward + autograd backward; pinned host buffers in, features "
+                   "and both mask gradients copied back to pinned host"}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def _cpu_inputs(n, samples, seed=123):
+    from oracle import lmfb_oracle as orc
+    gen = torch.Generator()
+    gen.manual_seed(seed)
+    tmax = 1 + samples // HOP
+    wave = (0.1 * torch.randn(n, samples, generator=gen)).clamp_(-1, 1)
+    mr = torch.rand(n, 161, tmax, generator=gen)
+    mi = torch.rand(n, 161, tmax, generator=gen)
+    g = torch.randn(n, 40, tmax, generator=gen)
+    mel = torch.from_numpy(orc.mel_filterbank().astype(np.float32))
+    win = torch.from_numpy(orc.hamming_window().astype(np.float32))
+    return wave, mr, mi, g, mel, win
+
+
+def _cpu_step_fn(n, samples):
+    from oracle import lmfb_torch_cpu as cpu
+    wave, mr, mi, g, mel, win = _cpu_inputs(n, samples)
+
+    def step():
+        cpu.fwd_bwd_batched(wave, mr, mi, g, mel, win, "per_bin", "reim")
+    return step
+
+
+def cpu_baseline(n, samples, budget_s=12.0):
+    """The oracle-side torch CPU path (kind 'port') on a bounded sample of the workload."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_s = min(n, 30)
+    step = _cpu_step_fn(n_s, samples)
+    for _ in range(2):
+        step()
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 200):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": n_s * samples / SR / med, "unit": "audio-s/s", "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"{len(times)} batched fwd+bwd passes over {n_s} x {samples / SR:g} s "
+                      f"(oracle/lmfb_torch_cpu.py: torch.stft + model.py:191-198 ops + CMVN + autograd), "
+                      f"median {med * 1e3:.1f} ms"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n, secs = WORKLOADS[args.workload]
+    samples = int(secs * SR)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bound the sample so that warmup+steps finish within a few minutes
+    n_s = min(n, 30)
+    step = _cpu_step_fn(n_s, samples)
+    t0 = time.perf_counter()
+    step()
+    est = time.perf_counter() - t0
+    total = args.steps + max(args.warmup, 1)
+    while n_s > 1 and est * total > 150.0:
+        n_s = max(1, n_s // 2)
+        step = _cpu_step_fn(n_s, samples)
+        t0 = time.perf_counter()
+        step()
+        est = time.perf_counter() - t0
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n_s * secs * args.steps / dt
+    sample = (f"{n_s} of {n} utterances x {secs:g} s per step, batched torch CPU path "
+              f"(oracle/lmfb_torch_cpu.py), {torch.get_num_threads()} threads")
+    line = {
+        "impl": "reference",
+        "metric": "LMFB fwd+bwd audio-seconds per second", "value": value, "unit": "audio-s/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "utterances_per_gpu": n, "seconds": secs,
+                   "mask_mode": "reim", "cmvn": "per_bin", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="chime4_30x6s", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 20
+        args.warmup = args.warmup if args.warmup is not None else 3
+        run_reference(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 2000
+        args.warmup = args.warmup if args.warmup is not None else 20
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+/* aas_lmfb.h -- C ABI of the B200-native LMFB front-end (libaas_lmfb.so).
+ *
+ * The reference (lifelongeek/AAS_enhancement) has no FFI layer; its de-facto operator API for
+ * this path is Python:
+ *   - BRNNmultiCH.__init__(..., mel_basis) / .forward   Speech_enhancement_by_AAS/model.py:148-200
+ *     (mask -> power -> mel -> log1p glue at :186-198, mel buffer at :167)
+ *   - the front-end parameters                          AM_training/train.py:39-42, :55-61, :190-199
+ *   - the (N, 40, T) fp32 channel-first batches         Speech_enhancement_by_AAS/loader_functions.py:47-105
+ * Each entry point below names the reference code it stands in for.  Plain pointers and
+ * sizes only; no torch types.  All device buffers are allocated and owned by the caller; the
+ * library never allocates device memory, never synchronises, and never keeps a pointer past
+ * the call.  Everything is asynchronous on the caller's stream.
+ *
+ * Layouts (fp32 unless noted):
+ *   wave      (N, wave_stride)   zero-padded samples, 16 kHz mono
+ *   lengths   (N,) int32         samples per utterance
+ *   mask_r/i  (N, 161, Tmax)     element (n,f,t) at n*mask_stride_n + f*mask_stride_f + t
+ *   out       (N, M, Tmax)       contiguous; frames t >= T_n are written as exact zeros
+ *   stats     (N, M, 2)          (mean, rstd) written by forward, read by backward
+ *   frame counts                 T_n = 1 + lengths[n] / 160, clipped to Tmax
+ */
+#ifndef AAS_LMFB_H
+#define AAS_LMFB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AAS_LMFB_ABI_VERSION 1
+
+#define AAS_LMFB_N_FFT   320   /* int(16000 * 0.02), AM_training/train.py:39-40 */
+#define AAS_LMFB_HOP     160   /* int(16000 * 0.01), AM_training/train.py:41    */
+#define AAS_LMFB_N_BINS  161   /* AM_training/train.py:199                      */
+
+/* flags: bits 0-1 mask mode, bits 2-3 CMVN mode */
+#define AAS_LMFB_MASK_NONE    0u   /* P = Re^2 + Im^2                                        */
+#define AAS_LMFB_MASK_REIM    1u   /* P = (Re*Mr)^2 + (Im*Mi)^2   (model.py:191-194)          */
+#define AAS_LMFB_MASK_POWER   2u   /* P = M * (Re^2 + Im^2)                                   */
+#define AAS_LMFB_CMVN_NONE    (0u << 2)
+#define AAS_LMFB_CMVN_PER_BIN (1u << 2)   /* mean/std per mel bin over the utterance's frames */
+#define AAS_LMFB_CMVN_GLOBAL  (2u << 2)   /* scalar mean/std over the utterance's (M, T) matrix */
+
+/* return codes: 0 ok, <0 argument errors, >0 a cudaError_t from the launch */
+#define AAS_LMFB_OK              0
+#define AAS_LMFB_E_NULL         -1
+#define AAS_LMFB_E_ALIGN        -2
+#define AAS_LMFB_E_SHAPE        -3
+#define AAS_LMFB_E_FLAGS        -4
+#define AAS_LMFB_E_MEL          -5   /* mel basis is not representable (see plan_create)       */
+#define AAS_LMFB_E_NOMEM        -6   /* host allocation failed                                 */
+
+typedef struct aas_lmfb_plan aas_lmfb_plan;
+
+int aas_lmfb_abi_version(void);
+const char* aas_lmfb_strerror(int code);
+
+/* Build a host-side plan from the mel basis, a HOST (n_mels, 161) row-major fp32 matrix -- the
+ * `mel_basis` constructor argument of BRNNmultiCH (model.py:148, :167).  The basis must be
+ * "banded": every bin feeds at most two filters, adjacent in index, and filters are ordered
+ * along frequency (true of every triangular mel filterbank).  Returns NULL and sets *status
+ * otherwise.  No device work. */
+aas_lmfb_plan* aas_lmfb_plan_create(const float* mel_host, int n_mels, int n_bins, int* status);
+void aas_lmfb_plan_destroy(aas_lmfb_plan* plan);
+
+/* Bytes of device workspace `backward` needs (forward needs none). */
+size_t aas_lmfb_workspace_bytes(int n, int n_mels, int tmax, uint32_t flags);
+
+/* Forward: framing + Hamming window + STFT(320/160) + mask + mel + log1p (+ CMVN).
+ * Stands in for the missing SpectrogramDataset front-end (AM_training/train.py:190-199,
+ * :255-259) fused with the glue of model.py:186-198.
+ *   window   device (320,) window samples (AM_training/train.py:42)
+ *   mask_r   may be NULL for MASK_NONE; mask_i may be NULL unless MASK_REIM
+ *   prof     optional array of 4 cudaEvent_t recorded around {stft-mel kernel, cmvn kernel};
+ *            NULL in normal use */
+int aas_lmfb_forward(const aas_lmfb_plan* plan,
+                     const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                     const float* mask_r, const float* mask_i,
+                     int64_t mask_stride_n, int64_t mask_stride_f,
+                     const float* window,
+                     float* out, float* stats, int tmax,
+                     uint32_t flags, float eps, void* cuda_stream, void* const* prof);
+
+/* Backward into the mask(s): what autograd does through model.py:191-198 (plus the CMVN).
+ *   out, stats   exactly what forward produced (not modified; backward may run repeatedly,
+ *                trainer_AAS.py:150 uses retain_graph=True)
+ *   grad_out     (N, M, Tmax) contiguous
+ *   grad_mask_r/i same strides as the masks; every element (incl. frames t >= T_n) is written
+ *   workspace    aas_lmfb_workspace_bytes() bytes, 16-byte aligned */
+int aas_lmfb_backward(const aas_lmfb_plan* plan,
+                      const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                      const float* mask_r, const float* mask_i,
+                      int64_t mask_stride_n, int64_t mask_stride_f,
+                      const float* window,
+                      const float* out, const float* stats, const float* grad_out,
+                      float* grad_mask_r, float* grad_mask_i,
+                      void* workspace, int tmax,
+                      uint32_t flags, float eps, void* cuda_stream, void* const* prof);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AAS_LMFB_H */

@@ -8,6 +8,8 @@ Fixtures written
                       CPU (only ``.cuda()`` in its ctor, model.py:167, is shimmed to a no-op);
                       the masks it multiplies by are captured with forward hooks; output and
                       autograd gradients w.r.t. both masks are stored.
+  ref_glue_on_stft.npz  LIVE REFERENCE: the same tail fed with the oracle's STFT of a seeded wave,
+                      so the CUDA path (STFT included) can be compared with the reference output.
   ref_collate.npz     LIVE REFERENCE: _collate_fn / _collate_fn_paired outputs
                       (loader_functions.py:47-105) for a seeded ragged batch.
   ref_ctc_sizes.npz   LIVE torch semantics of trainer_AAS.py:165-167 on a grid of (T, Tmax, T').
@@ -66,6 +68,53 @@ def make_ref_glue():
         stft_real=x[:, :f].numpy(), stft_imag=x[:, f:].numpy(),
         mask_real=captured["mr"].detach().numpy(), mask_imag=captured["mi"].detach().numpy(),
         mel_basis=mel, output=out.detach().numpy(), grad_out=g.numpy(),
+        grad_mask_real=captured["mr"].grad.numpy(), grad_mask_imag=captured["mi"].grad.numpy())
+    sys.path.remove(REF)
+
+
+def make_ref_glue_on_stft():
+    """The live reference tail (model.py:186-198) fed with a REAL STFT (the oracle's, of a
+    seeded wave), so that the CUDA path can be compared with the reference's own output."""
+    sys.path.insert(0, REF)
+    import model as ref_model
+
+    torch.manual_seed(321)
+    f, h = 161, 24
+    b = _synth.make_batch(2, 3200, seed=31)
+    win = orc.hamming_window().astype(np.float32).astype(np.float64)
+    mel = orc.mel_filterbank().astype(np.float32)
+    spec = np.stack([orc.stft_frames(b["wave"][i], int(b["lengths"][i]), win) for i in range(2)])
+    x = torch.from_numpy(np.concatenate([spec.real, spec.imag], axis=1).astype(np.float32))
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        net = ref_model.BRNNmultiCH(I=2 * f, H=h, L=3, nCH=1, mel_basis=mel).float()
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    # spread the masks so they are not all ~0
+    with torch.no_grad():
+        net.final_linear_real.bias.fill_(0.7)
+        net.final_linear_imag.bias.fill_(0.6)
+        net.final_linear_real.weight.mul_(3.0)
+        net.final_linear_imag.weight.mul_(3.0)
+    captured = {}
+
+    def hook(name):
+        def fn(_m, _i, out):
+            out.retain_grad()
+            captured[name] = out
+        return fn
+
+    net.final_linear_real.register_forward_hook(hook("mr"))
+    net.final_linear_imag.register_forward_hook(hook("mi"))
+    out = net(x)
+    g = torch.from_numpy(b["grad_out"][:, :, :out.shape[2]].copy())
+    out.backward(g)
+    np.savez_compressed(
+        os.path.join(HERE, "ref_glue_on_stft.npz"),
+        seed=31, n=2, max_len=3200,
+        mask_real=captured["mr"].detach().numpy(), mask_imag=captured["mi"].detach().numpy(),
+        output=out.detach().numpy(), grad_out=g.numpy(),
         grad_mask_real=captured["mr"].grad.numpy(), grad_mask_imag=captured["mi"].grad.numpy())
     sys.path.remove(REF)
 
@@ -137,6 +186,7 @@ def make_oracle_cases():
 
 if __name__ == "__main__":
     make_ref_glue()
+    make_ref_glue_on_stft()
     make_ref_collate()
     make_ref_ctc_sizes()
     make_oracle_cases()
