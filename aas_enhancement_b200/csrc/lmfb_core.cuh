@@ -6,16 +6,21 @@
 //   * every twiddle is a literal (the FFT code is identical for all lanes),
 //   * every global access of a (N, F, T)/(N, M, T) tensor has the lanes along T, i.e. is a
 //     128-byte coalesced row segment -- no transposition is ever needed,
-//   * no block-level synchronisation (only __syncwarp after staging).
+//   * no block-level synchronisation (only __syncwarp around staging).
 //
 // Real FFT of 320 samples = complex FFT of the 160 packed samples z[j] = x[2j] + i x[2j+1],
 // computed with the Good-Thomas prime-factor map 160 = 5 x 32 (no inter-stage twiddles):
-//   pass 1: five 32-point FFTs in registers (generated codelet), in place in the scratch;
-//   pass 2: 5-point DFTs for the index pair (k2, 32-k2) followed by the real-split
-//           butterfly, in place; bin f ends up in slot (f mod 5)*32 + (f mod 32), bins 0
-//           and 160 (both real) share slot 0.
-// The spectrum kept in the scratch is X' = 2 X (the 1/2 of the split is folded into the mel
-// weights as 1/4, exact in binary floating point).
+//   stage  : windowed samples -> private columns, permuted into PFA input order
+//   pass 1 : five 32-point FFTs in registers (generated codelet), in place in the scratch
+//   pass 2 : for each index pair (k2, 32-k2): two 5-point DFTs + the real-split butterfly give
+//            ten bins; the mask(s) for those ten bins (prefetched one step ahead into
+//            registers, lanes along T) are applied at once and the masked power (forward) or
+//            the mask-gradient factors (backward) replace the spectrum in place.  Bin f lives
+//            in slot (f mod 5)*32 + (f mod 32); bins 0 and 160 (both real) share slot 0.
+//   phase 3: walk the bins in ascending order out of the scratch: banded mel accumulation +
+//            log1p (forward), or dP * factors -> mask gradients (backward).
+// The spectrum is kept as X' = 2 X (the 1/2 of the split is folded into the mel weights as
+// 1/4, exact in binary floating point).
 //
 // The same code compiles as plain C++ for the CPU emulation harness under tests/emu/ (test
 // infrastructure only).
@@ -28,8 +33,10 @@
 
 #ifdef __CUDACC__
 #  define LMFB_LDG(p) __ldg(p)
+#  define LMFB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
 #  define LMFB_LDG(p) (*(p))
+#  define LMFB_PREFETCH_L2(p) ((void)(p))
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
 #endif
@@ -64,10 +71,6 @@ LMFB_HD int slot_of_packed(int j) {            // j in [0,160): packed-sample in
     return n1 * 32 + n2;
 }
 
-LMFB_HD int slot_of_bin(int f) {               // f in [1,159]
-    return (f % 5) * 32 + (f & 31);
-}
-
 // 'reflect' padding index (numpy semantics, any offset, length >= 1)
 LMFB_HD int reflect_index(int i, int len) {
     if (len <= 1) return 0;
@@ -79,48 +82,99 @@ LMFB_HD int reflect_index(int i, int len) {
 
 // ---------------------------------------------------------------------------------------
 // Staging: copy the (32+1)*160 samples a tile needs into the 32 private frame columns,
-// windowed and permuted into PFA input order.  lanes run along the packed-sample index.
-//   wave_row : first sample of this utterance;  len : its length (>=1)
-//   t0       : first frame of the tile
-//   S        : warp scratch base (float2 [kSlots][kPitch])
-//   vec_ok   : wave_row is 8-byte aligned
+// windowed and permuted into PFA input order.  Lanes run along the packed-sample index, so
+// global reads are coalesced 256-byte runs and the scratch writes are conflict-free.
+// Rows are loaded four at a time (12 independent 8-byte loads in flight per lane).
 // ---------------------------------------------------------------------------------------
-LMFB_HD void stage_tile(int lane, const float* __restrict__ wave_row, int len, int t0,
-                        const float* __restrict__ window, float2* __restrict__ S, bool vec_ok) {
+struct StageLane {                      // per-lane constants of the staging map
     int   slot_a[3], slot_b[3];
     float wa0[3], wa1[3], wb0[3], wb1[3];
+};
+
+LMFB_HD void stage_lane_init(int lane, const float* __restrict__ window, StageLane& sl) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         const int c = lane + 32 * q;                       // packed index inside a hop-row, < 80 valid
         const int cc = c < 80 ? c : 0;
-        slot_a[q] = slot_of_packed(cc) * kPitch;
-        slot_b[q] = slot_of_packed(cc + 80) * kPitch;
-        wa0[q] = LMFB_LDG(window + 2 * cc);
-        wa1[q] = LMFB_LDG(window + 2 * cc + 1);
-        wb0[q] = LMFB_LDG(window + 2 * cc + kHop);
-        wb1[q] = LMFB_LDG(window + 2 * cc + kHop + 1);
+        sl.slot_a[q] = slot_of_packed(cc) * kPitch;
+        sl.slot_b[q] = slot_of_packed(cc + 80) * kPitch;
+        sl.wa0[q] = LMFB_LDG(window + 2 * cc);
+        sl.wa1[q] = LMFB_LDG(window + 2 * cc + 1);
+        sl.wb0[q] = LMFB_LDG(window + 2 * cc + kHop);
+        sl.wb1[q] = LMFB_LDG(window + 2 * cc + kHop + 1);
     }
-#pragma unroll 3
-    for (int r = 0; r <= kTile; ++r) {
-        const int row = t0 + r - 1;                        // hop-row index in the unpadded signal
-        const long long base = (long long)row * kHop;
-        const bool interior = vec_ok && row >= 0 && (base + kHop) <= (long long)len;
-#pragma unroll
+}
+
+// rows [row_lo, row_hi) of the unpadded signal lie fully inside [0, len) and can be read as float2
+LMFB_HD bool rows_interior(int row_lo, int row_hi, int len, bool vec_ok) {
+    return vec_ok && row_lo >= 0 && (long long)row_hi * kHop <= (long long)len;
+}
+
+LMFB_HD void stage_store(const StageLane& sl, float2* __restrict__ S, int r, int q, float2 v) {
+    if (r < kTile)  S[sl.slot_a[q] + r]     = make_float2(v.x * sl.wa0[q], v.y * sl.wa1[q]);
+    if (r >= 1)     S[sl.slot_b[q] + r - 1] = make_float2(v.x * sl.wb0[q], v.y * sl.wb1[q]);
+}
+
+// edge rows (reflect padding at either end of the utterance, or an unaligned wave): one
+// element at a time, kept out of line and rolled -- only boundary tiles ever come here
+LMFB_HD void stage_rows_slow(int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
+                             int t0, float2* __restrict__ S, int r_lo, int r_hi) {
+#pragma unroll 1
+    for (int r = r_lo; r < r_hi; ++r) {
+        const int base = (t0 + r - 1) * kHop;
+#pragma unroll 1
         for (int q = 0; q < 3; ++q) {
             const int c = lane + 32 * q;
-            if (c < 80) {
-                float2 v;
-                if (interior) {
-                    v = LMFB_LDG(reinterpret_cast<const float2*>(wave_row + base) + c);
-                } else {
-                    const int i0 = (int)base + 2 * c;
-                    v.x = LMFB_LDG(wave_row + reflect_index(i0, len));
-                    v.y = LMFB_LDG(wave_row + reflect_index(i0 + 1, len));
-                }
-                if (r < kTile)  S[slot_a[q] + r]     = make_float2(v.x * wa0[q], v.y * wa1[q]);
-                if (r >= 1)     S[slot_b[q] + r - 1] = make_float2(v.x * wb0[q], v.y * wb1[q]);
-            }
+            if (c >= 80) continue;
+            float2 v;
+            v.x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
+            v.y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
+            const int qq = q;                      // slot/window tables are tiny: index dynamically
+            const int sa = qq == 0 ? sl.slot_a[0] : (qq == 1 ? sl.slot_a[1] : sl.slot_a[2]);
+            const int sb = qq == 0 ? sl.slot_b[0] : (qq == 1 ? sl.slot_b[1] : sl.slot_b[2]);
+            const float wa0 = qq == 0 ? sl.wa0[0] : (qq == 1 ? sl.wa0[1] : sl.wa0[2]);
+            const float wa1 = qq == 0 ? sl.wa1[0] : (qq == 1 ? sl.wa1[1] : sl.wa1[2]);
+            const float wb0 = qq == 0 ? sl.wb0[0] : (qq == 1 ? sl.wb0[1] : sl.wb0[2]);
+            const float wb1 = qq == 0 ? sl.wb1[0] : (qq == 1 ? sl.wb1[1] : sl.wb1[2]);
+            if (r < kTile)  S[sa + r]     = make_float2(v.x * wa0, v.y * wa1);
+            if (r >= 1)     S[sb + r - 1] = make_float2(v.x * wb0, v.y * wb1);
         }
+    }
+}
+
+LMFB_HD void stage_tile(int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
+                        int t0, float2* __restrict__ S, bool vec_ok) {
+    constexpr int kRowsPerBatch = 4;               // rows 0..31 in 8 batches, row 32 on its own
+#pragma unroll 1
+    for (int r0 = 0; r0 < kTile; r0 += kRowsPerBatch) {
+        if (!rows_interior(t0 + r0 - 1, t0 + r0 - 1 + kRowsPerBatch, len, vec_ok)) {
+            stage_rows_slow(lane, sl, wave_row, len, t0, S, r0, r0 + kRowsPerBatch);
+            continue;
+        }
+        const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r0 - 1) * kHop) + lane;
+        float2 v[kRowsPerBatch][3];
+#pragma unroll
+        for (int i = 0; i < kRowsPerBatch; ++i) {
+            v[i][0] = LMFB_LDG(src + i * 80);
+            v[i][1] = LMFB_LDG(src + i * 80 + 32);
+            v[i][2] = lane < 16 ? LMFB_LDG(src + i * 80 + 64) : make_float2(0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int i = 0; i < kRowsPerBatch; ++i) {
+            stage_store(sl, S, r0 + i, 0, v[i][0]);
+            stage_store(sl, S, r0 + i, 1, v[i][1]);
+            if (lane < 16) stage_store(sl, S, r0 + i, 2, v[i][2]);
+        }
+    }
+    if (!rows_interior(t0 + kTile - 1, t0 + kTile, len, vec_ok)) {
+        stage_rows_slow(lane, sl, wave_row, len, t0, S, kTile, kTile + 1);
+    } else {
+        const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + kTile - 1) * kHop) + lane;
+        const float2 v0 = LMFB_LDG(src), v1 = LMFB_LDG(src + 32);
+        const float2 v2 = lane < 16 ? LMFB_LDG(src + 64) : make_float2(0.0f, 0.0f);
+        stage_store(sl, S, kTile, 0, v0);
+        stage_store(sl, S, kTile, 1, v1);
+        if (lane < 16) stage_store(sl, S, kTile, 2, v2);
     }
 }
 
@@ -159,7 +213,8 @@ LMFB_HD void dft5(const float (&ar)[5], const float (&ai)[5], float (&br)[5], fl
     br[3] = m2r - n2i; bi[3] = m2i + n2r;
 }
 
-// real-split butterfly: A = Z[f], Bz = Z[160-f]; returns X'[f] and X'[160-f] (both scaled by 2)
+// real-split butterfly: A = Z[f], Bz = Z[160-f]; returns X'[f] and X'[160-f] (both scaled by 2).
+// Also correct for the self-paired bins: f = 0 gives (X'[0], X'[160]) and f = 80 gives X'[80] twice.
 LMFB_HD void split_pair(float Ar, float Ai, float Bzr, float Bzi, float sn, float cs,
                         float2& xf, float2& xp) {
     const float sr = Ar + Bzr, si = Ai - Bzi;        // S  = A + conj(Bz)
@@ -170,206 +225,165 @@ LMFB_HD void split_pair(float Ar, float Ai, float Bzr, float Bzi, float sn, floa
     xp = make_float2(sr + Dr, -(si + Di));
 }
 
-// ---------------------------------------------------------------------------------------
-// pass 2: radix-5 across the five sub-transforms + real split, in place.
-// ---------------------------------------------------------------------------------------
-LMFB_HD void fft_pass2(float2* __restrict__ col) {
-    float ar[5], ai[5], Ar[5], Ai[5], br[5], bi[5], Br[5], Bi[5];
-    // ---- k2 = 0 (self-paired; holds bins 0, 160, and pairs (96,64), (32,128))
-    {
+// what pass 2 leaves in the scratch for one bin, given the spectrum value and the mask(s)
+//   forward : .x = masked power P'            (.y unused)
+//   backward: (.x, .y) = (dP -> dMr factor, dP -> dMi factor) = (2 Mr Re'^2, 2 Mi Im'^2)
+//             'power' mode: .x = Re'^2 + Im'^2
+template <int MASK, bool BWD>
+LMFB_HD float2 bin_payload(float2 x, float mr, float mi) {
+    if (!BWD) {
+        if (MASK == kMaskReim) { const float a = x.x * mr, b = x.y * mi; return make_float2(fmaf(a, a, b * b), 0.0f); }
+        const float p = fmaf(x.x, x.x, x.y * x.y);
+        return make_float2(MASK == kMaskPower ? mr * p : p, 0.0f);
+    }
+    if (MASK == kMaskReim) return make_float2(2.0f * mr * x.x * x.x, 2.0f * mi * x.y * x.y);
+    return make_float2(fmaf(x.x, x.x, x.y * x.y), 0.0f);
+}
+
+// which mask tensors a kernel variant reads
+#define LMFB_NEEDS_MASK_R(MASK, BWD) ((BWD) ? (MASK) == kMaskReim : (MASK) != kMaskNone)
+#define LMFB_NEEDS_MASK_I(MASK, BWD) ((MASK) == kMaskReim)
+
+// mask values of the ten bins of pass-2 step k2: index k1 -> bin f, index 5+k1 -> bin 160-f
+template <int MASK, bool BWD>
+LMFB_HD void load_step_masks(int k2, const float* __restrict__ mr, const float* __restrict__ mi,
+                             long long sf, bool inrow, float (&vr)[10], float (&vi)[10]) {
+    const bool self = (k2 & 15) == 0;                 // k2 == 0 or 16: self-paired column
 #pragma unroll
-        for (int n = 0; n < 5; ++n) { const float2 v = col[(n * 32) * kPitch]; ar[n] = v.x; ai[n] = v.y; }
-        dft5(ar, ai, Ar, Ai);
-        col[0] = make_float2(2.0f * (Ar[0] + Ai[0]), 2.0f * (Ar[0] - Ai[0]));   // X'[0], X'[160]
-#pragma unroll
-        for (int k1 = 1; k1 <= 2; ++k1) {
-            float2 xf, xp;
-            split_pair(Ar[k1], Ai[k1], Ar[5 - k1], Ai[5 - k1], kSplitSin[0][k1], kSplitCos[0][k1], xf, xp);
-            col[(k1 * 32) * kPitch] = xf;
-            col[((5 - k1) * 32) * kPitch] = xp;
+    for (int k1 = 0; k1 < 5; ++k1) {
+        vr[k1] = vr[5 + k1] = vi[k1] = vi[5 + k1] = 0.0f;
+        if (!inrow || (self && k1 >= 3)) continue;
+        const int f = kBinOf[k2][k1];
+        const int fp = kBins - 1 - f;
+        if (LMFB_NEEDS_MASK_R(MASK, BWD)) {
+            vr[k1] = LMFB_LDG(mr + (long long)f * sf);
+            vr[5 + k1] = LMFB_LDG(mr + (long long)fp * sf);
+        }
+        if (LMFB_NEEDS_MASK_I(MASK, BWD)) {
+            vi[k1] = LMFB_LDG(mi + (long long)f * sf);
+            vi[5 + k1] = LMFB_LDG(mi + (long long)fp * sf);
         }
     }
-    // ---- k2 = 16 (self-paired; bin 80 and pairs (16,144), (112,48))
-    {
-#pragma unroll
-        for (int n = 0; n < 5; ++n) { const float2 v = col[(n * 32 + 16) * kPitch]; ar[n] = v.x; ai[n] = v.y; }
-        dft5(ar, ai, Ar, Ai);
-        col[16 * kPitch] = make_float2(2.0f * Ar[0], -2.0f * Ai[0]);             // X'[80] = 2 conj Z[80]
-#pragma unroll
-        for (int k1 = 1; k1 <= 2; ++k1) {
-            float2 xf, xp;
-            split_pair(Ar[k1], Ai[k1], Ar[5 - k1], Ai[5 - k1], kSplitSin[16][k1], kSplitCos[16][k1], xf, xp);
-            col[(k1 * 32 + 16) * kPitch] = xf;
-            col[((5 - k1) * 32 + 16) * kPitch] = xp;
-        }
-    }
-    // ---- k2 = 1..15 paired with 32-k2
+}
+
+// ---------------------------------------------------------------------------------------
+// pass 2: radix-5 across the five sub-transforms + real split + mask, in place.
+//   mr/mi : mask_r/mask_i + n*stride_n + t  (row f at + f*sf), only dereferenced if inrow
+// ---------------------------------------------------------------------------------------
+template <int MASK, bool BWD>
+LMFB_HD void fft_pass2_masked(float2* __restrict__ col, const float* __restrict__ mr,
+                              const float* __restrict__ mi, long long sf, bool inrow) {
+    float cr[10], ci[10], nr[10], ni[10];
+    load_step_masks<MASK, BWD>(0, mr, mi, sf, inrow, cr, ci);
 #pragma unroll 1
-    for (int k2 = 1; k2 < 16; ++k2) {
-        const int kb = 32 - k2;
+    for (int k2 = 0; k2 <= 16; ++k2) {
+        if (k2 < 16) load_step_masks<MASK, BWD>(k2 + 1, mr, mi, sf, inrow, nr, ni);
+        const bool self = (k2 & 15) == 0;
+        const int kb = (32 - k2) & 31;
+        float ar[5], ai[5], Ar[5], Ai[5], Br[5], Bi[5];
 #pragma unroll
-        for (int n = 0; n < 5; ++n) {
-            const float2 v = col[(n * 32 + k2) * kPitch]; ar[n] = v.x; ai[n] = v.y;
-            const float2 w = col[(n * 32 + kb) * kPitch]; br[n] = w.x; bi[n] = w.y;
-        }
+        for (int n = 0; n < 5; ++n) { const float2 v = col[(n * 32 + k2) * kPitch]; ar[n] = v.x; ai[n] = v.y; }
         dft5(ar, ai, Ar, Ai);
-        dft5(br, bi, Br, Bi);
+        if (self) {
+#pragma unroll
+            for (int n = 0; n < 5; ++n) { Br[n] = Ar[n]; Bi[n] = Ai[n]; }
+        } else {
+            float br[5], bi[5];
+#pragma unroll
+            for (int n = 0; n < 5; ++n) { const float2 v = col[(n * 32 + kb) * kPitch]; br[n] = v.x; bi[n] = v.y; }
+            dft5(br, bi, Br, Bi);
+        }
 #pragma unroll
         for (int k1 = 0; k1 < 5; ++k1) {
+            if (self && k1 >= 3) continue;                    // partners of k1 = 2, 1
             const int kp = (5 - k1) % 5;
             float2 xf, xp;
             split_pair(Ar[k1], Ai[k1], Br[kp], Bi[kp], kSplitSin[k2][k1], kSplitCos[k2][k1], xf, xp);
-            col[(k1 * 32 + k2) * kPitch] = xf;
-            col[(kp * 32 + kb) * kPitch] = xp;
+            const float2 pf = bin_payload<MASK, BWD>(xf, cr[k1], ci[k1]);
+            const float2 pp = bin_payload<MASK, BWD>(xp, cr[5 + k1], ci[5 + k1]);
+            if (k1 == 0 && k2 == 0) {
+                col[0] = make_float2(pf.x, pp.x);             // bins 0 and 160 (real) share slot 0
+            } else {
+                col[(k1 * 32 + k2) * kPitch] = pf;
+                col[(kp * 32 + kb) * kPitch] = pp;
+            }
         }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) { cr[i] = nr[i]; ci[i] = ni[i]; }
     }
 }
 
-// (re', im') of bin f from the finished scratch column
-LMFB_HD float2 load_bin(const float2* __restrict__ col, int f) {
-    if (f == 0)          { const float2 v = col[0]; return make_float2(v.x, 0.0f); }
-    if (f == kBins - 1)  { const float2 v = col[0]; return make_float2(v.y, 0.0f); }
-    return col[slot_of_bin(f) * kPitch];
-}
-
-template <int MASK>
-LMFB_HD float masked_power(float2 x, float mr, float mi) {
-    if (MASK == kMaskReim) { const float a = x.x * mr, b = x.y * mi; return fmaf(a, a, b * b); }
-    const float p = fmaf(x.x, x.x, x.y * x.y);
-    return MASK == kMaskPower ? mr * p : p;
-}
-
-}  // namespace aas_lmfb
-
-namespace aas_lmfb {
-
 // ---------------------------------------------------------------------------------------
-// phase 3 (forward): walk the bins in ascending order, multiply by the mask(s), accumulate the
-// two live mel filters, and emit log1p(E[m]) whenever a filter is complete.
-//   mr/mi   : mask_r/mask_i + n*stride_n + t      (row f is at + f*sf)
-//   out     : out + n*stride_n + t                (row m is at + m*som)
-//   inrow   : t < Tmax (memory exists);  valid : t < T_i (frame exists)
+// phase 3 (forward): banded mel accumulation over ascending bins + log1p on completion.
+//   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
-template <int MASK>
 LMFB_HD void phase3_fwd(const float2* __restrict__ col, const MelBand& mb,
-                        const float* __restrict__ mr, const float* __restrict__ mi, long long sf,
                         float* __restrict__ out, long long som, bool inrow, bool valid) {
-    int m = 0;
+    const float* colf = reinterpret_cast<const float*>(col);
     const int n_mels = mb.n_mels;
+    int m = 0;
     float acc0 = 0.0f, acc1 = 0.0f;
-#define LMFB_EMIT()                                                        \
-    do {                                                                   \
-        if (m < n_mels) {                                                  \
-            const float y_ = valid ? log1pf(acc0) : 0.0f;                  \
-            if (inrow) out[(long long)m * som] = y_;                       \
-        }                                                                  \
-        acc0 = acc1; acc1 = 0.0f; ++m;                                     \
-    } while (0)
 #pragma unroll 1
-    for (int b = 0; b < 4; ++b) {
-        const int fb = 40 * b;
-#pragma unroll
-        for (int g = 0; g < 5; ++g) {
-            float vr[8], vi[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int f = fb + g * 8 + i;
-                vr[i] = (MASK != kMaskNone && inrow) ? LMFB_LDG(mr + (long long)f * sf) : 0.0f;
-                vi[i] = (MASK == kMaskReim && inrow) ? LMFB_LDG(mi + (long long)f * sf) : 0.0f;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int fi = g * 8 + i;                  // compile-time
-                const int f = fb + fi;
-                float2 x = col[((fi % 5) * 32 + ((8 * b + fi) & 31)) * kPitch];
-                if (fi == 0 && b == 0) x = make_float2(x.x, 0.0f);       // bin 0 is real (slot 0 .x)
-                const float p = masked_power<MASK>(x, vr[i], vi[i]);
-                const int ml = mb.ml[f];
-                while (m < ml) LMFB_EMIT();
-                acc0 = fmaf(mb.wl[f], p, acc0);
-                acc1 = fmaf(mb.wh[f], p, acc1);
-            }
+    for (int f = 0; f <= kBins; ++f) {                    // f == kBins: sentinel that flushes the rest
+        const int ml = f < kBins ? (int)mb.ml[f] : n_mels;
+#pragma unroll 1
+        while (m < ml) {
+            const float y = valid ? log1pf(acc0) : 0.0f;
+            if (inrow) out[(long long)m * som] = y;
+            acc0 = acc1; acc1 = 0.0f; ++m;
+        }
+        if (f < kBins) {
+            const float p = colf[kBinOff[f]];
+            acc0 = fmaf(mb.wl[f], p, acc0);
+            acc1 = fmaf(mb.wh[f], p, acc1);
         }
     }
-    {   // bin 160 (real, slot 0 .y)
-        const int f = kBins - 1;
-        const float vr = (MASK != kMaskNone && inrow) ? LMFB_LDG(mr + (long long)f * sf) : 0.0f;
-        const float vi = 0.0f;
-        const float2 x = make_float2(col[0].y, 0.0f);
-        const float p = masked_power<MASK>(x, vr, vi);
-        const int ml = mb.ml[f];
-        while (m < ml) LMFB_EMIT();
-        acc0 = fmaf(mb.wl[f], p, acc0);
-        acc1 = fmaf(mb.wh[f], p, acc1);
-    }
-    while (m < n_mels) LMFB_EMIT();
-#undef LMFB_EMIT
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 3 (backward): dP[f] = wl*dE[ml] + wh*dE[ml+1];  'reim': dMr = 2 Mr Re^2 dP,
-// dMi = 2 Mi Im^2 dP;  'power': dM = (Re^2 + Im^2) dP.
+// phase 3 (backward): dP[f] = wl*dE[ml] + wh*dE[ml+1]; gradients = factors * dP.
 //   dE : dE + n*stride_n + t (row m at + m*sem), zero for frames t >= T_i
 // ---------------------------------------------------------------------------------------
 template <int MASK>
 LMFB_HD void phase3_bwd(const float2* __restrict__ col, const MelBand& mb,
-                        const float* __restrict__ mr, const float* __restrict__ mi, long long sf,
                         const float* __restrict__ dE, long long sem,
                         float* __restrict__ gr, float* __restrict__ gi, long long gsf, bool inrow) {
-    int m = 0;
+    const float* colf = reinterpret_cast<const float*>(col);
     const int n_mels = mb.n_mels;
+    int m = 0;
     float d0 = (inrow && 0 < n_mels) ? LMFB_LDG(dE) : 0.0f;
     float d1 = (inrow && 1 < n_mels) ? LMFB_LDG(dE + sem) : 0.0f;
     float d2 = (inrow && 2 < n_mels) ? LMFB_LDG(dE + 2 * sem) : 0.0f;
-#define LMFB_ADV()                                                                         \
-    do {                                                                                   \
-        d0 = d1; d1 = d2; ++m;                                                             \
-        d2 = (inrow && m + 2 < n_mels) ? LMFB_LDG(dE + (long long)(m + 2) * sem) : 0.0f;   \
-    } while (0)
-#define LMFB_GRAD(x, vr_, vi_, f_)                                                         \
-    do {                                                                                   \
-        const int ml_ = mb.ml[f_];                                                         \
-        while (m < ml_) LMFB_ADV();                                                        \
-        const float dp_ = fmaf(mb.wh[f_], d1, mb.wl[f_] * d0);                             \
-        if (MASK == kMaskReim) {                                                           \
-            const float a_ = (x).x * (x).x * (vr_), b_ = (x).y * (x).y * (vi_);            \
-            if (inrow) { gr[(long long)(f_) * gsf] = 2.0f * a_ * dp_;                      \
-                         gi[(long long)(f_) * gsf] = 2.0f * b_ * dp_; }                    \
-        } else {                                                                           \
-            const float pw_ = fmaf((x).x, (x).x, (x).y * (x).y);                           \
-            if (inrow) gr[(long long)(f_) * gsf] = pw_ * dp_;                              \
-        }                                                                                  \
-    } while (0)
+    float d3 = (inrow && 3 < n_mels) ? LMFB_LDG(dE + 3 * sem) : 0.0f;
 #pragma unroll 1
-    for (int b = 0; b < 4; ++b) {
-        const int fb = 40 * b;
-#pragma unroll
-        for (int g = 0; g < 5; ++g) {
-            float vr[8], vi[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int f = fb + g * 8 + i;
-                vr[i] = (MASK == kMaskReim && inrow) ? LMFB_LDG(mr + (long long)f * sf) : 0.0f;
-                vi[i] = (MASK == kMaskReim && inrow) ? LMFB_LDG(mi + (long long)f * sf) : 0.0f;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int fi = g * 8 + i;
-                const int f = fb + fi;
-                float2 x = col[((fi % 5) * 32 + ((8 * b + fi) & 31)) * kPitch];
-                if (fi == 0 && b == 0) x = make_float2(x.x, 0.0f);
-                LMFB_GRAD(x, vr[i], vi[i], f);
-            }
+    for (int f = 0; f < kBins; ++f) {
+        const int ml = mb.ml[f];
+#pragma unroll 1
+        while (m < ml) {
+            d0 = d1; d1 = d2; d2 = d3; ++m;
+            d3 = (inrow && m + 3 < n_mels) ? LMFB_LDG(dE + (long long)(m + 3) * sem) : 0.0f;
+        }
+        const float dp = fmaf(mb.wh[f], d1, mb.wl[f] * d0);
+        const int off = kBinOff[f];
+        const float a = colf[off];
+        const float b = (f == 0 || f == kBins - 1) ? 0.0f : colf[off + 1];
+        if (inrow) {
+            gr[(long long)f * gsf] = a * dp;
+            if (MASK == kMaskReim) gi[(long long)f * gsf] = b * dp;
         }
     }
-    {
-        const int f = kBins - 1;
-        const float vr = (MASK == kMaskReim && inrow) ? LMFB_LDG(mr + (long long)f * sf) : 0.0f;
-        const float2 x = make_float2(col[0].y, 0.0f);
-        LMFB_GRAD(x, vr, 0.0f, f);
+}
+
+// L2 prefetch of the mask rows a tile will read: lanes take rows lane, lane+32, ...; a 128-byte
+// row segment may straddle two lines, so both ends are touched.
+LMFB_HD void prefetch_rows_l2(int lane, const float* __restrict__ base, long long sf, int rows, int t0, int tmax) {
+    if (t0 >= tmax) return;
+    const int last = (t0 + kTile <= tmax ? t0 + kTile : tmax) - 1;
+#pragma unroll 1
+    for (int f = lane; f < rows; f += 32) {
+        LMFB_PREFETCH_L2(base + (long long)f * sf + t0);
+        LMFB_PREFETCH_L2(base + (long long)f * sf + last);
     }
-#undef LMFB_GRAD
-#undef LMFB_ADV
 }
 
 }  // namespace aas_lmfb

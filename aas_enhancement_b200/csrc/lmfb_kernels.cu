@@ -38,6 +38,7 @@ struct K1Args {
     float*         gi;
     int            tmax;
     int            tiles_per_utt;
+    int            total_tiles;
     int            vec_ok;
 };
 
@@ -46,51 +47,59 @@ __global__ void __launch_bounds__(kTile)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     extern __shared__ __align__(16) float2 S[];
     const int lane = threadIdx.x;
-    const int n    = blockIdx.x / a.tiles_per_utt;
-    const int t0   = (blockIdx.x - n * a.tiles_per_utt) * kTile;
-    const int t    = t0 + lane;
-    const int len  = a.lengths[n];
-    int T = len >= 1 ? 1 + len / kHop : 0;
-    T = T < a.tmax ? T : a.tmax;
-    const bool inrow = t < a.tmax;
-    const bool valid = t < T;
-    const int  n_mels = mb.n_mels;
+    const int n_mels = mb.n_mels;
     const long long som = a.tmax;
-    const long long row_nm = (long long)n * n_mels * som + t;
+    StageLane sl;
+    stage_lane_init(lane, a.window, sl);
+    float2* col = S + lane;
 
-    if (t0 >= T) {                                  // tile lies entirely in the zero padding
-        if (inrow) {
-            if (!BWD) {
-                for (int m = 0; m < n_mels; ++m) a.out[row_nm + m * som] = 0.0f;
-            } else if (MASK != kMaskNone) {
-                const long long g = (long long)n * a.msn + t;
-                for (int f = 0; f < kBins; ++f) {
-                    a.gr[g + f * a.msf] = 0.0f;
-                    if (MASK == kMaskReim) a.gi[g + f * a.msf] = 0.0f;
+    // persistent warp: tiles are dealt round-robin, neighbouring tiles run at the same time
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int n   = tile / a.tiles_per_utt;
+        const int t0  = (tile - n * a.tiles_per_utt) * kTile;
+        const int t   = t0 + lane;
+        const int len = a.lengths[n];
+        int T = len >= 1 ? 1 + len / kHop : 0;
+        T = T < a.tmax ? T : a.tmax;
+        const bool inrow = t < a.tmax;
+        const bool valid = t < T;
+        const long long row_nm = (long long)n * n_mels * som + t;
+        const long long moff = (long long)n * a.msn + t;
+
+        if (t0 >= T) {                              // tile lies entirely in the zero padding
+            if (inrow) {
+                if (!BWD) {
+#pragma unroll 4
+                    for (int m = 0; m < n_mels; ++m) a.out[row_nm + m * som] = 0.0f;
+                } else if (MASK != kMaskNone) {
+#pragma unroll 4
+                    for (int f = 0; f < kBins; ++f) {
+                        a.gr[moff + f * a.msf] = 0.0f;
+                        if (MASK == kMaskReim) a.gi[moff + f * a.msf] = 0.0f;
+                    }
                 }
             }
+            continue;
         }
-        return;
-    }
 
-    stage_tile(lane, a.wave + (long long)n * a.wave_stride, len, t0, a.window, S, a.vec_ok != 0);
-    __syncwarp();
-    float2* col = S + lane;
-    fft_pass1(col);
-    fft_pass2(col);
+        // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs
+        if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(lane, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
+        if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(lane, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
+        if (BWD) prefetch_rows_l2(lane, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
 
-    const long long moff = (long long)n * a.msn + t;
-    if (!BWD) {
-        phase3_fwd<MASK>(col, mb, a.mask_r + moff, a.mask_i + moff, a.msf,
-                         a.out + row_nm, som, inrow, valid);
-    } else {
-        phase3_bwd<MASK>(col, mb, a.mask_r + moff, a.mask_i + moff, a.msf,
-                         a.dE + row_nm, som, a.gr + moff, a.gi + moff, a.msf, inrow);
+        __syncwarp();                               // previous tile's columns are no longer read
+        stage_tile(lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
+        __syncwarp();
+        fft_pass1(col);
+        fft_pass2_masked<MASK, BWD>(col, a.mask_r + moff, a.mask_i + moff, a.msf, inrow);
+        if (!BWD) phase3_fwd(col, mb, a.out + row_nm, som, inrow, valid);
+        else      phase3_bwd<MASK>(col, mb, a.dE + row_nm, som, a.gr + moff, a.gi + moff, a.msf, inrow);
     }
 }
 
 // ------------------------------------------------------------------------------------ K2
 constexpr int kRowThreads = 128;
+constexpr int kWarpsPerSM = 5;              // 5 x (42,240 + 1,024) B of shared memory per SM
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
 #pragma unroll
@@ -290,13 +299,20 @@ int ensure_attrs(k1_fn fn) {
     return 0;
 }
 
-int launch_k1(k1_fn fn, const K1Args& a, const MelBand& mb, int n, cudaStream_t stream) {
+int launch_k1(k1_fn fn, K1Args& a, const MelBand& mb, int n, cudaStream_t stream) {
     const int rc = ensure_attrs(fn);
     if (rc) return rc;
-    const long long blocks = (long long)n * a.tiles_per_utt;
-    if (blocks <= 0) return AAS_LMFB_OK;
-    if (blocks > 0x7fffffffLL) return AAS_LMFB_E_SHAPE;
-    fn<<<(unsigned)blocks, kTile, kScratchBytes, stream>>>(a, mb);
+    const long long total = (long long)n * a.tiles_per_utt;
+    if (total <= 0) return AAS_LMFB_OK;
+    if (total > 0x7fffffffLL) return AAS_LMFB_E_SHAPE;
+    a.total_tiles = (int)total;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    const long long resident = (long long)sms * kWarpsPerSM;      // one warp-CTA per scratch slot
+    const unsigned blocks = (unsigned)(total < resident ? total : resident);
+    fn<<<blocks, kTile, kScratchBytes, stream>>>(a, mb);
     return (int)cudaPeekAtLastError();
 }
 

@@ -10,14 +10,23 @@ using namespace aas_lmfb;
 extern "C" int emu_stft_tile(const float* wave_row, int len, int t0, const float* window,
                              int vec_ok, float* re_out /*[161][32]*/, float* im_out /*[161][32]*/) {
     std::vector<float2> S(kSlots * kPitch);
-    for (int lane = 0; lane < 32; ++lane) stage_tile(lane, wave_row, len, t0, window, S.data(), vec_ok != 0);
-    for (int lane = 0; lane < 32; ++lane) { fft_pass1(S.data() + lane); fft_pass2(S.data() + lane); }
-    for (int lane = 0; lane < 32; ++lane)
-        for (int f = 0; f < kBins; ++f) {
-            const float2 v = load_bin(S.data() + lane, f);
-            re_out[f * 32 + lane] = v.x;
-            im_out[f * 32 + lane] = v.y;
+    // power-spectrum probes: 'reim' forward with masks (1,0) and (0,1) gives Re'^2 and Im'^2
+    std::vector<float> ones(kBins, 1.0f), zeros(kBins, 0.0f);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int lane = 0; lane < 32; ++lane) {
+            StageLane sl;
+            stage_lane_init(lane, window, sl);
+            stage_tile(lane, sl, wave_row, len, t0, S.data(), vec_ok != 0);
         }
+        for (int lane = 0; lane < 32; ++lane) {
+            float2* col = S.data() + lane;
+            fft_pass1(col);
+            fft_pass2_masked<kMaskReim, false>(col, pass == 0 ? ones.data() : zeros.data(),
+                                               pass == 0 ? zeros.data() : ones.data(), 1, true);
+            const float* colf = reinterpret_cast<const float*>(col);
+            for (int f = 0; f < kBins; ++f) (pass == 0 ? re_out : im_out)[f * 32 + lane] = colf[kBinOff[f]];
+        }
+    }
     return 0;
 }
 
@@ -52,8 +61,11 @@ static void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_ut
                 }
                 continue;
             }
-            for (int lane = 0; lane < 32; ++lane)
-                stage_tile(lane, wave + (long long)n * wave_stride, len, t0, window, S.data(), vec_ok != 0);
+            for (int lane = 0; lane < 32; ++lane) {
+                StageLane sl;
+                stage_lane_init(lane, window, sl);
+                stage_tile(lane, sl, wave + (long long)n * wave_stride, len, t0, S.data(), vec_ok != 0);
+            }
             for (int lane = 0; lane < 32; ++lane) {
                 const int t = t0 + lane;
                 const bool inrow = t < tmax, valid = t < T;
@@ -61,10 +73,13 @@ static void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_ut
                 const long long moff = (long long)n * msn + t;
                 float2* col = S.data() + lane;
                 fft_pass1(col);
-                fft_pass2(col);
-                if (!bwd) phase3_fwd<MASK>(col, mb, mask_r + moff, mask_i + moff, msf, out + row_nm, som, inrow, valid);
-                else      phase3_bwd<MASK>(col, mb, mask_r + moff, mask_i + moff, msf, dE + row_nm, som,
-                                           gr + moff, gi + moff, msf, inrow);
+                if (!bwd) {
+                    fft_pass2_masked<MASK, false>(col, mask_r + moff, mask_i + moff, msf, inrow);
+                    phase3_fwd(col, mb, out + row_nm, som, inrow, valid);
+                } else {
+                    fft_pass2_masked<MASK, true>(col, mask_r + moff, mask_i + moff, msf, inrow);
+                    phase3_bwd<MASK>(col, mb, dE + row_nm, som, gr + moff, gi + moff, msf, inrow);
+                }
             }
         }
 }

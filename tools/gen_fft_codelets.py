@@ -237,6 +237,23 @@ def main():
     parts.append("// real-split twiddles (sin, cos of 2*pi*f/320) for bin f = (96*k1 + 65*k2) mod 160, [k2][k1]")
     parts.append("LMFB_CONST float kSplitSin[17][5] = {\n  {" + "},\n  {".join(sin_rows) + "}};")
     parts.append("LMFB_CONST float kSplitCos[17][5] = {\n  {" + "},\n  {".join(cos_rows) + "}};")
+    # bin handled by (k2, k1) in pass 2, and the float offset of bin f inside a scratch column
+    rows = []
+    for k2 in range(17):
+        rows.append(", ".join(str((96 * k1 + 65 * k2) % 160) for k1 in range(5)))
+    parts.append("// bin f = (96*k1 + 65*k2) mod 160 produced by pass-2 step k2, output k1")
+    parts.append("LMFB_CONST unsigned char kBinOf[17][5] = {\n  {" + "},\n  {".join(rows) + "}};")
+    pitch = 33
+    offs = []
+    for f in range(161):
+        if f == 0:
+            offs.append(0)
+        elif f == 160:
+            offs.append(1)
+        else:
+            offs.append(((f % 5) * 32 + (f % 32)) * pitch * 2)
+    parts.append("// float offset of bin f in a finished scratch column (slot*kPitch*2; bin 160 is slot 0 .y)")
+    parts.append("LMFB_CONST unsigned short kBinOff[161] = {" + ", ".join(str(o) for o in offs) + "};")
     parts.append("}  // namespace aas_lmfb")
     with open(OUT, "w") as f:
         f.write("\n".join(parts) + "\n")
