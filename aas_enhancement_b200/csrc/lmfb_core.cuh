@@ -55,14 +55,18 @@ constexpr int kScratchBytes = kSlots * kPitch * 8;     // 42,240 B per warp
 enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2 };
 
 // Banded-2 description of the mel basis, passed by value as a kernel parameter (constant
-// bank).  Bin f feeds filters ml[f] (weight wl[f]) and ml[f]+1 (weight wh[f]); ml is
-// non-decreasing.  Weights already carry the 1/4 that undoes X' = 2X.
+// bank).  Bin f feeds filters ml(f) (weight wl) and ml(f)+1 (weight wh) with ml non-decreasing,
+// so the bins whose lower filter is m form the contiguous range [fend[m-1], fend[m]).
+// Weights already carry the 1/4 that undoes X' = 2X.
+struct BinEnt {
+    float    wl, wh;
+    uint32_t off;      // float offset of the bin's payload inside a scratch column
+    uint32_t sel;      // 0: regular bin; 1: bin 0 (.x of slot 0, real); 2: bin 160 (.y of slot 0, real)
+};
 struct MelBand {
-    float   wl[kBins];
-    float   wh[kBins];
-    uint8_t ml[kBins];
-    uint8_t n_mels;
-    uint8_t pad_[2];
+    BinEnt  ent[kBins];
+    uint8_t fend[kMaxMels];
+    int     n_mels;
 };
 
 LMFB_HD int slot_of_packed(int j) {            // j in [0,160): packed-sample index -> PFA input slot
@@ -84,7 +88,7 @@ LMFB_HD int reflect_index(int i, int len) {
 // Staging: copy the (32+1)*160 samples a tile needs into the 32 private frame columns,
 // windowed and permuted into PFA input order.  Lanes run along the packed-sample index, so
 // global reads are coalesced 256-byte runs and the scratch writes are conflict-free.
-// Rows are loaded four at a time (12 independent 8-byte loads in flight per lane).
+// Rows are loaded eight at a time (24 independent 8-byte loads in flight per lane).
 // ---------------------------------------------------------------------------------------
 struct StageLane {                      // per-lane constants of the staging map
     int   slot_a[3], slot_b[3];
@@ -144,7 +148,7 @@ LMFB_HD void stage_rows_slow(int lane, const StageLane& sl, const float* __restr
 
 LMFB_HD void stage_tile(int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
                         int t0, float2* __restrict__ S, bool vec_ok) {
-    constexpr int kRowsPerBatch = 4;               // rows 0..31 in 8 batches, row 32 on its own
+    constexpr int kRowsPerBatch = 8;               // rows 0..31 in 4 batches, row 32 on its own
 #pragma unroll 1
     for (int r0 = 0; r0 < kTile; r0 += kRowsPerBatch) {
         if (!rows_interior(t0 + r0 - 1, t0 + r0 - 1 + kRowsPerBatch, len, vec_ok)) {
@@ -314,64 +318,87 @@ LMFB_HD void fft_pass2_masked(float2* __restrict__ col, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 3 (forward): banded mel accumulation over ascending bins + log1p on completion.
+// phase 3 (forward): banded mel accumulation, filter by filter, + log1p on completion.
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
 LMFB_HD void phase3_fwd(const float2* __restrict__ col, const MelBand& mb,
                         float* __restrict__ out, long long som, bool inrow, bool valid) {
     const float* colf = reinterpret_cast<const float*>(col);
     const int n_mels = mb.n_mels;
-    int m = 0;
+    int f = 0;
     float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll 1
-    for (int f = 0; f <= kBins; ++f) {                    // f == kBins: sentinel that flushes the rest
-        const int ml = f < kBins ? (int)mb.ml[f] : n_mels;
-#pragma unroll 1
-        while (m < ml) {
-            const float y = valid ? log1pf(acc0) : 0.0f;
-            if (inrow) out[(long long)m * som] = y;
-            acc0 = acc1; acc1 = 0.0f; ++m;
+    for (int m = 0; m < n_mels; ++m) {
+        const int fe = mb.fend[m];
+#pragma unroll 4
+        for (; f < fe; ++f) {
+            const float p = colf[mb.ent[f].off];
+            acc0 = fmaf(mb.ent[f].wl, p, acc0);
+            acc1 = fmaf(mb.ent[f].wh, p, acc1);
         }
-        if (f < kBins) {
-            const float p = colf[kBinOff[f]];
-            acc0 = fmaf(mb.wl[f], p, acc0);
-            acc1 = fmaf(mb.wh[f], p, acc1);
-        }
+        const float y = valid ? log1pf(acc0) : 0.0f;
+        if (inrow) out[(long long)m * som] = y;
+        acc0 = acc1;
+        acc1 = 0.0f;
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 3 (backward): dP[f] = wl*dE[ml] + wh*dE[ml+1]; gradients = factors * dP.
-//   dE : dE + n*stride_n + t (row m at + m*sem), zero for frames t >= T_i
+// phase 3 (backward): dP[f] = wl*dE[ml] + wh*dE[ml+1]; gradients = payload * dP.
+//   dE : dE + n*stride_n + t (row m at + m*sem), zero for frames t >= T_i.  The dE values are
+//   consumed in filter order through a sliding register window kDWin filters deep, which the
+//   caller pre-loads (before the FFT) with dE[0..kDWin).
 // ---------------------------------------------------------------------------------------
+constexpr int kDWin = 12;
+
+LMFB_HD void dwin_preload(const float* __restrict__ dE, long long sem, int n_mels, bool inrow,
+                          float (&dw)[kDWin]) {
+#pragma unroll
+    for (int i = 0; i < kDWin; ++i) dw[i] = (inrow && i < n_mels) ? LMFB_LDG(dE + (long long)i * sem) : 0.0f;
+}
+
 template <int MASK>
 LMFB_HD void phase3_bwd(const float2* __restrict__ col, const MelBand& mb,
-                        const float* __restrict__ dE, long long sem,
+                        const float* __restrict__ dE, long long sem, float (&dw)[kDWin],
                         float* __restrict__ gr, float* __restrict__ gi, long long gsf, bool inrow) {
-    const float* colf = reinterpret_cast<const float*>(col);
     const int n_mels = mb.n_mels;
-    int m = 0;
-    float d0 = (inrow && 0 < n_mels) ? LMFB_LDG(dE) : 0.0f;
-    float d1 = (inrow && 1 < n_mels) ? LMFB_LDG(dE + sem) : 0.0f;
-    float d2 = (inrow && 2 < n_mels) ? LMFB_LDG(dE + 2 * sem) : 0.0f;
-    float d3 = (inrow && 3 < n_mels) ? LMFB_LDG(dE + 3 * sem) : 0.0f;
+    int f = 0;
 #pragma unroll 1
-    for (int f = 0; f < kBins; ++f) {
-        const int ml = mb.ml[f];
-#pragma unroll 1
-        while (m < ml) {
-            d0 = d1; d1 = d2; d2 = d3; ++m;
-            d3 = (inrow && m + 3 < n_mels) ? LMFB_LDG(dE + (long long)(m + 3) * sem) : 0.0f;
+    for (int m = 0; m < n_mels; ++m) {
+        const int fe = mb.fend[m];
+        const float d0 = dw[0], d1 = dw[1];
+#pragma unroll 2
+        for (; f < fe; ++f) {
+            const uint32_t off = mb.ent[f].off, sel = mb.ent[f].sel;
+            const float dp = fmaf(mb.ent[f].wh, d1, mb.ent[f].wl * d0);
+            const float2 v = col[off >> 1];
+            const float a = sel == 2u ? v.y : v.x;
+            const float b = sel != 0u ? 0.0f : v.y;
+            if (inrow) {
+                gr[(long long)f * gsf] = a * dp;
+                if (MASK == kMaskReim) gi[(long long)f * gsf] = b * dp;
+            }
         }
-        const float dp = fmaf(mb.wh[f], d1, mb.wl[f] * d0);
-        const int off = kBinOff[f];
-        const float a = colf[off];
-        const float b = (f == 0 || f == kBins - 1) ? 0.0f : colf[off + 1];
-        if (inrow) {
-            gr[(long long)f * gsf] = a * dp;
-            if (MASK == kMaskReim) gi[(long long)f * gsf] = b * dp;
+#pragma unroll
+        for (int i = 0; i + 1 < kDWin; ++i) dw[i] = dw[i + 1];
+        dw[kDWin - 1] = (inrow && m + kDWin < n_mels) ? LMFB_LDG(dE + (long long)(m + kDWin) * sem) : 0.0f;
+    }
+    if (inrow) {
+#pragma unroll 1
+        for (; f < kBins; ++f) {                         // bins above the last filter: no gradient
+            gr[(long long)f * gsf] = 0.0f;
+            if (MASK == kMaskReim) gi[(long long)f * gsf] = 0.0f;
         }
     }
+}
+
+// L2 prefetch of the (32+1)*160 samples of a tile (165 lines of 128 B)
+LMFB_HD void prefetch_wave_l2(int lane, const float* __restrict__ wave_row, int len, int t0) {
+    long long lo = (long long)(t0 - 1) * kHop, hi = (long long)(t0 + kTile) * kHop;
+    if (lo < 0) lo = 0;
+    if (hi > len) hi = len;
+#pragma unroll 1
+    for (long long i = lo + lane * 32; i < hi; i += 32 * 32) LMFB_PREFETCH_L2(wave_row + i);
 }
 
 // L2 prefetch of the mask rows a tile will read: lanes take rows lane, lane+32, ...; a 128-byte

@@ -87,13 +87,25 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(lane, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (BWD) prefetch_rows_l2(lane, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
 
+        // ... and the next tile's samples, so that its staging loads hit L2
+        {
+            const int nt = tile + gridDim.x;
+            if (nt < a.total_tiles) {
+                const int nn = nt / a.tiles_per_utt;
+                prefetch_wave_l2(lane, a.wave + (long long)nn * a.wave_stride, a.lengths[nn],
+                                 (nt - nn * a.tiles_per_utt) * kTile);
+            }
+        }
+
         __syncwarp();                               // previous tile's columns are no longer read
         stage_tile(lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
         __syncwarp();
+        float dw[kDWin];
+        if (BWD) dwin_preload(a.dE + row_nm, som, n_mels, inrow, dw);
         fft_pass1(col);
         fft_pass2_masked<MASK, BWD>(col, a.mask_r + moff, a.mask_i + moff, a.msf, inrow);
         if (!BWD) phase3_fwd(col, mb, a.out + row_nm, som, inrow, valid);
-        else      phase3_bwd<MASK>(col, mb, a.dE + row_nm, som, a.gr + moff, a.gi + moff, a.msf, inrow);
+        else      phase3_bwd<MASK>(col, mb, a.dE + row_nm, som, dw, a.gr + moff, a.gi + moff, a.msf, inrow);
     }
 }
 

@@ -77,8 +77,10 @@ static void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_ut
                     fft_pass2_masked<MASK, false>(col, mask_r + moff, mask_i + moff, msf, inrow);
                     phase3_fwd(col, mb, out + row_nm, som, inrow, valid);
                 } else {
+                    float dw[kDWin];
+                    dwin_preload(dE + row_nm, som, n_mels, inrow, dw);
                     fft_pass2_masked<MASK, true>(col, mask_r + moff, mask_i + moff, msf, inrow);
-                    phase3_bwd<MASK>(col, mb, dE + row_nm, som, gr + moff, gi + moff, msf, inrow);
+                    phase3_bwd<MASK>(col, mb, dE + row_nm, som, dw, gr + moff, gi + moff, msf, inrow);
                 }
             }
         }
@@ -106,7 +108,15 @@ extern "C" int emu_k1(int bwd, int mask_mode, const float* wave, const int* leng
 extern "C" int emu_mel_band(const float* mel, int n_mels, float* wl, float* wh, int* ml) {
     MelBand mb;
     memset(&mb, 0, sizeof(mb));
-    const int rc = build_mel_band(mel, n_mels, &mb);
-    for (int f = 0; f < kBins; ++f) { wl[f] = mb.wl[f]; wh[f] = mb.wh[f]; ml[f] = mb.ml[f]; }
+    const int rc = build_mel_band(mel, n_mels, &mb, ml);
+    for (int f = 0; f < kBins; ++f) { wl[f] = mb.ent[f].wl; wh[f] = mb.ent[f].wh; }
+    // the filter ranges must tile the bins in order
+    if (rc == 0) {
+        int f = 0;
+        for (int m = 0; m < n_mels; ++m) {
+            for (; f < mb.fend[m]; ++f) if (ml[f] != m) return -100 - m;
+        }
+        for (; f < kBins; ++f) if (ml[f] != n_mels) return -300;
+    }
     return rc;
 }
