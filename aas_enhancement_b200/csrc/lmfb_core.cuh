@@ -248,85 +248,91 @@ LMFB_HD float2 bin_payload(float2 x, float mr, float mi) {
 #define LMFB_NEEDS_MASK_R(MASK, BWD) ((BWD) ? (MASK) == kMaskReim : (MASK) != kMaskNone)
 #define LMFB_NEEDS_MASK_I(MASK, BWD) ((MASK) == kMaskReim)
 
-// mask values of the ten bins of pass-2 step k2: index k1 -> bin f, index 5+k1 -> bin 160-f
+// mask values of the ten bins of pass-2 step k2: index k1 -> bin f, index 5+k1 -> bin 160-f.
+// mr/mi point at a column that is always readable (out-of-row lanes are clamped by the caller),
+// so the loads carry no predicate; sf (floats per mask row) fits 32 bits.
 template <int MASK, bool BWD>
 LMFB_HD void load_step_masks(int k2, const float* __restrict__ mr, const float* __restrict__ mi,
-                             long long sf, bool inrow, float (&vr)[10], float (&vi)[10]) {
-    const bool self = (k2 & 15) == 0;                 // k2 == 0 or 16: self-paired column
+                             unsigned sf, float (&vr)[10], float (&vi)[10]) {
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
+        const unsigned f = kBinOf[k2][k1];
+        const unsigned of = f * sf, op = (kBins - 1 - f) * sf;
         vr[k1] = vr[5 + k1] = vi[k1] = vi[5 + k1] = 0.0f;
-        if (!inrow || (self && k1 >= 3)) continue;
-        const int f = kBinOf[k2][k1];
-        const int fp = kBins - 1 - f;
-        if (LMFB_NEEDS_MASK_R(MASK, BWD)) {
-            vr[k1] = LMFB_LDG(mr + (long long)f * sf);
-            vr[5 + k1] = LMFB_LDG(mr + (long long)fp * sf);
-        }
-        if (LMFB_NEEDS_MASK_I(MASK, BWD)) {
-            vi[k1] = LMFB_LDG(mi + (long long)f * sf);
-            vi[5 + k1] = LMFB_LDG(mi + (long long)fp * sf);
-        }
+        if (LMFB_NEEDS_MASK_R(MASK, BWD)) { vr[k1] = LMFB_LDG(mr + of); vr[5 + k1] = LMFB_LDG(mr + op); }
+        if (LMFB_NEEDS_MASK_I(MASK, BWD)) { vi[k1] = LMFB_LDG(mi + of); vi[5 + k1] = LMFB_LDG(mi + op); }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// pass 2: radix-5 across the five sub-transforms + real split + mask, in place.
-//   mr/mi : mask_r/mask_i + n*stride_n + t  (row f at + f*sf), only dereferenced if inrow
+// pass 2, one step: columns k2 and kb = (32-k2) mod 32 of the five sub-transforms -> two 5-point
+// DFTs -> real split -> ten bins -> mask -> payload, in place.  Branch-free and identical for
+// all k2: the self-paired columns (k2 = 0, 16, where kb == k2) simply compute each of their
+// bins twice; only bins 0/160 (k2 = 0, k1 = 0), which share slot 0, need a select.
 // ---------------------------------------------------------------------------------------
 template <int MASK, bool BWD>
-LMFB_HD void fft_pass2_masked(float2* __restrict__ col, const float* __restrict__ mr,
-                              const float* __restrict__ mi, long long sf, bool inrow) {
-    float cr[10], ci[10], nr[10], ni[10];
-    load_step_masks<MASK, BWD>(0, mr, mi, sf, inrow, cr, ci);
-#pragma unroll 1
-    for (int k2 = 0; k2 <= 16; ++k2) {
-        if (k2 < 16) load_step_masks<MASK, BWD>(k2 + 1, mr, mi, sf, inrow, nr, ni);
-        const bool self = (k2 & 15) == 0;
-        const int kb = (32 - k2) & 31;
-        float ar[5], ai[5], Ar[5], Ai[5], Br[5], Bi[5];
+LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const float (&vr)[10], const float (&vi)[10]) {
+    const int kb = (32 - k2) & 31;
+    float2* ca = col + k2 * kPitch;
+    float2* cb = col + kb * kPitch;
+    float ar[5], ai[5], br[5], bi[5], Ar[5], Ai[5], Br[5], Bi[5];
 #pragma unroll
-        for (int n = 0; n < 5; ++n) { const float2 v = col[(n * 32 + k2) * kPitch]; ar[n] = v.x; ai[n] = v.y; }
-        dft5(ar, ai, Ar, Ai);
-        if (self) {
+    for (int n = 0; n < 5; ++n) {
+        const float2 v = ca[n * 32 * kPitch]; ar[n] = v.x; ai[n] = v.y;
+        const float2 w = cb[n * 32 * kPitch]; br[n] = w.x; bi[n] = w.y;
+    }
+    dft5(ar, ai, Ar, Ai);
+    dft5(br, bi, Br, Bi);
 #pragma unroll
-            for (int n = 0; n < 5; ++n) { Br[n] = Ar[n]; Bi[n] = Ai[n]; }
-        } else {
-            float br[5], bi[5];
-#pragma unroll
-            for (int n = 0; n < 5; ++n) { const float2 v = col[(n * 32 + kb) * kPitch]; br[n] = v.x; bi[n] = v.y; }
-            dft5(br, bi, Br, Bi);
+    for (int k1 = 0; k1 < 5; ++k1) {
+        const int kp = (5 - k1) % 5;
+        float2 xf, xp;
+        split_pair(Ar[k1], Ai[k1], Br[kp], Bi[kp], kSplitSin[k2][k1], kSplitCos[k2][k1], xf, xp);
+        float2 pf = bin_payload<MASK, BWD>(xf, vr[k1], vi[k1]);
+        float2 pp = bin_payload<MASK, BWD>(xp, vr[5 + k1], vi[5 + k1]);
+        if (k1 == 0) {                                    // bins 0 and 160 (real) share slot 0
+            const bool z = k2 == 0;
+            pf = make_float2(pf.x, z ? pp.x : pf.y);
+            pp = make_float2(z ? pf.x : pp.x, z ? pf.y : pp.y);
         }
-#pragma unroll
-        for (int k1 = 0; k1 < 5; ++k1) {
-            if (self && k1 >= 3) continue;                    // partners of k1 = 2, 1
-            const int kp = (5 - k1) % 5;
-            float2 xf, xp;
-            split_pair(Ar[k1], Ai[k1], Br[kp], Bi[kp], kSplitSin[k2][k1], kSplitCos[k2][k1], xf, xp);
-            const float2 pf = bin_payload<MASK, BWD>(xf, cr[k1], ci[k1]);
-            const float2 pp = bin_payload<MASK, BWD>(xp, cr[5 + k1], ci[5 + k1]);
-            if (k1 == 0 && k2 == 0) {
-                col[0] = make_float2(pf.x, pp.x);             // bins 0 and 160 (real) share slot 0
-            } else {
-                col[(k1 * 32 + k2) * kPitch] = pf;
-                col[(kp * 32 + kb) * kPitch] = pp;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 10; ++i) { cr[i] = nr[i]; ci[i] = ni[i]; }
+        ca[k1 * 32 * kPitch] = pf;
+        cb[kp * 32 * kPitch] = pp;
     }
 }
 
+// pass 2 over all 17 columns, two at a time; the masks of the next pair are loaded into
+// registers while the current pair is being computed.
+template <int MASK, bool BWD>
+LMFB_HD void fft_pass2_masked(float2* __restrict__ col, const float* __restrict__ mr,
+                              const float* __restrict__ mi, unsigned sf) {
+    float r0[10], i0[10], r1[10], i1[10];
+    load_step_masks<MASK, BWD>(0, mr, mi, sf, r0, i0);
+    load_step_masks<MASK, BWD>(1, mr, mi, sf, r1, i1);
+#pragma unroll 1
+    for (int k2 = 0; k2 < 16; k2 += 2) {
+        float nr0[10], ni0[10], nr1[10], ni1[10];
+        load_step_masks<MASK, BWD>(k2 + 2, mr, mi, sf, nr0, ni0);
+        if (k2 + 3 <= 16) load_step_masks<MASK, BWD>(k2 + 3, mr, mi, sf, nr1, ni1);
+        pass2_step<MASK, BWD>(col, k2, r0, i0);
+        pass2_step<MASK, BWD>(col, k2 + 1, r1, i1);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) { r0[i] = nr0[i]; i0[i] = ni0[i]; r1[i] = nr1[i]; i1[i] = ni1[i]; }
+    }
+    pass2_step<MASK, BWD>(col, 16, r0, i0);
+}
+
 // ---------------------------------------------------------------------------------------
-// phase 3 (forward): banded mel accumulation, filter by filter, + log1p on completion.
+// phase 3 (forward): banded mel accumulation filter by filter (E[m] parked in the free .y of
+// slot 1+m), then log1p + store for all filters in an unrolled second sweep.
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
-LMFB_HD void phase3_fwd(const float2* __restrict__ col, const MelBand& mb,
-                        float* __restrict__ out, long long som, bool inrow, bool valid) {
-    const float* colf = reinterpret_cast<const float*>(col);
+LMFB_HD void phase3_fwd(float2* __restrict__ col, const MelBand& mb,
+                        float* __restrict__ out, unsigned som, bool inrow, bool valid) {
+    float* colf = reinterpret_cast<float*>(col);
     const int n_mels = mb.n_mels;
     int f = 0;
     float acc0 = 0.0f, acc1 = 0.0f;
+    float* ep = colf + 2 * kPitch + 1;                    // slot 1, .y
 #pragma unroll 1
     for (int m = 0; m < n_mels; ++m) {
         const int fe = mb.fend[m];
@@ -336,58 +342,72 @@ LMFB_HD void phase3_fwd(const float2* __restrict__ col, const MelBand& mb,
             acc0 = fmaf(mb.ent[f].wl, p, acc0);
             acc1 = fmaf(mb.ent[f].wh, p, acc1);
         }
-        const float y = valid ? log1pf(acc0) : 0.0f;
-        if (inrow) out[(long long)m * som] = y;
+        *ep = acc0;
+        ep += 2 * kPitch;
         acc0 = acc1;
         acc1 = 0.0f;
+    }
+    ep = colf + 2 * kPitch + 1;
+#pragma unroll 8
+    for (int m = 0; m < n_mels; ++m) {
+        const float y = valid ? log1pf(ep[m * 2 * kPitch]) : 0.0f;
+        if (inrow) out[(unsigned)m * som] = y;
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // phase 3 (backward): dP[f] = wl*dE[ml] + wh*dE[ml+1]; gradients = payload * dP.
-//   dE : dE + n*stride_n + t (row m at + m*sem), zero for frames t >= T_i.  The dE values are
-//   consumed in filter order through a sliding register window kDWin filters deep, which the
-//   caller pre-loads (before the FFT) with dE[0..kDWin).
+//   dE : dE + n*stride_n + t (row m at + m*sem), zero for frames t >= T_i; readable for every
+//   lane (clamped by the caller).  The dE values are consumed in filter order through a sliding
+//   register window: filters are handled four at a time and the window runs kDAhead filters
+//   ahead; the caller pre-loads it (before the FFT) with dE[0 .. kDWin).
 // ---------------------------------------------------------------------------------------
-constexpr int kDWin = 12;
+constexpr int kDAhead = 8;
+constexpr int kDWin = 5 + kDAhead;                        // d[j], d[j+1] for j < 4, plus the look-ahead
 
-LMFB_HD void dwin_preload(const float* __restrict__ dE, long long sem, int n_mels, bool inrow,
-                          float (&dw)[kDWin]) {
+LMFB_HD void dwin_preload(const float* __restrict__ dE, unsigned sem, int n_mels, float (&dw)[kDWin]) {
 #pragma unroll
-    for (int i = 0; i < kDWin; ++i) dw[i] = (inrow && i < n_mels) ? LMFB_LDG(dE + (long long)i * sem) : 0.0f;
+    for (int i = 0; i < kDWin; ++i) dw[i] = i < n_mels ? LMFB_LDG(dE + (unsigned)i * sem) : 0.0f;
 }
 
 template <int MASK>
 LMFB_HD void phase3_bwd(const float2* __restrict__ col, const MelBand& mb,
-                        const float* __restrict__ dE, long long sem, float (&dw)[kDWin],
-                        float* __restrict__ gr, float* __restrict__ gi, long long gsf, bool inrow) {
+                        const float* __restrict__ dE, unsigned sem, float (&dw)[kDWin],
+                        float* __restrict__ gr, float* __restrict__ gi, unsigned gsf, bool inrow) {
     const int n_mels = mb.n_mels;
     int f = 0;
 #pragma unroll 1
-    for (int m = 0; m < n_mels; ++m) {
-        const int fe = mb.fend[m];
-        const float d0 = dw[0], d1 = dw[1];
+    for (int m0 = 0; m0 < n_mels; m0 += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (m0 + j < n_mels) {
+                const int fe = mb.fend[m0 + j];
+                const float d0 = dw[j], d1 = dw[j + 1];
 #pragma unroll 2
-        for (; f < fe; ++f) {
-            const uint32_t off = mb.ent[f].off, sel = mb.ent[f].sel;
-            const float dp = fmaf(mb.ent[f].wh, d1, mb.ent[f].wl * d0);
-            const float2 v = col[off >> 1];
-            const float a = sel == 2u ? v.y : v.x;
-            const float b = sel != 0u ? 0.0f : v.y;
-            if (inrow) {
-                gr[(long long)f * gsf] = a * dp;
-                if (MASK == kMaskReim) gi[(long long)f * gsf] = b * dp;
+                for (; f < fe; ++f) {
+                    const uint32_t off = mb.ent[f].off, sel = mb.ent[f].sel;
+                    const float dp = fmaf(mb.ent[f].wh, d1, mb.ent[f].wl * d0);
+                    const float2 v = col[off >> 1];
+                    const float a = sel == 2u ? v.y : v.x;
+                    const float b = sel != 0u ? 0.0f : v.y;
+                    if (inrow) gr[(unsigned)f * gsf] = a * dp;
+                    if (MASK == kMaskReim) { if (inrow) gi[(unsigned)f * gsf] = b * dp; }
+                }
             }
         }
 #pragma unroll
-        for (int i = 0; i + 1 < kDWin; ++i) dw[i] = dw[i + 1];
-        dw[kDWin - 1] = (inrow && m + kDWin < n_mels) ? LMFB_LDG(dE + (long long)(m + kDWin) * sem) : 0.0f;
+        for (int i = 0; i + 4 < kDWin; ++i) dw[i] = dw[i + 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + kDWin + i;
+            dw[kDWin - 4 + i] = m < n_mels ? LMFB_LDG(dE + (unsigned)m * sem) : 0.0f;
+        }
     }
     if (inrow) {
 #pragma unroll 1
         for (; f < kBins; ++f) {                         // bins above the last filter: no gradient
-            gr[(long long)f * gsf] = 0.0f;
-            if (MASK == kMaskReim) gi[(long long)f * gsf] = 0.0f;
+            gr[(unsigned)f * gsf] = 0.0f;
+            if (MASK == kMaskReim) gi[(unsigned)f * gsf] = 0.0f;
         }
     }
 }
@@ -403,13 +423,13 @@ LMFB_HD void prefetch_wave_l2(int lane, const float* __restrict__ wave_row, int 
 
 // L2 prefetch of the mask rows a tile will read: lanes take rows lane, lane+32, ...; a 128-byte
 // row segment may straddle two lines, so both ends are touched.
-LMFB_HD void prefetch_rows_l2(int lane, const float* __restrict__ base, long long sf, int rows, int t0, int tmax) {
+LMFB_HD void prefetch_rows_l2(int lane, const float* __restrict__ base, unsigned sf, int rows, int t0, int tmax) {
     if (t0 >= tmax) return;
     const int last = (t0 + kTile <= tmax ? t0 + kTile : tmax) - 1;
 #pragma unroll 1
     for (int f = lane; f < rows; f += 32) {
-        LMFB_PREFETCH_L2(base + (long long)f * sf + t0);
-        LMFB_PREFETCH_L2(base + (long long)f * sf + last);
+        LMFB_PREFETCH_L2(base + (unsigned)f * sf + t0);
+        LMFB_PREFETCH_L2(base + (unsigned)f * sf + last);
     }
 }
 

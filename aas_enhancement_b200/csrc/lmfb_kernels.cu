@@ -30,7 +30,8 @@ struct K1Args {
     long long      wave_stride;
     const float*   mask_r;
     const float*   mask_i;
-    long long      msn, msf;
+    long long      msn;
+    unsigned       msf;
     const float*   window;
     float*         out;        // forward: (N, M, Tmax), receives log1p(E)
     const float*   dE;         // backward: (N, M, Tmax)
@@ -48,7 +49,6 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     extern __shared__ __align__(16) float2 S[];
     const int lane = threadIdx.x;
     const int n_mels = mb.n_mels;
-    const long long som = a.tmax;
     StageLane sl;
     stage_lane_init(lane, a.window, sl);
     float2* col = S + lane;
@@ -63,6 +63,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         T = T < a.tmax ? T : a.tmax;
         const bool inrow = t < a.tmax;
         const bool valid = t < T;
+        const unsigned som = (unsigned)a.tmax;
         const long long row_nm = (long long)n * n_mels * som + t;
         const long long moff = (long long)n * a.msn + t;
 
@@ -70,12 +71,12 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
             if (inrow) {
                 if (!BWD) {
 #pragma unroll 4
-                    for (int m = 0; m < n_mels; ++m) a.out[row_nm + m * som] = 0.0f;
+                    for (int m = 0; m < n_mels; ++m) a.out[row_nm + (unsigned)m * som] = 0.0f;
                 } else if (MASK != kMaskNone) {
 #pragma unroll 4
                     for (int f = 0; f < kBins; ++f) {
-                        a.gr[moff + f * a.msf] = 0.0f;
-                        if (MASK == kMaskReim) a.gi[moff + f * a.msf] = 0.0f;
+                        a.gr[moff + (unsigned)f * a.msf] = 0.0f;
+                        if (MASK == kMaskReim) a.gi[moff + (unsigned)f * a.msf] = 0.0f;
                     }
                 }
             }
@@ -86,7 +87,6 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(lane, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(lane, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (BWD) prefetch_rows_l2(lane, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
-
         // ... and the next tile's samples, so that its staging loads hit L2
         {
             const int nt = tile + gridDim.x;
@@ -100,12 +100,14 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         __syncwarp();                               // previous tile's columns are no longer read
         stage_tile(lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
         __syncwarp();
+        // loads of out-of-row lanes are redirected to the last column of the row (always readable)
+        const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
         float dw[kDWin];
-        if (BWD) dwin_preload(a.dE + row_nm, som, n_mels, inrow, dw);
+        if (BWD) dwin_preload(a.dE + row_nm + clamp, som, n_mels, dw);
         fft_pass1(col);
-        fft_pass2_masked<MASK, BWD>(col, a.mask_r + moff, a.mask_i + moff, a.msf, inrow);
+        fft_pass2_masked<MASK, BWD>(col, a.mask_r + moff + clamp, a.mask_i + moff + clamp, a.msf);
         if (!BWD) phase3_fwd(col, mb, a.out + row_nm, som, inrow, valid);
-        else      phase3_bwd<MASK>(col, mb, a.dE + row_nm, som, dw, a.gr + moff, a.gi + moff, a.msf, inrow);
+        else      phase3_bwd<MASK>(col, mb, a.dE + row_nm + clamp, som, dw, a.gr + moff, a.gi + moff, a.msf, inrow);
     }
 }
 
@@ -332,7 +334,7 @@ int check_common(const aas_lmfb_plan* plan, const float* wave, const int32_t* le
                  const float* mask_r, const float* mask_i, const float* window, int tmax,
                  uint32_t flags) {
     if (!plan || !window || (n > 0 && (!wave || !lengths))) return AAS_LMFB_E_NULL;
-    if (n < 0 || tmax < 1) return AAS_LMFB_E_SHAPE;
+    if (n < 0 || tmax < 1 || tmax > (1 << 24)) return AAS_LMFB_E_SHAPE;
     const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
     if (mask > 2u || cm > 2u || (flags >> 4)) return AAS_LMFB_E_FLAGS;
     if (mask != AAS_LMFB_MASK_NONE && !mask_r) return AAS_LMFB_E_NULL;
@@ -359,6 +361,7 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
     if (rc) return rc;
     if (n == 0) return AAS_LMFB_OK;
     const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
+    if (mask != AAS_LMFB_MASK_NONE && (mask_stride_f < tmax || mask_stride_f > (1 << 24))) return AAS_LMFB_E_SHAPE;
     if (!out || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
     if (((uintptr_t)out | (uintptr_t)stats) & 3u) return AAS_LMFB_E_ALIGN;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
@@ -366,7 +369,7 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
     K1Args a;
     memset(&a, 0, sizeof(a));
     a.wave = wave; a.lengths = lengths; a.wave_stride = wave_stride;
-    a.mask_r = mask_r; a.mask_i = mask_i; a.msn = mask_stride_n; a.msf = mask_stride_f;
+    a.mask_r = mask_r; a.mask_i = mask_i; a.msn = mask_stride_n; a.msf = (unsigned)mask_stride_f;
     a.window = window; a.out = out; a.tmax = tmax;
     a.tiles_per_utt = (tmax + kTile - 1) / kTile;
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
@@ -399,6 +402,7 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     if (n == 0) return AAS_LMFB_OK;
     const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
     if (mask == AAS_LMFB_MASK_NONE) return AAS_LMFB_E_FLAGS;        // nothing to differentiate into
+    if (mask_stride_f < tmax || mask_stride_f > (1 << 24)) return AAS_LMFB_E_SHAPE;
     if (!out || !grad_out || !workspace || !grad_mask_r || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
     if (mask == AAS_LMFB_MASK_REIM && !grad_mask_i) return AAS_LMFB_E_NULL;
     if (((uintptr_t)out | (uintptr_t)grad_out | (uintptr_t)workspace | (uintptr_t)grad_mask_r |
@@ -418,7 +422,7 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     K1Args a;
     memset(&a, 0, sizeof(a));
     a.wave = wave; a.lengths = lengths; a.wave_stride = wave_stride;
-    a.mask_r = mask_r; a.mask_i = mask_i; a.msn = mask_stride_n; a.msf = mask_stride_f;
+    a.mask_r = mask_r; a.mask_i = mask_i; a.msn = mask_stride_n; a.msf = (unsigned)mask_stride_f;
     a.window = window; a.dE = dE; a.gr = grad_mask_r; a.gi = grad_mask_i; a.tmax = tmax;
     a.tiles_per_utt = (tmax + kTile - 1) / kTile;
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;

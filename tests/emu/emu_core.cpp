@@ -22,7 +22,7 @@ extern "C" int emu_stft_tile(const float* wave_row, int len, int t0, const float
             float2* col = S.data() + lane;
             fft_pass1(col);
             fft_pass2_masked<kMaskReim, false>(col, pass == 0 ? ones.data() : zeros.data(),
-                                               pass == 0 ? zeros.data() : ones.data(), 1, true);
+                                               pass == 0 ? zeros.data() : ones.data(), 1u);
             const float* colf = reinterpret_cast<const float*>(col);
             for (int f = 0; f < kBins; ++f) (pass == 0 ? re_out : im_out)[f * 32 + lane] = colf[kBinOff[f]];
         }
@@ -71,16 +71,21 @@ static void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_ut
                 const bool inrow = t < tmax, valid = t < T;
                 const long long row_nm = (long long)n * n_mels * som + t;
                 const long long moff = (long long)n * msn + t;
+                const long long clamp = inrow ? 0 : (long long)(tmax - 1 - t);
+                const bool has_mask = MASK != kMaskNone;
                 float2* col = S.data() + lane;
                 fft_pass1(col);
                 if (!bwd) {
-                    fft_pass2_masked<MASK, false>(col, mask_r + moff, mask_i + moff, msf, inrow);
-                    phase3_fwd(col, mb, out + row_nm, som, inrow, valid);
+                    fft_pass2_masked<MASK, false>(col, mask_r + (has_mask ? moff + clamp : 0),
+                                                  mask_i + (MASK == kMaskReim ? moff + clamp : 0), (unsigned)msf);
+                    phase3_fwd(col, mb, out + row_nm, (unsigned)som, inrow, valid);
                 } else {
                     float dw[kDWin];
-                    dwin_preload(dE + row_nm, som, n_mels, inrow, dw);
-                    fft_pass2_masked<MASK, true>(col, mask_r + moff, mask_i + moff, msf, inrow);
-                    phase3_bwd<MASK>(col, mb, dE + row_nm, som, dw, gr + moff, gi + moff, msf, inrow);
+                    dwin_preload(dE + row_nm + clamp, (unsigned)som, n_mels, dw);
+                    fft_pass2_masked<MASK, true>(col, mask_r + (has_mask ? moff + clamp : 0),
+                                                 mask_i + (MASK == kMaskReim ? moff + clamp : 0), (unsigned)msf);
+                    phase3_bwd<MASK>(col, mb, dE + row_nm + clamp, (unsigned)som, dw, gr + moff, gi + moff,
+                                     (unsigned)msf, inrow);
                 }
             }
         }
