@@ -1,12 +1,15 @@
 // Per-thread building blocks of the fused STFT -> mask -> mel (-> log1p) kernels.
 //
-// Execution model ("lane = frame"): one warp owns a tile of 32 consecutive frames of one
-// utterance and lane t does the whole 320-point real FFT of frame t0+t by itself, using a
-// private column of shared memory as scratch.  Consequences:
+// Execution model ("lane = frame"): a CTA of W warps owns a tile of 32 consecutive frames of
+// one utterance.  Lane t of EVERY warp works on frame t0+t, whose 320-point real FFT lives in
+// column t of a shared-memory scratch; the W warps split the independent pieces of that FFT
+// between them (sub-transforms in pass 1, column pairs in pass 2, filter ranges in phase 3) and
+// meet at block barriers between the passes.  Consequences:
 //   * every twiddle is a literal (the FFT code is identical for all lanes),
 //   * every global access of a (N, F, T)/(N, M, T) tensor has the lanes along T, i.e. is a
 //     128-byte coalesced row segment -- no transposition is ever needed,
-//   * no block-level synchronisation (only __syncwarp around staging).
+//   * W times more warps are resident per SM for the same shared memory (the scratch, 42 KB per
+//     32 frames, is what limits residency), which is what hides the load and FFT latencies.
 //
 // Real FFT of 320 samples = complex FFT of the 160 packed samples z[j] = x[2j] + i x[2j+1],
 // computed with the Good-Thomas prime-factor map 160 = 5 x 32 (no inter-stage twiddles):
@@ -14,11 +17,12 @@
 //   pass 1 : five 32-point FFTs in registers (generated codelet), in place in the scratch
 //   pass 2 : for each index pair (k2, 32-k2): two 5-point DFTs + the real-split butterfly give
 //            ten bins; the mask(s) for those ten bins (prefetched one step ahead into
-//            registers, lanes along T) are applied at once and the masked power (forward) or
-//            the mask-gradient factors (backward) replace the spectrum in place.  Bin f lives
-//            in slot (f mod 5)*32 + (f mod 32); bins 0 and 160 (both real) share slot 0.
-//   phase 3: walk the bins in ascending order out of the scratch: banded mel accumulation +
-//            log1p (forward), or dP * factors -> mask gradients (backward).
+//            registers, lanes along T) are applied at once.  Forward: the masked power replaces
+//            the spectrum in place (bin f lives in slot (f mod 5)*32 + (f mod 32); bins 0 and
+//            160, both real, share slot 0).  Backward: dP of the ten bins is formed from dE and
+//            the mask gradients are stored straight from here -- there is no phase 3.
+//   phase 3: (forward only) banded mel accumulation over ascending bins out of the scratch,
+//            then log1p.
 // The spectrum is kept as X' = 2 X (the 1/2 of the split is folded into the mel weights as
 // 1/4, exact in binary floating point).
 //
@@ -46,13 +50,18 @@ namespace aas_lmfb {
 constexpr int kNfft  = 320;
 constexpr int kHop   = 160;
 constexpr int kBins  = 161;
-constexpr int kTile  = 32;             // frames per warp tile
+constexpr int kTile  = 32;             // frames per tile
 constexpr int kPitch = 33;             // float2 per scratch slot (32 lanes + 1 pad: conflict-free staging)
 constexpr int kSlots = 160;
 constexpr int kMaxMels = 128;
-constexpr int kScratchBytes = kSlots * kPitch * 8;     // 42,240 B per warp
+constexpr int kScratchBytes = kSlots * kPitch * 8;     // 42,240 B per tile
+constexpr int kMaxW = 8;               // most warps that may share a tile
 
 enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2 };
+
+// which mask tensors a kernel variant reads
+#define LMFB_NEEDS_MASK_R(MASK, BWD) ((BWD) ? (MASK) == kMaskReim : (MASK) != kMaskNone)
+#define LMFB_NEEDS_MASK_I(MASK, BWD) ((MASK) == kMaskReim)
 
 // Banded-2 description of the mel basis, passed by value as a kernel parameter (constant
 // bank).  Bin f feeds filters ml(f) (weight wl) and ml(f)+1 (weight wh) with ml non-decreasing,
@@ -60,12 +69,14 @@ enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2 };
 // Weights already carry the 1/4 that undoes X' = 2X.
 struct BinEnt {
     float    wl, wh;
-    uint32_t off;      // float offset of the bin's payload inside a scratch column
-    uint32_t sel;      // 0: regular bin; 1: bin 0 (.x of slot 0, real); 2: bin 160 (.y of slot 0, real)
+    uint32_t off;      // float offset of the bin's masked power inside a scratch column (forward)
+    uint32_t dd;       // backward: dlo | dhi << 8, the (always valid) dE rows that wl / wh multiply
 };
 struct MelBand {
     BinEnt  ent[kBins];
     uint8_t fend[kMaxMels];
+    uint8_t mbeg[kMaxW + 1];   // forward phase 3: warp w owns filters [mbeg[w], mbeg[w+1])
+    uint8_t pad_[3];
     int     n_mels;
 };
 
@@ -84,11 +95,22 @@ LMFB_HD int reflect_index(int i, int len) {
     return j >= len ? period - j : j;
 }
 
+#ifdef __CUDACC__
+// predicated 4-byte global store (keeps the store a single predicated instruction)
+__device__ __forceinline__ void st_if(float* p, float v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}"
+                 :: "l"(p), "f"(v), "r"((int)pred));
+}
+#else
+static inline void st_if(float* p, float v, bool pred) { if (pred) *p = v; }
+#endif
+
 // ---------------------------------------------------------------------------------------
-// Staging: copy the (32+1)*160 samples a tile needs into the 32 private frame columns,
-// windowed and permuted into PFA input order.  Lanes run along the packed-sample index, so
-// global reads are coalesced 256-byte runs and the scratch writes are conflict-free.
-// Rows are loaded eight at a time (24 independent 8-byte loads in flight per lane).
+// Staging: copy the (32+1)*160 samples a tile needs into the 32 frame columns, windowed and
+// permuted into PFA input order.  Lanes run along the packed-sample index, so global reads are
+// coalesced 256-byte runs and the scratch writes are conflict-free.  The 33 hop-rows are split
+// between the W warps; each warp loads its rows in one or two batches (<= 27 independent 8-byte
+// loads in flight per lane).
 // ---------------------------------------------------------------------------------------
 struct StageLane {                      // per-lane constants of the staging map
     int   slot_a[3], slot_b[3];
@@ -120,7 +142,7 @@ LMFB_HD void stage_store(const StageLane& sl, float2* __restrict__ S, int r, int
 }
 
 // edge rows (reflect padding at either end of the utterance, or an unaligned wave): one
-// element at a time, kept out of line and rolled -- only boundary tiles ever come here
+// element at a time, rolled -- only boundary tiles ever come here
 LMFB_HD void stage_rows_slow(int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
                              int t0, float2* __restrict__ S, int r_lo, int r_hi) {
 #pragma unroll 1
@@ -133,61 +155,59 @@ LMFB_HD void stage_rows_slow(int lane, const StageLane& sl, const float* __restr
             float2 v;
             v.x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
             v.y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
-            const int qq = q;                      // slot/window tables are tiny: index dynamically
-            const int sa = qq == 0 ? sl.slot_a[0] : (qq == 1 ? sl.slot_a[1] : sl.slot_a[2]);
-            const int sb = qq == 0 ? sl.slot_b[0] : (qq == 1 ? sl.slot_b[1] : sl.slot_b[2]);
-            const float wa0 = qq == 0 ? sl.wa0[0] : (qq == 1 ? sl.wa0[1] : sl.wa0[2]);
-            const float wa1 = qq == 0 ? sl.wa1[0] : (qq == 1 ? sl.wa1[1] : sl.wa1[2]);
-            const float wb0 = qq == 0 ? sl.wb0[0] : (qq == 1 ? sl.wb0[1] : sl.wb0[2]);
-            const float wb1 = qq == 0 ? sl.wb1[0] : (qq == 1 ? sl.wb1[1] : sl.wb1[2]);
+            const int sa = q == 0 ? sl.slot_a[0] : (q == 1 ? sl.slot_a[1] : sl.slot_a[2]);
+            const int sb = q == 0 ? sl.slot_b[0] : (q == 1 ? sl.slot_b[1] : sl.slot_b[2]);
+            const float wa0 = q == 0 ? sl.wa0[0] : (q == 1 ? sl.wa0[1] : sl.wa0[2]);
+            const float wa1 = q == 0 ? sl.wa1[0] : (q == 1 ? sl.wa1[1] : sl.wa1[2]);
+            const float wb0 = q == 0 ? sl.wb0[0] : (q == 1 ? sl.wb0[1] : sl.wb0[2]);
+            const float wb1 = q == 0 ? sl.wb1[0] : (q == 1 ? sl.wb1[1] : sl.wb1[2]);
             if (r < kTile)  S[sa + r]     = make_float2(v.x * wa0, v.y * wa1);
             if (r >= 1)     S[sb + r - 1] = make_float2(v.x * wb0, v.y * wb1);
         }
     }
 }
 
-LMFB_HD void stage_tile(int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
+template <int W>
+LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
                         int t0, float2* __restrict__ S, bool vec_ok) {
-    constexpr int kRowsPerBatch = 8;               // rows 0..31 in 4 batches, row 32 on its own
+    constexpr int kRowsPerWarp = (kTile + 1 + W - 1) / W;
+    constexpr int kBatch = kRowsPerWarp <= 9 ? kRowsPerWarp : 9;
+    const int r_lo = w * kRowsPerWarp;
+    const int r_hi = r_lo + kRowsPerWarp < kTile + 1 ? r_lo + kRowsPerWarp : kTile + 1;
 #pragma unroll 1
-    for (int r0 = 0; r0 < kTile; r0 += kRowsPerBatch) {
-        if (!rows_interior(t0 + r0 - 1, t0 + r0 - 1 + kRowsPerBatch, len, vec_ok)) {
-            stage_rows_slow(lane, sl, wave_row, len, t0, S, r0, r0 + kRowsPerBatch);
+    for (int r0 = r_lo; r0 < r_hi; r0 += kBatch) {
+        const int r1 = r0 + kBatch < r_hi ? r0 + kBatch : r_hi;
+        if (!rows_interior(t0 + r0 - 1, t0 + r1 - 1, len, vec_ok)) {
+            stage_rows_slow(lane, sl, wave_row, len, t0, S, r0, r1);
             continue;
         }
         const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r0 - 1) * kHop) + lane;
-        float2 v[kRowsPerBatch][3];
+        float2 v[kBatch][3];
 #pragma unroll
-        for (int i = 0; i < kRowsPerBatch; ++i) {
-            v[i][0] = LMFB_LDG(src + i * 80);
-            v[i][1] = LMFB_LDG(src + i * 80 + 32);
-            v[i][2] = lane < 16 ? LMFB_LDG(src + i * 80 + 64) : make_float2(0.0f, 0.0f);
+        for (int i = 0; i < kBatch; ++i) {
+            const bool on = r0 + i < r1;
+            v[i][0] = on ? LMFB_LDG(src + i * 80) : make_float2(0.0f, 0.0f);
+            v[i][1] = on ? LMFB_LDG(src + i * 80 + 32) : make_float2(0.0f, 0.0f);
+            v[i][2] = (on && lane < 16) ? LMFB_LDG(src + i * 80 + 64) : make_float2(0.0f, 0.0f);
         }
 #pragma unroll
-        for (int i = 0; i < kRowsPerBatch; ++i) {
-            stage_store(sl, S, r0 + i, 0, v[i][0]);
-            stage_store(sl, S, r0 + i, 1, v[i][1]);
-            if (lane < 16) stage_store(sl, S, r0 + i, 2, v[i][2]);
+        for (int i = 0; i < kBatch; ++i) {
+            if (r0 + i < r1) {
+                stage_store(sl, S, r0 + i, 0, v[i][0]);
+                stage_store(sl, S, r0 + i, 1, v[i][1]);
+                if (lane < 16) stage_store(sl, S, r0 + i, 2, v[i][2]);
+            }
         }
-    }
-    if (!rows_interior(t0 + kTile - 1, t0 + kTile, len, vec_ok)) {
-        stage_rows_slow(lane, sl, wave_row, len, t0, S, kTile, kTile + 1);
-    } else {
-        const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + kTile - 1) * kHop) + lane;
-        const float2 v0 = LMFB_LDG(src), v1 = LMFB_LDG(src + 32);
-        const float2 v2 = lane < 16 ? LMFB_LDG(src + 64) : make_float2(0.0f, 0.0f);
-        stage_store(sl, S, kTile, 0, v0);
-        stage_store(sl, S, kTile, 1, v1);
-        if (lane < 16) stage_store(sl, S, kTile, 2, v2);
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// pass 1: five in-register 32-point FFTs over the thread's private column (col = S + lane)
+// pass 1: the five in-register 32-point FFTs of a column, dealt round-robin to the W warps
 // ---------------------------------------------------------------------------------------
-LMFB_HD void fft_pass1(float2* __restrict__ col) {
+template <int W>
+LMFB_HD void fft_pass1(int w, float2* __restrict__ col) {
 #pragma unroll 1
-    for (int n1 = 0; n1 < 5; ++n1) {
+    for (int n1 = w; n1 < 5; n1 += W) {
         float2* p = col + n1 * 32 * kPitch;
         float xr[32], xi[32];
 #pragma unroll
@@ -229,49 +249,53 @@ LMFB_HD void split_pair(float Ar, float Ai, float Bzr, float Bzi, float sn, floa
     xp = make_float2(sr + Dr, -(si + Di));
 }
 
-// what pass 2 leaves in the scratch for one bin, given the spectrum value and the mask(s)
-//   forward : .x = masked power P'            (.y unused)
-//   backward: (.x, .y) = (dP -> dMr factor, dP -> dMi factor) = (2 Mr Re'^2, 2 Mi Im'^2)
-//             'power' mode: .x = Re'^2 + Im'^2
-template <int MASK, bool BWD>
-LMFB_HD float2 bin_payload(float2 x, float mr, float mi) {
-    if (!BWD) {
-        if (MASK == kMaskReim) { const float a = x.x * mr, b = x.y * mi; return make_float2(fmaf(a, a, b * b), 0.0f); }
-        const float p = fmaf(x.x, x.x, x.y * x.y);
-        return make_float2(MASK == kMaskPower ? mr * p : p, 0.0f);
-    }
-    if (MASK == kMaskReim) return make_float2(2.0f * mr * x.x * x.x, 2.0f * mi * x.y * x.y);
-    return make_float2(fmaf(x.x, x.x, x.y * x.y), 0.0f);
+// forward: masked power P' of one bin
+template <int MASK>
+LMFB_HD float masked_power(float2 x, float mr, float mi) {
+    if (MASK == kMaskReim) { const float a = x.x * mr, b = x.y * mi; return fmaf(a, a, b * b); }
+    const float p = fmaf(x.x, x.x, x.y * x.y);
+    return MASK == kMaskPower ? mr * p : p;
 }
 
-// which mask tensors a kernel variant reads
-#define LMFB_NEEDS_MASK_R(MASK, BWD) ((BWD) ? (MASK) == kMaskReim : (MASK) != kMaskNone)
-#define LMFB_NEEDS_MASK_I(MASK, BWD) ((MASK) == kMaskReim)
-
-// mask values of the ten bins of pass-2 step k2: index k1 -> bin f, index 5+k1 -> bin 160-f.
-// mr/mi point at a column that is always readable (out-of-row lanes are clamped by the caller),
-// so the loads carry no predicate; sf (floats per mask row) fits 32 bits.
+// what pass 2 needs from global memory for the ten bins of column pair k2: index k1 -> bin f,
+// index 5+k1 -> bin 160-f.  All pointers are readable for every lane (out-of-row lanes are
+// clamped by the caller), so no load is predicated; row strides fit 32 bits.
 template <int MASK, bool BWD>
-LMFB_HD void load_step_masks(int k2, const float* __restrict__ mr, const float* __restrict__ mi,
-                             unsigned sf, float (&vr)[10], float (&vi)[10]) {
+struct StepIn {
+    float vr[10], vi[10];     // mask values
+    float d0[10], d1[10];     // backward: dE rows that the bin's two mel weights multiply
+};
+
+template <int MASK, bool BWD>
+LMFB_HD void load_step(int k2, const MelBand& mb, const float* __restrict__ mr, const float* __restrict__ mi,
+                       unsigned sf, const float* __restrict__ dE, unsigned sem, StepIn<MASK, BWD>& in) {
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
-        const unsigned f = kBinOf[k2][k1];
-        const unsigned of = f * sf, op = (kBins - 1 - f) * sf;
-        vr[k1] = vr[5 + k1] = vi[k1] = vi[5 + k1] = 0.0f;
-        if (LMFB_NEEDS_MASK_R(MASK, BWD)) { vr[k1] = LMFB_LDG(mr + of); vr[5 + k1] = LMFB_LDG(mr + op); }
-        if (LMFB_NEEDS_MASK_I(MASK, BWD)) { vi[k1] = LMFB_LDG(mi + of); vi[5 + k1] = LMFB_LDG(mi + op); }
+        const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
+        const unsigned of = f * sf, op = fp * sf;
+        if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(mr + of); in.vr[5 + k1] = LMFB_LDG(mr + op); }
+        if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(mi + of); in.vi[5 + k1] = LMFB_LDG(mi + op); }
+        if (BWD) {
+            const unsigned df = mb.ent[f].dd, dp = mb.ent[fp].dd;
+            in.d0[k1]     = LMFB_LDG(dE + (df & 255u) * sem);
+            in.d1[k1]     = LMFB_LDG(dE + (df >> 8) * sem);
+            in.d0[5 + k1] = LMFB_LDG(dE + (dp & 255u) * sem);
+            in.d1[5 + k1] = LMFB_LDG(dE + (dp >> 8) * sem);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------
 // pass 2, one step: columns k2 and kb = (32-k2) mod 32 of the five sub-transforms -> two 5-point
-// DFTs -> real split -> ten bins -> mask -> payload, in place.  Branch-free and identical for
-// all k2: the self-paired columns (k2 = 0, 16, where kb == k2) simply compute each of their
-// bins twice; only bins 0/160 (k2 = 0, k1 = 0), which share slot 0, need a select.
+// DFTs -> real split -> ten bins -> mask.  Branch-free and identical for all k2: the self-paired
+// columns (k2 = 0, 16, where kb == k2) simply compute each of their bins twice.
+//   forward : masked power stored in place (bins 0/160 share slot 0 -> one select)
+//   backward: gradients = (2 Mr Re'^2, 2 Mi Im'^2) * dP, or (Re'^2 + Im'^2) * dP for 'power',
+//             stored to gr/gi (+ f*gsf); every lane's pointers are valid, `inrow` gates the store
 // ---------------------------------------------------------------------------------------
 template <int MASK, bool BWD>
-LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const float (&vr)[10], const float (&vi)[10]) {
+LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, const StepIn<MASK, BWD>& in,
+                        float* __restrict__ gr, float* __restrict__ gi, unsigned gsf, bool inrow) {
     const int kb = (32 - k2) & 31;
     float2* ca = col + k2 * kPitch;
     float2* cb = col + kb * kPitch;
@@ -279,7 +303,7 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const float (&vr)[10],
 #pragma unroll
     for (int n = 0; n < 5; ++n) {
         const float2 v = ca[n * 32 * kPitch]; ar[n] = v.x; ai[n] = v.y;
-        const float2 w = cb[n * 32 * kPitch]; br[n] = w.x; bi[n] = w.y;
+        const float2 u = cb[n * 32 * kPitch]; br[n] = u.x; bi[n] = u.y;
     }
     dft5(ar, ai, Ar, Ai);
     dft5(br, bi, Br, Bi);
@@ -288,53 +312,72 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const float (&vr)[10],
         const int kp = (5 - k1) % 5;
         float2 xf, xp;
         split_pair(Ar[k1], Ai[k1], Br[kp], Bi[kp], kSplitSin[k2][k1], kSplitCos[k2][k1], xf, xp);
-        float2 pf = bin_payload<MASK, BWD>(xf, vr[k1], vi[k1]);
-        float2 pp = bin_payload<MASK, BWD>(xp, vr[5 + k1], vi[5 + k1]);
-        if (k1 == 0) {                                    // bins 0 and 160 (real) share slot 0
-            const bool z = k2 == 0;
-            pf = make_float2(pf.x, z ? pp.x : pf.y);
-            pp = make_float2(z ? pf.x : pp.x, z ? pf.y : pp.y);
+        if (!BWD) {
+            float pf = masked_power<MASK>(xf, in.vr[k1], in.vi[k1]);
+            float pp = masked_power<MASK>(xp, in.vr[5 + k1], in.vi[5 + k1]);
+            float2 sf2 = make_float2(pf, 0.0f), sp2 = make_float2(pp, 0.0f);
+            if (k1 == 0) {                                // bins 0 and 160 (real) share slot 0
+                const bool z = k2 == 0;
+                sf2 = make_float2(pf, z ? pp : 0.0f);
+                sp2 = make_float2(z ? pf : pp, z ? pp : 0.0f);
+            }
+            ca[k1 * 32 * kPitch] = sf2;
+            cb[kp * 32 * kPitch] = sp2;
+        } else {
+            const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
+            const float dpf = fmaf(mb.ent[f].wh, in.d1[k1], mb.ent[f].wl * in.d0[k1]);
+            const float dpp = fmaf(mb.ent[fp].wh, in.d1[5 + k1], mb.ent[fp].wl * in.d0[5 + k1]);
+            if (MASK == kMaskReim) {
+                st_if(gr + f * gsf,  2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
+                st_if(gi + f * gsf,  2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
+                st_if(gr + fp * gsf, 2.0f * in.vr[5 + k1] * xp.x * xp.x * dpp, inrow);
+                st_if(gi + fp * gsf, 2.0f * in.vi[5 + k1] * xp.y * xp.y * dpp, inrow);
+            } else {
+                st_if(gr + f * gsf,  fmaf(xf.x, xf.x, xf.y * xf.y) * dpf, inrow);
+                st_if(gr + fp * gsf, fmaf(xp.x, xp.x, xp.y * xp.y) * dpp, inrow);
+            }
         }
-        ca[k1 * 32 * kPitch] = pf;
-        cb[kp * 32 * kPitch] = pp;
     }
 }
 
-// pass 2 over all 17 columns, two at a time; the masks of the next pair are loaded into
-// registers while the current pair is being computed.
-template <int MASK, bool BWD>
-LMFB_HD void fft_pass2_masked(float2* __restrict__ col, const float* __restrict__ mr,
-                              const float* __restrict__ mi, unsigned sf) {
-    float r0[10], i0[10], r1[10], i1[10];
-    load_step_masks<MASK, BWD>(0, mr, mi, sf, r0, i0);
-    load_step_masks<MASK, BWD>(1, mr, mi, sf, r1, i1);
+// pass 2 over the 17 column pairs, dealt round-robin to the W warps; the global inputs of a
+// warp's next step are loaded into a second register set while the current step is computed.
+template <int W, int MASK, bool BWD>
+LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb,
+                       const float* __restrict__ mr, const float* __restrict__ mi, unsigned sf,
+                       const float* __restrict__ dE, unsigned sem,
+                       float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
+    StepIn<MASK, BWD> a, b;
+    load_step<MASK, BWD>(w, mb, mr, mi, sf, dE, sem, a);
 #pragma unroll 1
-    for (int k2 = 0; k2 < 16; k2 += 2) {
-        float nr0[10], ni0[10], nr1[10], ni1[10];
-        load_step_masks<MASK, BWD>(k2 + 2, mr, mi, sf, nr0, ni0);
-        if (k2 + 3 <= 16) load_step_masks<MASK, BWD>(k2 + 3, mr, mi, sf, nr1, ni1);
-        pass2_step<MASK, BWD>(col, k2, r0, i0);
-        pass2_step<MASK, BWD>(col, k2 + 1, r1, i1);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) { r0[i] = nr0[i]; i0[i] = ni0[i]; r1[i] = nr1[i]; i1[i] = ni1[i]; }
+    for (int k2 = w; k2 <= 16; k2 += 2 * W) {
+        const bool has_b = k2 + W <= 16;
+        if (has_b) load_step<MASK, BWD>(k2 + W, mb, mr, mi, sf, dE, sem, b);
+        pass2_step<MASK, BWD>(col, k2, mb, a, gr, gi, sf, inrow);
+        if (has_b) {
+            if (k2 + 2 * W <= 16) load_step<MASK, BWD>(k2 + 2 * W, mb, mr, mi, sf, dE, sem, a);
+            pass2_step<MASK, BWD>(col, k2 + W, mb, b, gr, gi, sf, inrow);
+        }
     }
-    pass2_step<MASK, BWD>(col, 16, r0, i0);
 }
 
 // ---------------------------------------------------------------------------------------
 // phase 3 (forward): banded mel accumulation filter by filter (E[m] parked in the free .y of
-// slot 1+m), then log1p + store for all filters in an unrolled second sweep.
+// slot 1+m), then log1p + store in an unrolled second sweep.  Warp w owns filters
+// [mbeg[w], mbeg[w+1]); to get the upper-weight contributions of its first filter it starts
+// one filter early and discards that filter's sum.
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
-LMFB_HD void phase3_fwd(float2* __restrict__ col, const MelBand& mb,
+LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const MelBand& mb,
                         float* __restrict__ out, unsigned som, bool inrow, bool valid) {
     float* colf = reinterpret_cast<float*>(col);
-    const int n_mels = mb.n_mels;
-    int f = 0;
+    const int m_lo = mb.mbeg[w], m_hi = mb.mbeg[w + 1];
+    if (m_lo >= m_hi) return;
+    const int m_first = m_lo > 0 ? m_lo - 1 : 0;
+    int f = m_first > 0 ? (int)mb.fend[m_first - 1] : 0;
     float acc0 = 0.0f, acc1 = 0.0f;
-    float* ep = colf + 2 * kPitch + 1;                    // slot 1, .y
 #pragma unroll 1
-    for (int m = 0; m < n_mels; ++m) {
+    for (int m = m_first; m < m_hi; ++m) {
         const int fe = mb.fend[m];
 #pragma unroll 4
         for (; f < fe; ++f) {
@@ -342,92 +385,34 @@ LMFB_HD void phase3_fwd(float2* __restrict__ col, const MelBand& mb,
             acc0 = fmaf(mb.ent[f].wl, p, acc0);
             acc1 = fmaf(mb.ent[f].wh, p, acc1);
         }
-        *ep = acc0;
-        ep += 2 * kPitch;
+        if (m >= m_lo) colf[(1 + m) * 2 * kPitch + 1] = acc0;
         acc0 = acc1;
         acc1 = 0.0f;
     }
-    ep = colf + 2 * kPitch + 1;
-#pragma unroll 8
-    for (int m = 0; m < n_mels; ++m) {
-        const float y = valid ? log1pf(ep[m * 2 * kPitch]) : 0.0f;
-        if (inrow) out[(unsigned)m * som] = y;
+#pragma unroll 4
+    for (int m = m_lo; m < m_hi; ++m) {
+        const float y = valid ? log1pf(colf[(1 + m) * 2 * kPitch + 1]) : 0.0f;
+        st_if(out + (unsigned)m * som, y, inrow);
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// phase 3 (backward): dP[f] = wl*dE[ml] + wh*dE[ml+1]; gradients = payload * dP.
-//   dE : dE + n*stride_n + t (row m at + m*sem), zero for frames t >= T_i; readable for every
-//   lane (clamped by the caller).  The dE values are consumed in filter order through a sliding
-//   register window: filters are handled four at a time and the window runs kDAhead filters
-//   ahead; the caller pre-loads it (before the FFT) with dE[0 .. kDWin).
-// ---------------------------------------------------------------------------------------
-constexpr int kDAhead = 8;
-constexpr int kDWin = 5 + kDAhead;                        // d[j], d[j+1] for j < 4, plus the look-ahead
-
-LMFB_HD void dwin_preload(const float* __restrict__ dE, unsigned sem, int n_mels, float (&dw)[kDWin]) {
-#pragma unroll
-    for (int i = 0; i < kDWin; ++i) dw[i] = i < n_mels ? LMFB_LDG(dE + (unsigned)i * sem) : 0.0f;
-}
-
-template <int MASK>
-LMFB_HD void phase3_bwd(const float2* __restrict__ col, const MelBand& mb,
-                        const float* __restrict__ dE, unsigned sem, float (&dw)[kDWin],
-                        float* __restrict__ gr, float* __restrict__ gi, unsigned gsf, bool inrow) {
-    const int n_mels = mb.n_mels;
-    int f = 0;
-#pragma unroll 1
-    for (int m0 = 0; m0 < n_mels; m0 += 4) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (m0 + j < n_mels) {
-                const int fe = mb.fend[m0 + j];
-                const float d0 = dw[j], d1 = dw[j + 1];
-#pragma unroll 2
-                for (; f < fe; ++f) {
-                    const uint32_t off = mb.ent[f].off, sel = mb.ent[f].sel;
-                    const float dp = fmaf(mb.ent[f].wh, d1, mb.ent[f].wl * d0);
-                    const float2 v = col[off >> 1];
-                    const float a = sel == 2u ? v.y : v.x;
-                    const float b = sel != 0u ? 0.0f : v.y;
-                    if (inrow) gr[(unsigned)f * gsf] = a * dp;
-                    if (MASK == kMaskReim) { if (inrow) gi[(unsigned)f * gsf] = b * dp; }
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i + 4 < kDWin; ++i) dw[i] = dw[i + 4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = m0 + kDWin + i;
-            dw[kDWin - 4 + i] = m < n_mels ? LMFB_LDG(dE + (unsigned)m * sem) : 0.0f;
-        }
-    }
-    if (inrow) {
-#pragma unroll 1
-        for (; f < kBins; ++f) {                         // bins above the last filter: no gradient
-            gr[(unsigned)f * gsf] = 0.0f;
-            if (MASK == kMaskReim) gi[(unsigned)f * gsf] = 0.0f;
-        }
-    }
-}
-
-// L2 prefetch of the (32+1)*160 samples of a tile (165 lines of 128 B)
-LMFB_HD void prefetch_wave_l2(int lane, const float* __restrict__ wave_row, int len, int t0) {
+// L2 prefetch of the (32+1)*160 samples of a tile (165 lines of 128 B), `idx`/`cnt` = this
+// thread's index / the number of threads sharing the job
+LMFB_HD void prefetch_wave_l2(int idx, int cnt, const float* __restrict__ wave_row, int len, int t0) {
     long long lo = (long long)(t0 - 1) * kHop, hi = (long long)(t0 + kTile) * kHop;
     if (lo < 0) lo = 0;
     if (hi > len) hi = len;
 #pragma unroll 1
-    for (long long i = lo + lane * 32; i < hi; i += 32 * 32) LMFB_PREFETCH_L2(wave_row + i);
+    for (long long i = lo + idx * 32; i < hi; i += (long long)cnt * 32) LMFB_PREFETCH_L2(wave_row + i);
 }
 
-// L2 prefetch of the mask rows a tile will read: lanes take rows lane, lane+32, ...; a 128-byte
-// row segment may straddle two lines, so both ends are touched.
-LMFB_HD void prefetch_rows_l2(int lane, const float* __restrict__ base, unsigned sf, int rows, int t0, int tmax) {
+// L2 prefetch of the row segments a tile will read: threads take rows idx, idx+cnt, ...; a
+// 128-byte segment may straddle two lines, so both ends are touched.
+LMFB_HD void prefetch_rows_l2(int idx, int cnt, const float* __restrict__ base, unsigned sf, int rows, int t0, int tmax) {
     if (t0 >= tmax) return;
     const int last = (t0 + kTile <= tmax ? t0 + kTile : tmax) - 1;
 #pragma unroll 1
-    for (int f = lane; f < rows; f += 32) {
+    for (int f = idx; f < rows; f += cnt) {
         LMFB_PREFETCH_L2(base + (unsigned)f * sf + t0);
         LMFB_PREFETCH_L2(base + (unsigned)f * sf + last);
     }

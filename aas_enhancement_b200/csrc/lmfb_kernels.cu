@@ -43,17 +43,23 @@ struct K1Args {
     int            vec_ok;
 };
 
-template <int MASK, bool BWD>
-__global__ void __launch_bounds__(kTile)
+// warps per tile (see lmfb_core.cuh); 5 CTAs are resident per SM either way
+constexpr int kWFwd = 4;
+constexpr int kWBwd = 4;
+constexpr int kCtasPerSM = 5;               // 5 x (42,240 + 1,024) B of shared memory per SM
+
+template <int MASK, bool BWD, int W>
+__global__ void __launch_bounds__(kTile * W, kCtasPerSM)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     extern __shared__ __align__(16) float2 S[];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int w    = threadIdx.x >> 5;
     const int n_mels = mb.n_mels;
     StageLane sl;
     stage_lane_init(lane, a.window, sl);
     float2* col = S + lane;
 
-    // persistent warp: tiles are dealt round-robin, neighbouring tiles run at the same time
+    // persistent CTA: tiles are dealt round-robin, neighbouring tiles run at the same time
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int n   = tile / a.tiles_per_utt;
         const int t0  = (tile - n * a.tiles_per_utt) * kTile;
@@ -71,10 +77,10 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
             if (inrow) {
                 if (!BWD) {
 #pragma unroll 4
-                    for (int m = 0; m < n_mels; ++m) a.out[row_nm + (unsigned)m * som] = 0.0f;
+                    for (int m = w; m < n_mels; m += W) a.out[row_nm + (unsigned)m * som] = 0.0f;
                 } else if (MASK != kMaskNone) {
 #pragma unroll 4
-                    for (int f = 0; f < kBins; ++f) {
+                    for (int f = w; f < kBins; f += W) {
                         a.gr[moff + (unsigned)f * a.msf] = 0.0f;
                         if (MASK == kMaskReim) a.gi[moff + (unsigned)f * a.msf] = 0.0f;
                     }
@@ -83,37 +89,38 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
             continue;
         }
 
-        // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs
-        if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(lane, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
-        if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(lane, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
-        if (BWD) prefetch_rows_l2(lane, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
+        // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs ...
+        if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
+        if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
+        if (BWD) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
         // ... and the next tile's samples, so that its staging loads hit L2
         {
             const int nt = tile + gridDim.x;
             if (nt < a.total_tiles) {
                 const int nn = nt / a.tiles_per_utt;
-                prefetch_wave_l2(lane, a.wave + (long long)nn * a.wave_stride, a.lengths[nn],
+                prefetch_wave_l2(threadIdx.x, kTile * W, a.wave + (long long)nn * a.wave_stride, a.lengths[nn],
                                  (nt - nn * a.tiles_per_utt) * kTile);
             }
         }
 
-        __syncwarp();                               // previous tile's columns are no longer read
-        stage_tile(lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
-        __syncwarp();
+        stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
+        __syncthreads();
+        fft_pass1<W>(w, col);
+        __syncthreads();
         // loads of out-of-row lanes are redirected to the last column of the row (always readable)
         const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
-        float dw[kDWin];
-        if (BWD) dwin_preload(a.dE + row_nm + clamp, som, n_mels, dw);
-        fft_pass1(col);
-        fft_pass2_masked<MASK, BWD>(col, a.mask_r + moff + clamp, a.mask_i + moff + clamp, a.msf);
-        if (!BWD) phase3_fwd(col, mb, a.out + row_nm, som, inrow, valid);
-        else      phase3_bwd<MASK>(col, mb, a.dE + row_nm + clamp, som, dw, a.gr + moff, a.gi + moff, a.msf, inrow);
+        fft_pass2<W, MASK, BWD>(w, col, mb, a.mask_r + moff + clamp, a.mask_i + moff + clamp, a.msf,
+                                a.dE + row_nm + clamp, som, a.gr + moff, a.gi + moff, inrow);
+        if (!BWD) {
+            __syncthreads();
+            phase3_fwd(w, col, mb, a.out + row_nm, som, inrow, valid);
+        }
+        __syncthreads();                            // the scratch is free for the next tile
     }
 }
 
 // ------------------------------------------------------------------------------------ K2
 constexpr int kRowThreads = 128;
-constexpr int kWarpsPerSM = 5;              // 5 x (42,240 + 1,024) B of shared memory per SM
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
 #pragma unroll
@@ -267,7 +274,7 @@ extern "C" aas_lmfb_plan* aas_lmfb_plan_create(const float* mel, int n_mels, int
         if (!p) { st = AAS_LMFB_E_NOMEM; break; }
         memset(p, 0, sizeof(*p));
         p->n_mels = n_mels;
-        if (build_mel_band(mel, n_mels, &p->band) != 0) st = AAS_LMFB_E_MEL;
+        if (build_mel_band(mel, n_mels, kWFwd, &p->band) != 0) st = AAS_LMFB_E_MEL;
     } while (0);
     if (st != AAS_LMFB_OK && p) { delete p; p = nullptr; }
     if (status) *status = st;
@@ -287,9 +294,9 @@ typedef void (*k1_fn)(const K1Args, const MelBand);
 
 k1_fn pick_k1(unsigned mask, bool bwd) {
     switch (mask) {
-        case AAS_LMFB_MASK_NONE:  return bwd ? nullptr : (k1_fn)lmfb_k1<kMaskNone, false>;
-        case AAS_LMFB_MASK_REIM:  return bwd ? (k1_fn)lmfb_k1<kMaskReim, true>  : (k1_fn)lmfb_k1<kMaskReim, false>;
-        case AAS_LMFB_MASK_POWER: return bwd ? (k1_fn)lmfb_k1<kMaskPower, true> : (k1_fn)lmfb_k1<kMaskPower, false>;
+        case AAS_LMFB_MASK_NONE:  return bwd ? nullptr : (k1_fn)lmfb_k1<kMaskNone, false, kWFwd>;
+        case AAS_LMFB_MASK_REIM:  return bwd ? (k1_fn)lmfb_k1<kMaskReim, true, kWBwd>  : (k1_fn)lmfb_k1<kMaskReim, false, kWFwd>;
+        case AAS_LMFB_MASK_POWER: return bwd ? (k1_fn)lmfb_k1<kMaskPower, true, kWBwd> : (k1_fn)lmfb_k1<kMaskPower, false, kWFwd>;
     }
     return nullptr;
 }
@@ -313,7 +320,7 @@ int ensure_attrs(k1_fn fn) {
     return 0;
 }
 
-int launch_k1(k1_fn fn, K1Args& a, const MelBand& mb, int n, cudaStream_t stream) {
+int launch_k1(k1_fn fn, int warps, K1Args& a, const MelBand& mb, int n, cudaStream_t stream) {
     const int rc = ensure_attrs(fn);
     if (rc) return rc;
     const long long total = (long long)n * a.tiles_per_utt;
@@ -324,9 +331,9 @@ int launch_k1(k1_fn fn, K1Args& a, const MelBand& mb, int n, cudaStream_t stream
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    const long long resident = (long long)sms * kWarpsPerSM;      // one warp-CTA per scratch slot
+    const long long resident = (long long)sms * kCtasPerSM;       // one CTA per scratch slot
     const unsigned blocks = (unsigned)(total < resident ? total : resident);
-    fn<<<blocks, kTile, kScratchBytes, stream>>>(a, mb);
+    fn<<<blocks, kTile * warps, kScratchBytes, stream>>>(a, mb);
     return (int)cudaPeekAtLastError();
 }
 
@@ -375,7 +382,7 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
 
     rec(prof, 0, stream);
-    rc = launch_k1(pick_k1(mask, false), a, plan->band, n, stream);
+    rc = launch_k1(pick_k1(mask, false), kWFwd, a, plan->band, n, stream);
     rec(prof, 1, stream);
     if (rc) return rc;
     rec(prof, 2, stream);
@@ -428,7 +435,7 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
 
     rec(prof, 0, stream);
-    rc = launch_k1(pick_k1(mask, true), a, plan->band, n, stream);
+    rc = launch_k1(pick_k1(mask, true), kWBwd, a, plan->band, n, stream);
     rec(prof, 1, stream);
     return rc;
 }

@@ -5,15 +5,17 @@
 
 namespace aas_lmfb {
 
-// mel: (n_mels, kBins) row-major.  Returns 0 on success, -1 if some bin feeds a filter outside
-// the two live ones (basis not banded / not frequency-ordered).
 inline uint32_t kBinOffHost(int f) {
     if (f == 0) return 0u;
     if (f == kBins - 1) return 1u;
     return (uint32_t)(((f % 5) * 32 + (f & 31)) * kPitch * 2);
 }
 
-inline int build_mel_band(const float* mel, int n_mels, MelBand* out, int* ml_out = nullptr) {
+// mel: (n_mels, kBins) row-major.  `warps` = warps per tile of the forward kernel (phase-3 split).
+// Returns 0 on success, -1 if some bin feeds a filter outside the two live ones (basis not
+// banded / not frequency-ordered).  ml_out (optional, kBins ints) receives the lower filter of
+// every bin (n_mels for bins above the last filter).
+inline int build_mel_band(const float* mel, int n_mels, int warps, MelBand* out, int* ml_out = nullptr) {
     int hi[kMaxMels];                 // last bin with a non-zero weight, per filter (-1: empty)
     for (int m = 0; m < n_mels; ++m) {
         hi[m] = -1;
@@ -31,10 +33,30 @@ inline int build_mel_band(const float* mel, int n_mels, MelBand* out, int* ml_ou
         e.wl = ml < n_mels ? 0.25f * mel[ml * kBins + f] : 0.0f;
         e.wh = ml + 1 < n_mels ? 0.25f * mel[(ml + 1) * kBins + f] : 0.0f;
         e.off = kBinOffHost(f);
-        e.sel = f == 0 ? 1u : (f == kBins - 1 ? 2u : 0u);
+        const uint32_t dlo = ml < n_mels ? (uint32_t)ml : 0u;            // weights are 0 where clamped
+        const uint32_t dhi = ml + 1 < n_mels ? (uint32_t)(ml + 1) : 0u;
+        e.dd = dlo | (dhi << 8);
         for (int m = ml; m < n_mels; ++m) out->fend[m] = (uint8_t)(f + 1);
     }
     // now fend[m] = one past the last bin whose lower filter is <= m (empty ranges repeat the value)
+
+    // split the filters between the warps of the forward kernel, balancing bins*6 + 40 per filter
+    if (warps < 1) warps = 1;
+    if (warps > kMaxW) warps = kMaxW;
+    int cost[kMaxMels], total = 0;
+    for (int m = 0; m < n_mels; ++m) {
+        const int lo = m > 0 ? out->fend[m - 1] : 0;
+        cost[m] = 6 * (out->fend[m] - lo) + 40;
+        total += cost[m];
+    }
+    for (int w = 0; w <= kMaxW; ++w) out->mbeg[w] = (uint8_t)n_mels;
+    out->mbeg[0] = 0;
+    int m = 0, acc = 0;
+    for (int w = 1; w < warps; ++w) {
+        const int target = (int)((long long)total * w / warps);
+        while (m < n_mels && acc + cost[m] / 2 < target) acc += cost[m++];
+        out->mbeg[w] = (uint8_t)m;
+    }
     return 0;
 }
 

@@ -1,43 +1,51 @@
 // CPU emulation of the per-thread device code in aas_enhancement_b200/csrc/lmfb_core.cuh.
 // TEST INFRASTRUCTURE ONLY: lets the index algebra of the lane=frame FFT be checked on a
-// machine without a GPU.  A warp is emulated by running the 32 lanes one after another.
+// machine without a GPU.  A CTA of W warps is emulated phase by phase (a block barrier becomes
+// "finish the phase for every warp and lane before starting the next one").
 #include <vector>
 #include <cstring>
 #include "lmfb_core.cuh"
+#include "mel_band.hpp"
 
 using namespace aas_lmfb;
 
-extern "C" int emu_stft_tile(const float* wave_row, int len, int t0, const float* window,
-                             int vec_ok, float* re_out /*[161][32]*/, float* im_out /*[161][32]*/) {
-    std::vector<float2> S(kSlots * kPitch);
-    // power-spectrum probes: 'reim' forward with masks (1,0) and (0,1) gives Re'^2 and Im'^2
-    std::vector<float> ones(kBins, 1.0f), zeros(kBins, 0.0f);
-    for (int pass = 0; pass < 2; ++pass) {
+namespace {
+
+template <int W, int MASK, bool BWD>
+void emu_tile(const float* wave_row, int len, int t0, const float* window, bool vec_ok,
+              const MelBand& mb, const float* mr, const float* mi, unsigned sf,
+              const float* dE, float* out, unsigned som, float* gr, float* gi, int tmax, int T,
+              std::vector<float2>& S) {
+    for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
             StageLane sl;
             stage_lane_init(lane, window, sl);
-            stage_tile(lane, sl, wave_row, len, t0, S.data(), vec_ok != 0);
+            stage_tile<W>(w, lane, sl, wave_row, len, t0, S.data(), vec_ok);
         }
+    for (int w = 0; w < W; ++w)
+        for (int lane = 0; lane < 32; ++lane) fft_pass1<W>(w, S.data() + lane);
+    for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
-            float2* col = S.data() + lane;
-            fft_pass1(col);
-            fft_pass2_masked<kMaskReim, false>(col, pass == 0 ? ones.data() : zeros.data(),
-                                               pass == 0 ? zeros.data() : ones.data(), 1u);
-            const float* colf = reinterpret_cast<const float*>(col);
-            for (int f = 0; f < kBins; ++f) (pass == 0 ? re_out : im_out)[f * 32 + lane] = colf[kBinOff[f]];
+            const int t = t0 + lane;
+            const bool inrow = t < tmax;
+            const long long clamp = inrow ? 0 : (long long)(tmax - 1 - t);
+            fft_pass2<W, MASK, BWD>(w, S.data() + lane, mb, mr ? mr + t + clamp : nullptr,
+                                    mi ? mi + t + clamp : nullptr, sf, dE ? dE + t + clamp : nullptr, som,
+                                    gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
         }
-    }
-    return 0;
+    if (!BWD)
+        for (int w = 0; w < W; ++w)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int t = t0 + lane;
+                phase3_fwd(w, S.data() + lane, mb, out + t, som, t < tmax, t < T);
+            }
 }
 
-// ---- whole K1 (forward / backward), tile by tile, same control flow as lmfb_k1<> ----
-#include "mel_band.hpp"
-
-template <int MASK>
-static void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_utt, long long wave_stride,
-                        const float* mask_r, const float* mask_i, long long msn, long long msf,
-                        const float* window, const MelBand& mb, float* out, const float* dE,
-                        float* gr, float* gi, int tmax, int vec_ok) {
+template <int W, int MASK>
+void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_utt, long long wave_stride,
+                 const float* mask_r, const float* mask_i, long long msn, long long msf,
+                 const float* window, const MelBand& mb, float* out, const float* dE,
+                 float* gr, float* gi, int tmax, int vec_ok) {
     const int tiles = (tmax + kTile - 1) / kTile;
     const int n_mels = mb.n_mels;
     std::vector<float2> S(kSlots * kPitch);
@@ -47,13 +55,13 @@ static void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_ut
             const int len = lengths[n];
             int T = len >= 1 ? 1 + len / kHop : 0;
             T = T < tmax ? T : tmax;
-            const long long som = tmax;
+            const unsigned som = (unsigned)tmax;
+            const long long nb = (long long)n * n_mels * som;
             if (t0 >= T) {
                 for (int lane = 0; lane < 32; ++lane) {
                     const int t = t0 + lane;
                     if (t >= tmax) continue;
-                    const long long row_nm = (long long)n * n_mels * som + t;
-                    if (!bwd) for (int m = 0; m < n_mels; ++m) out[row_nm + m * som] = 0.0f;
+                    if (!bwd) for (int m = 0; m < n_mels; ++m) out[nb + t + (long long)m * som] = 0.0f;
                     else if (MASK != kMaskNone) for (int f = 0; f < kBins; ++f) {
                         gr[(long long)n * msn + t + f * msf] = 0.0f;
                         if (MASK == kMaskReim) gi[(long long)n * msn + t + f * msf] = 0.0f;
@@ -61,67 +69,67 @@ static void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_ut
                 }
                 continue;
             }
-            for (int lane = 0; lane < 32; ++lane) {
-                StageLane sl;
-                stage_lane_init(lane, window, sl);
-                stage_tile(lane, sl, wave + (long long)n * wave_stride, len, t0, S.data(), vec_ok != 0);
-            }
-            for (int lane = 0; lane < 32; ++lane) {
-                const int t = t0 + lane;
-                const bool inrow = t < tmax, valid = t < T;
-                const long long row_nm = (long long)n * n_mels * som + t;
-                const long long moff = (long long)n * msn + t;
-                const long long clamp = inrow ? 0 : (long long)(tmax - 1 - t);
-                const bool has_mask = MASK != kMaskNone;
-                float2* col = S.data() + lane;
-                fft_pass1(col);
-                if (!bwd) {
-                    fft_pass2_masked<MASK, false>(col, mask_r + (has_mask ? moff + clamp : 0),
-                                                  mask_i + (MASK == kMaskReim ? moff + clamp : 0), (unsigned)msf);
-                    phase3_fwd(col, mb, out + row_nm, (unsigned)som, inrow, valid);
-                } else {
-                    float dw[kDWin];
-                    dwin_preload(dE + row_nm + clamp, (unsigned)som, n_mels, dw);
-                    fft_pass2_masked<MASK, true>(col, mask_r + (has_mask ? moff + clamp : 0),
-                                                 mask_i + (MASK == kMaskReim ? moff + clamp : 0), (unsigned)msf);
-                    phase3_bwd<MASK>(col, mb, dE + row_nm + clamp, (unsigned)som, dw, gr + moff, gi + moff,
-                                     (unsigned)msf, inrow);
-                }
-            }
+            const float* wr = wave + (long long)n * wave_stride;
+            const float* mr = mask_r ? mask_r + (long long)n * msn : nullptr;
+            const float* mi = mask_i ? mask_i + (long long)n * msn : nullptr;
+            if (!bwd)
+                emu_tile<W, MASK, false>(wr, len, t0, window, vec_ok != 0, mb, mr, mi, (unsigned)msf, nullptr,
+                                         out + nb, som, nullptr, nullptr, tmax, T, S);
+            else
+                emu_tile<W, MASK, true>(wr, len, t0, window, vec_ok != 0, mb, mr, mi, (unsigned)msf, dE + nb,
+                                        nullptr, som, gr + (long long)n * msn, gi ? gi + (long long)n * msn : nullptr,
+                                        tmax, T, S);
         }
 }
 
-extern "C" int emu_k1(int bwd, int mask_mode, const float* wave, const int* lengths, int n_utt,
-                      long long wave_stride, const float* mask_r, const float* mask_i,
-                      long long msn, long long msf, const float* window, const float* mel, int n_mels,
-                      float* out, const float* dE, float* gr, float* gi, int tmax, int vec_ok) {
+template <int W>
+int emu_k1_w(int bwd, int mask_mode, const float* wave, const int* lengths, int n_utt,
+             long long wave_stride, const float* mask_r, const float* mask_i,
+             long long msn, long long msf, const float* window, const float* mel, int n_mels,
+             float* out, const float* dE, float* gr, float* gi, int tmax, int vec_ok) {
     MelBand mb;
     memset(&mb, 0, sizeof(mb));
-    if (build_mel_band(mel, n_mels, &mb) != 0) return -5;
-    static const float zero = 0.0f;
-    if (!mask_r) mask_r = &zero;      // never dereferenced in the modes that leave it NULL
-    if (!mask_i) mask_i = &zero;
+    if (build_mel_band(mel, n_mels, W, &mb) != 0) return -5;
     switch (mask_mode) {
-        case kMaskNone:  emu_k1_impl<kMaskNone>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
-        case kMaskReim:  emu_k1_impl<kMaskReim>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
-        case kMaskPower: emu_k1_impl<kMaskPower>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
+        case kMaskNone:  emu_k1_impl<W, kMaskNone>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
+        case kMaskReim:  emu_k1_impl<W, kMaskReim>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
+        case kMaskPower: emu_k1_impl<W, kMaskPower>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
         default: return -4;
     }
     return 0;
 }
 
-extern "C" int emu_mel_band(const float* mel, int n_mels, float* wl, float* wh, int* ml) {
+}  // namespace
+
+// whole K1 (forward / backward), tile by tile, same control flow as lmfb_k1<>, for `warps` in {1,2,4,5}
+extern "C" int emu_k1(int warps, int bwd, int mask_mode, const float* wave, const int* lengths, int n_utt,
+                      long long wave_stride, const float* mask_r, const float* mask_i,
+                      long long msn, long long msf, const float* window, const float* mel, int n_mels,
+                      float* out, const float* dE, float* gr, float* gi, int tmax, int vec_ok) {
+#define CALL(W) return emu_k1_w<W>(bwd, mask_mode, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mel, n_mels, out, dE, gr, gi, tmax, vec_ok)
+    switch (warps) {
+        case 1: CALL(1);
+        case 2: CALL(2);
+        case 4: CALL(4);
+        case 5: CALL(5);
+    }
+#undef CALL
+    return -3;
+}
+
+extern "C" int emu_mel_band(const float* mel, int n_mels, int warps, float* wl, float* wh, int* ml, int* mbeg) {
     MelBand mb;
     memset(&mb, 0, sizeof(mb));
-    const int rc = build_mel_band(mel, n_mels, &mb, ml);
+    const int rc = build_mel_band(mel, n_mels, warps, &mb, ml);
     for (int f = 0; f < kBins; ++f) { wl[f] = mb.ent[f].wl; wh[f] = mb.ent[f].wh; }
-    // the filter ranges must tile the bins in order
-    if (rc == 0) {
+    for (int w = 0; w <= kMaxW; ++w) mbeg[w] = mb.mbeg[w];
+    if (rc == 0) {                      // the filter ranges must tile the bins in order
         int f = 0;
-        for (int m = 0; m < n_mels; ++m) {
+        for (int m = 0; m < n_mels; ++m)
             for (; f < mb.fend[m]; ++f) if (ml[f] != m) return -100 - m;
-        }
         for (; f < kBins; ++f) if (ml[f] != n_mels) return -300;
+        for (int w = 0; w < warps; ++w) if (mb.mbeg[w] > mb.mbeg[w + 1]) return -400;
+        if (mb.mbeg[0] != 0 || mb.mbeg[warps] != n_mels) return -401;
     }
     return rc;
 }

@@ -20,42 +20,15 @@ def emu(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libemu_core.so")
     subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-I", INC, SRC, "-o", so])
     lib = ctypes.CDLL(so)
-    lib.emu_stft_tile.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    vp = ctypes.c_void_p
+    lib.emu_k1.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_longlong,
+                           vp, vp, ctypes.c_longlong, ctypes.c_longlong, vp, vp, ctypes.c_int, vp, vp, vp, vp,
+                           ctypes.c_int, ctypes.c_int]
+    lib.emu_mel_band.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     return lib
 
 
-def _run(lib, wave, length, t0, window, vec_ok=1):
-    re = np.zeros((161, 32), dtype=np.float32)
-    im = np.zeros((161, 32), dtype=np.float32)
-    w = np.ascontiguousarray(wave, dtype=np.float32)
-    win = np.ascontiguousarray(window, dtype=np.float32)
-    lib.emu_stft_tile(w.ctypes.data, int(length), int(t0), win.ctypes.data, vec_ok,
-                      re.ctypes.data, im.ctypes.data)
-    return re, im
-
-
-@pytest.mark.parametrize("length,sym", [(16000, True), (5000, True), (4999, False), (333, True),
-                                        (161, True), (100, True), (1, True)])
-def test_emulated_stft_matches_oracle(emu, length, sym):
-    rs = np.random.RandomState(length)
-    wave = (0.1 * rs.randn(length + 7)).astype(np.float32)   # trailing garbage must not be read as data
-    window = orc.hamming_window(320, sym)
-    spec = orc.stft_frames(wave, length, window.astype(np.float32).astype(np.float64))
-    t_i = spec.shape[1]
-    scale = np.abs(spec).max()
-    for t0 in range(0, t_i, 32):
-        for vec_ok in (1, 0):
-            re, im = _run(emu, wave, length, t0, window, vec_ok)
-            nv = min(32, t_i - t0)
-            # the emulation returns Re'^2 and Im'^2 of the doubled spectrum X' = 2X
-            ref = spec[:, t0:t0 + nv]
-            err_r = np.abs(0.25 * re[:, :nv] - ref.real ** 2).max() / scale ** 2
-            err_i = np.abs(0.25 * im[:, :nv] - ref.imag ** 2).max() / scale ** 2
-            assert max(err_r, err_i) < 2e-6, (t0, vec_ok, err_r, err_i)
-
-
-def _k1(lib, bwd, mode, b, mel, window, dE=None, vec_ok=1):
+def _k1(lib, warps, bwd, mode, b, mel, window, dE=None, vec_ok=1):
     modes = {"none": 0, "reim": 1, "power": 2}
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     wave, mr, mi = f32(b["wave"]), f32(b["mask_r"]), f32(b["mask_i"])
@@ -66,11 +39,7 @@ def _k1(lib, bwd, mode, b, mel, window, dE=None, vec_ok=1):
     gr = np.full_like(mr, np.nan)
     gi = np.full_like(mi, np.nan)
     dE = f32(dE) if dE is not None else np.zeros_like(out)
-    vp = ctypes.c_void_p
-    lib.emu_k1.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_longlong, vp, vp,
-                           ctypes.c_longlong, ctypes.c_longlong, vp, vp, ctypes.c_int, vp, vp, vp, vp,
-                           ctypes.c_int, ctypes.c_int]
-    rc = lib.emu_k1(int(bwd), modes[mode], wave.ctypes.data, lens.ctypes.data, n, wave.shape[1],
+    rc = lib.emu_k1(warps, int(bwd), modes[mode], wave.ctypes.data, lens.ctypes.data, n, wave.shape[1],
                     mr.ctypes.data if mode != "none" else None,
                     mi.ctypes.data if mode == "reim" else None,
                     mr.shape[1] * mr.shape[2], mr.shape[2], win.ctypes.data, melf.ctypes.data,
@@ -80,8 +49,35 @@ def _k1(lib, bwd, mode, b, mel, window, dE=None, vec_ok=1):
     return out, gr, gi
 
 
+@pytest.mark.parametrize("length,sym", [(16000, True), (5000, True), (4999, False), (333, True),
+                                        (161, True), (100, True), (1, True)])
+def test_emulated_stft_matches_oracle(emu, length, sym):
+    """Unit mel basis picks single bins: with masks (1,0) / (0,1) the forward output is
+    log1p(Re^2) / log1p(Im^2) of every bin, i.e. the STFT itself (edge tiles, unaligned path)."""
+    rs = np.random.RandomState(length)
+    wave = (0.1 * rs.randn(1, length + 7)).astype(np.float32)   # trailing garbage must not be read
+    window = orc.hamming_window(320, sym)
+    spec = orc.stft_frames(wave[0], length, window.astype(np.float32).astype(np.float64))
+    t_i = spec.shape[1]
+    scale = np.abs(spec).max() ** 2
+    # 80 single-bin "filters" per run (bins lo..lo+79), two runs cover all 161 bins
+    for lo in (0, 81):
+        nb = min(80, 161 - lo)
+        mel = np.zeros((nb, 161))
+        mel[np.arange(nb), lo + np.arange(nb)] = 1.0
+        for which, vec_ok in (("re", 1), ("im", 0)):
+            b = dict(wave=wave, lengths=np.array([length]), tmax=t_i,
+                     mask_r=np.full((1, 161, t_i), 1.0 if which == "re" else 0.0, np.float32),
+                     mask_i=np.full((1, 161, t_i), 0.0 if which == "re" else 1.0, np.float32))
+            y, _, _ = _k1(emu, 4, 0, "reim", b, mel, window, vec_ok=vec_ok)
+            got = np.expm1(y[0].astype(np.float64))
+            ref = (spec.real if which == "re" else spec.imag)[lo:lo + nb] ** 2
+            assert np.abs(got - ref).max() / scale < 3e-6, (lo, which)
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 5])
 @pytest.mark.parametrize("mode", ["reim", "power", "none"])
-def test_emulated_k1_forward_and_backward(emu, mode):
+def test_emulated_k1_forward_and_backward(emu, mode, warps):
     b = _synth.make_batch(3, 5000, seed=17, ragged=True, tonal=(mode == "power"))
     mel, window = orc.mel_filterbank(), orc.hamming_window()
     mel32 = mel.astype(np.float32).astype(np.float64)
@@ -90,7 +86,7 @@ def test_emulated_k1_forward_and_backward(emu, mode):
     mi = b["mask_i"] if mode == "reim" else None
     y_ref, fl = orc.lmfb_forward(b["wave"], b["lengths"], mr, mi, mel32, win32, mask_mode=mode,
                                  cmvn_mode="none")
-    y, _, _ = _k1(emu, 0, mode, b, mel, window)
+    y, _, _ = _k1(emu, warps, 0, mode, b, mel, window)
     assert not np.isnan(y).any()
     assert orc.rel_err(y, y_ref) < 2e-5
     for i in range(3):
@@ -102,7 +98,7 @@ def test_emulated_k1_forward_and_backward(emu, mode):
     dE = b["grad_out"].astype(np.float64) * np.exp(-y_ref)
     for i in range(3):
         dE[i, :, fl[i]:] = 0.0
-    _, gr, gi = _k1(emu, 1, mode, b, mel, window, dE=dE)
+    _, gr, gi = _k1(emu, warps, 1, mode, b, mel, window, dE=dE)
     assert not np.isnan(gr).any()
     assert orc.rel_err(gr, g_ref["grad_mask_r"]) < 2e-5
     if mode == "reim":
@@ -111,20 +107,23 @@ def test_emulated_k1_forward_and_backward(emu, mode):
 
 
 def test_mel_band_tables(emu):
-    vp = ctypes.c_void_p
-    emu.emu_mel_band.argtypes = [vp, ctypes.c_int, vp, vp, vp]
     for n_mels in (40, 23, 64, 80):
-        mel = np.ascontiguousarray(orc.mel_filterbank(n_mels=n_mels), dtype=np.float32)
-        wl = np.zeros(161, np.float32); wh = np.zeros(161, np.float32); ml = np.zeros(161, np.int32)
-        assert emu.emu_mel_band(mel.ctypes.data, n_mels, wl.ctypes.data, wh.ctypes.data, ml.ctypes.data) == 0
-        rebuilt = np.zeros_like(mel)
-        for f in range(161):
-            if ml[f] < n_mels:
-                rebuilt[ml[f], f] += 4 * wl[f]
-            if ml[f] + 1 < n_mels:
-                rebuilt[ml[f] + 1, f] += 4 * wh[f]
-        assert np.array_equal(rebuilt, mel)
-        assert np.all(np.diff(ml) >= 0)
+        for warps in (1, 2, 4, 5):
+            mel = np.ascontiguousarray(orc.mel_filterbank(n_mels=n_mels), dtype=np.float32)
+            wl = np.zeros(161, np.float32); wh = np.zeros(161, np.float32)
+            ml = np.zeros(161, np.int32); mbeg = np.zeros(9, np.int32)
+            assert emu.emu_mel_band(mel.ctypes.data, n_mels, warps, wl.ctypes.data, wh.ctypes.data,
+                                    ml.ctypes.data, mbeg.ctypes.data) == 0
+            rebuilt = np.zeros_like(mel)
+            for f in range(161):
+                if ml[f] < n_mels:
+                    rebuilt[ml[f], f] += 4 * wl[f]
+                if ml[f] + 1 < n_mels:
+                    rebuilt[ml[f] + 1, f] += 4 * wh[f]
+            assert np.array_equal(rebuilt, mel)
+            assert np.all(np.diff(ml) >= 0)
     dense = np.ones((40, 161), dtype=np.float32)
-    wl = np.zeros(161, np.float32); wh = np.zeros(161, np.float32); ml = np.zeros(161, np.int32)
-    assert emu.emu_mel_band(dense.ctypes.data, 40, wl.ctypes.data, wh.ctypes.data, ml.ctypes.data) == -1
+    wl = np.zeros(161, np.float32); wh = np.zeros(161, np.float32)
+    ml = np.zeros(161, np.int32); mbeg = np.zeros(9, np.int32)
+    assert emu.emu_mel_band(dense.ctypes.data, 40, 4, wl.ctypes.data, wh.ctypes.data, ml.ctypes.data,
+                            mbeg.ctypes.data) == -1
