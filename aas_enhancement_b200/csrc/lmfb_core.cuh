@@ -68,9 +68,10 @@ enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2 };
 // so the bins whose lower filter is m form the contiguous range [fend[m-1], fend[m]).
 // Weights already carry the 1/4 that undoes X' = 2X.
 struct BinEnt {
-    float    wl, wh;
-    uint32_t off;      // float offset of the bin's masked power inside a scratch column (forward)
-    uint32_t dd;       // backward: dlo | dhi << 8, the (always valid) dE rows that wl / wh multiply
+    float    wl, wh;   // forward: weights into filters ml, ml+1.  backward: weights of dE rows dlo, dlo+1
+    uint32_t off;      // forward: float offset of the bin's masked power inside a scratch column
+                       // backward: dlo * (floats per dE row), dlo+1 always being a valid row
+    uint32_t moff;     // f * (floats per mask row)
 };
 struct MelBand {
     BinEnt  ent[kBins];
@@ -167,13 +168,16 @@ LMFB_HD void stage_rows_slow(int lane, const StageLane& sl, const float* __restr
     }
 }
 
+// hop-row r feeds frame r (first half, r < 32) and frame r-1 (second half, r >= 1).  The 31 rows
+// 1..31 feed two frames each and are dealt to the warps in equal shares, loaded in one batch per
+// warp without any per-row predicate; rows 0 and 32 (one frame each) go to warps 0 and W-1.
 template <int W>
 LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
                         int t0, float2* __restrict__ S, bool vec_ok) {
-    constexpr int kRowsPerWarp = (kTile + 1 + W - 1) / W;
-    constexpr int kBatch = kRowsPerWarp <= 9 ? kRowsPerWarp : 9;
-    const int r_lo = w * kRowsPerWarp;
-    const int r_hi = r_lo + kRowsPerWarp < kTile + 1 ? r_lo + kRowsPerWarp : kTile + 1;
+    constexpr int kShare = (kTile - 1 + W - 1) / W;               // rows per warp (last warp may have fewer)
+    constexpr int kBatch = kShare <= 8 ? kShare : 8;
+    const int r_lo = 1 + w * kShare;
+    const int r_hi = r_lo + kShare < kTile ? r_lo + kShare : kTile;
 #pragma unroll 1
     for (int r0 = r_lo; r0 < r_hi; r0 += kBatch) {
         const int r1 = r0 + kBatch < r_hi ? r0 + kBatch : r_hi;
@@ -182,20 +186,50 @@ LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __res
             continue;
         }
         const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r0 - 1) * kHop) + lane;
+        float2* da0 = S + sl.slot_a[0] + r0; float2* db0 = S + sl.slot_b[0] + r0 - 1;
+        float2* da1 = S + sl.slot_a[1] + r0; float2* db1 = S + sl.slot_b[1] + r0 - 1;
+        float2* da2 = S + sl.slot_a[2] + r0; float2* db2 = S + sl.slot_b[2] + r0 - 1;
         float2 v[kBatch][3];
+        if (r1 - r0 == kBatch) {                                  // full batch: no predicates at all
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            const bool on = r0 + i < r1;
-            v[i][0] = on ? LMFB_LDG(src + i * 80) : make_float2(0.0f, 0.0f);
-            v[i][1] = on ? LMFB_LDG(src + i * 80 + 32) : make_float2(0.0f, 0.0f);
-            v[i][2] = (on && lane < 16) ? LMFB_LDG(src + i * 80 + 64) : make_float2(0.0f, 0.0f);
+            for (int i = 0; i < kBatch; ++i) {
+                v[i][0] = LMFB_LDG(src + i * 80);
+                v[i][1] = LMFB_LDG(src + i * 80 + 32);
+                if (lane < 16) v[i][2] = LMFB_LDG(src + i * 80 + 64);
+            }
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+                da0[i] = make_float2(v[i][0].x * sl.wa0[0], v[i][0].y * sl.wa1[0]);
+                db0[i] = make_float2(v[i][0].x * sl.wb0[0], v[i][0].y * sl.wb1[0]);
+                da1[i] = make_float2(v[i][1].x * sl.wa0[1], v[i][1].y * sl.wa1[1]);
+                db1[i] = make_float2(v[i][1].x * sl.wb0[1], v[i][1].y * sl.wb1[1]);
+                if (lane < 16) {
+                    da2[i] = make_float2(v[i][2].x * sl.wa0[2], v[i][2].y * sl.wa1[2]);
+                    db2[i] = make_float2(v[i][2].x * sl.wb0[2], v[i][2].y * sl.wb1[2]);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int r = r0; r < r1; ++r) {
+                const float2* s2 = src + (r - r0) * 80;
+                stage_store(sl, S, r, 0, LMFB_LDG(s2));
+                stage_store(sl, S, r, 1, LMFB_LDG(s2 + 32));
+                if (lane < 16) stage_store(sl, S, r, 2, LMFB_LDG(s2 + 64));
+            }
         }
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            if (r0 + i < r1) {
-                stage_store(sl, S, r0 + i, 0, v[i][0]);
-                stage_store(sl, S, r0 + i, 1, v[i][1]);
-                if (lane < 16) stage_store(sl, S, r0 + i, 2, v[i][2]);
+    }
+    // the two half rows
+    const int r_edge = w == 0 ? 0 : (w == W - 1 ? kTile : -1);
+    if (W == 1 || r_edge >= 0) {
+#pragma unroll 1
+        for (int r = (W == 1 ? 0 : r_edge); r <= (W == 1 ? kTile : r_edge); r += kTile) {
+            if (!rows_interior(t0 + r - 1, t0 + r, len, vec_ok)) {
+                stage_rows_slow(lane, sl, wave_row, len, t0, S, r, r + 1);
+            } else {
+                const float2* s2 = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r - 1) * kHop) + lane;
+                stage_store(sl, S, r, 0, LMFB_LDG(s2));
+                stage_store(sl, S, r, 1, LMFB_LDG(s2 + 32));
+                if (lane < 16) stage_store(sl, S, r, 2, LMFB_LDG(s2 + 64));
             }
         }
     }
@@ -268,19 +302,20 @@ struct StepIn {
 
 template <int MASK, bool BWD>
 LMFB_HD void load_step(int k2, const MelBand& mb, const float* __restrict__ mr, const float* __restrict__ mi,
-                       unsigned sf, const float* __restrict__ dE, unsigned sem, StepIn<MASK, BWD>& in) {
+                       const float* __restrict__ dE, unsigned sem, StepIn<MASK, BWD>& in) {
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
         const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
-        const unsigned of = f * sf, op = fp * sf;
+        const unsigned of = mb.ent[f].moff, op = mb.ent[fp].moff;
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(mr + of); in.vr[5 + k1] = LMFB_LDG(mr + op); }
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(mi + of); in.vi[5 + k1] = LMFB_LDG(mi + op); }
         if (BWD) {
-            const unsigned df = mb.ent[f].dd, dp = mb.ent[fp].dd;
-            in.d0[k1]     = LMFB_LDG(dE + (df & 255u) * sem);
-            in.d1[k1]     = LMFB_LDG(dE + (df >> 8) * sem);
-            in.d0[5 + k1] = LMFB_LDG(dE + (dp & 255u) * sem);
-            in.d1[5 + k1] = LMFB_LDG(dE + (dp >> 8) * sem);
+            const float* pf = dE + mb.ent[f].off;
+            const float* pp = dE + mb.ent[fp].off;
+            in.d0[k1]     = LMFB_LDG(pf);
+            in.d1[k1]     = LMFB_LDG(pf + sem);
+            in.d0[5 + k1] = LMFB_LDG(pp);
+            in.d1[5 + k1] = LMFB_LDG(pp + sem);
         }
     }
 }
@@ -295,7 +330,7 @@ LMFB_HD void load_step(int k2, const MelBand& mb, const float* __restrict__ mr, 
 // ---------------------------------------------------------------------------------------
 template <int MASK, bool BWD>
 LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, const StepIn<MASK, BWD>& in,
-                        float* __restrict__ gr, float* __restrict__ gi, unsigned gsf, bool inrow) {
+                        float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
     const int kb = (32 - k2) & 31;
     float2* ca = col + k2 * kPitch;
     float2* cb = col + kb * kPitch;
@@ -325,16 +360,17 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, con
             cb[kp * 32 * kPitch] = sp2;
         } else {
             const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
+            const unsigned of = mb.ent[f].moff, op = mb.ent[fp].moff;
             const float dpf = fmaf(mb.ent[f].wh, in.d1[k1], mb.ent[f].wl * in.d0[k1]);
             const float dpp = fmaf(mb.ent[fp].wh, in.d1[5 + k1], mb.ent[fp].wl * in.d0[5 + k1]);
             if (MASK == kMaskReim) {
-                st_if(gr + f * gsf,  2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
-                st_if(gi + f * gsf,  2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
-                st_if(gr + fp * gsf, 2.0f * in.vr[5 + k1] * xp.x * xp.x * dpp, inrow);
-                st_if(gi + fp * gsf, 2.0f * in.vi[5 + k1] * xp.y * xp.y * dpp, inrow);
+                st_if(gr + of, 2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
+                st_if(gi + of, 2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
+                st_if(gr + op, 2.0f * in.vr[5 + k1] * xp.x * xp.x * dpp, inrow);
+                st_if(gi + op, 2.0f * in.vi[5 + k1] * xp.y * xp.y * dpp, inrow);
             } else {
-                st_if(gr + f * gsf,  fmaf(xf.x, xf.x, xf.y * xf.y) * dpf, inrow);
-                st_if(gr + fp * gsf, fmaf(xp.x, xp.x, xp.y * xp.y) * dpp, inrow);
+                st_if(gr + of, fmaf(xf.x, xf.x, xf.y * xf.y) * dpf, inrow);
+                st_if(gr + op, fmaf(xp.x, xp.x, xp.y * xp.y) * dpp, inrow);
             }
         }
     }
@@ -342,21 +378,22 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, con
 
 // pass 2 over the 17 column pairs, dealt round-robin to the W warps; the global inputs of a
 // warp's next step are loaded into a second register set while the current step is computed.
+// `a` must already hold the inputs of the warp's first step (k2 = w): the caller issues that
+// load before the block barrier that ends pass 1, so its latency hides behind the barrier.
 template <int W, int MASK, bool BWD>
-LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb,
-                       const float* __restrict__ mr, const float* __restrict__ mi, unsigned sf,
+LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb, StepIn<MASK, BWD>& a,
+                       const float* __restrict__ mr, const float* __restrict__ mi,
                        const float* __restrict__ dE, unsigned sem,
                        float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
-    StepIn<MASK, BWD> a, b;
-    load_step<MASK, BWD>(w, mb, mr, mi, sf, dE, sem, a);
+    StepIn<MASK, BWD> b;
 #pragma unroll 1
     for (int k2 = w; k2 <= 16; k2 += 2 * W) {
         const bool has_b = k2 + W <= 16;
-        if (has_b) load_step<MASK, BWD>(k2 + W, mb, mr, mi, sf, dE, sem, b);
-        pass2_step<MASK, BWD>(col, k2, mb, a, gr, gi, sf, inrow);
+        if (has_b) load_step<MASK, BWD>(k2 + W, mb, mr, mi, dE, sem, b);
+        pass2_step<MASK, BWD>(col, k2, mb, a, gr, gi, inrow);
         if (has_b) {
-            if (k2 + 2 * W <= 16) load_step<MASK, BWD>(k2 + 2 * W, mb, mr, mi, sf, dE, sem, a);
-            pass2_step<MASK, BWD>(col, k2 + W, mb, b, gr, gi, sf, inrow);
+            if (k2 + 2 * W <= 16) load_step<MASK, BWD>(k2 + 2 * W, mb, mr, mi, dE, sem, a);
+            pass2_step<MASK, BWD>(col, k2 + W, mb, b, gr, gi, inrow);
         }
     }
 }
@@ -365,7 +402,7 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb,
 // phase 3 (forward): banded mel accumulation filter by filter (E[m] parked in the free .y of
 // slot 1+m), then log1p + store in an unrolled second sweep.  Warp w owns filters
 // [mbeg[w], mbeg[w+1]); to get the upper-weight contributions of its first filter it starts
-// one filter early and discards that filter's sum.
+// one filter early and discards that filter's (partial) sum.
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
 LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const MelBand& mb,
@@ -374,25 +411,38 @@ LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const MelBand& mb,
     const int m_lo = mb.mbeg[w], m_hi = mb.mbeg[w + 1];
     if (m_lo >= m_hi) return;
     const int m_first = m_lo > 0 ? m_lo - 1 : 0;
-    int f = m_first > 0 ? (int)mb.fend[m_first - 1] : 0;
+    const int f_lo = m_first > 0 ? (int)mb.fend[m_first - 1] : 0;
+    const int f_hi = mb.fend[m_hi - 1];
+    int m = m_first;
+    int fe = mb.fend[m];
     float acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll 1
-    for (int m = m_first; m < m_hi; ++m) {
-        const int fe = mb.fend[m];
+    float* ep = colf + (1 + m_first) * 2 * kPitch + 1;     // E[m] -> .y of slot 1+m
 #pragma unroll 4
-        for (; f < fe; ++f) {
-            const float p = colf[mb.ent[f].off];
-            acc0 = fmaf(mb.ent[f].wl, p, acc0);
-            acc1 = fmaf(mb.ent[f].wh, p, acc1);
+    for (int f = f_lo; f < f_hi; ++f) {
+        while (f >= fe) {                                  // filter m is complete (rare: ~1 bin in 4)
+            if (m >= m_lo) *ep = acc0;                     // the early filter m_lo-1 belongs to another warp
+            ep += 2 * kPitch;
+            acc0 = acc1; acc1 = 0.0f;
+            fe = mb.fend[++m];
         }
-        if (m >= m_lo) colf[(1 + m) * 2 * kPitch + 1] = acc0;
-        acc0 = acc1;
-        acc1 = 0.0f;
+        const float p = colf[mb.ent[f].off];
+        acc0 = fmaf(mb.ent[f].wl, p, acc0);
+        acc1 = fmaf(mb.ent[f].wh, p, acc1);
     }
+#pragma unroll 1
+    for (; m < m_hi; ++m) {                                // the last filter(s), incl. empty ones
+        if (m >= m_lo) *ep = acc0;
+        ep += 2 * kPitch;
+        acc0 = acc1; acc1 = 0.0f;
+    }
+    const float* eq = colf + (1 + m_lo) * 2 * kPitch + 1;
+    float* op = out + (unsigned)m_lo * som;
 #pragma unroll 4
-    for (int m = m_lo; m < m_hi; ++m) {
-        const float y = valid ? log1pf(colf[(1 + m) * 2 * kPitch + 1]) : 0.0f;
-        st_if(out + (unsigned)m * som, y, inrow);
+    for (m = m_lo; m < m_hi; ++m) {
+        const float y = valid ? log1pf(*eq) : 0.0f;
+        st_if(op, y, inrow);
+        eq += 2 * kPitch;
+        op += som;
     }
 }
 

@@ -43,13 +43,10 @@ struct K1Args {
     int            vec_ok;
 };
 
-// warps per tile (see lmfb_core.cuh); 5 CTAs are resident per SM either way
-constexpr int kWFwd = 4;
-constexpr int kWBwd = 4;
-constexpr int kCtasPerSM = 5;               // 5 x (42,240 + 1,024) B of shared memory per SM
+constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
 
-template <int MASK, bool BWD, int W>
-__global__ void __launch_bounds__(kTile * W, kCtasPerSM)
+template <int MASK, bool BWD, int W, int CTAS>
+__global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     extern __shared__ __align__(16) float2 S[];
     const int lane = threadIdx.x & 31;
@@ -106,11 +103,15 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
         __syncthreads();
         fft_pass1<W>(w, col);
-        __syncthreads();
         // loads of out-of-row lanes are redirected to the last column of the row (always readable)
         const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
-        fft_pass2<W, MASK, BWD>(w, col, mb, a.mask_r + moff + clamp, a.mask_i + moff + clamp, a.msf,
-                                a.dE + row_nm + clamp, som, a.gr + moff, a.gi + moff, inrow);
+        const float* mr = a.mask_r + moff + clamp;
+        const float* mi = a.mask_i + moff + clamp;
+        const float* de = a.dE + row_nm + clamp;
+        StepIn<MASK, BWD> first;                    // issued before the barrier: its latency hides behind it
+        load_step<MASK, BWD>(w, mb, mr, mi, de, som, first);
+        __syncthreads();
+        fft_pass2<W, MASK, BWD>(w, col, mb, first, mr, mi, de, som, a.gr + moff, a.gi + moff, inrow);
         if (!BWD) {
             __syncthreads();
             phase3_fwd(w, col, mb, a.out + row_nm, som, inrow, valid);
@@ -242,9 +243,38 @@ cmvn_bwd(const float* __restrict__ z, const float* __restrict__ stats,
 // ======================================================================================
 using namespace aas_lmfb;
 
+typedef void (*k1_fn)(const K1Args, const MelBand);
+
+struct K1Variant { int warps, ctas; k1_fn fwd[3], bwd[3]; };   // indexed by mask mode
+
+#define LMFB_VARIANT(W, C)                                                                       \
+    { W, C,                                                                                      \
+      { (k1_fn)lmfb_k1<kMaskNone, false, W, C>, (k1_fn)lmfb_k1<kMaskReim, false, W, C>,          \
+        (k1_fn)lmfb_k1<kMaskPower, false, W, C> },                                               \
+      { nullptr, (k1_fn)lmfb_k1<kMaskReim, true, W, C>, (k1_fn)lmfb_k1<kMaskPower, true, W, C> } }
+
+// (warps per tile, resident CTAs per SM the register budget is sized for)
+static const K1Variant kVariants[] = {
+    LMFB_VARIANT(4, 5), LMFB_VARIANT(2, 5), LMFB_VARIANT(3, 5), LMFB_VARIANT(5, 4), LMFB_VARIANT(1, 5),
+};
+constexpr int kDefaultFwdVariant = 0;       // 4 warps
+constexpr int kDefaultBwdVariant = 2;       // 3 warps (two register sets of 40 prefetched values)
+
+static int pick_variant(const char* env, int dflt) {
+    const char* v = getenv(env);            // tuning knob: warps per tile
+    if (v) {
+        const int wanted = atoi(v);
+        for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
+            if (kVariants[i].warps == wanted) return (int)i;
+    }
+    return dflt;
+}
+
 struct aas_lmfb_plan {
-    MelBand band;
+    MelBand fwd, bwd;
+    uint8_t dlo[kBins];
     int     n_mels;
+    int     vfwd, vbwd;
 };
 
 extern "C" int aas_lmfb_abi_version(void) { return AAS_LMFB_ABI_VERSION; }
@@ -254,7 +284,7 @@ extern "C" const char* aas_lmfb_strerror(int code) {
         case AAS_LMFB_OK:      return "ok";
         case AAS_LMFB_E_NULL:  return "aas_lmfb: required pointer is NULL";
         case AAS_LMFB_E_ALIGN: return "aas_lmfb: buffer is not sufficiently aligned";
-        case AAS_LMFB_E_SHAPE: return "aas_lmfb: unsupported shape (n_bins must be 161, 1 <= n_mels <= 128, n >= 0, tmax >= 1)";
+        case AAS_LMFB_E_SHAPE: return "aas_lmfb: unsupported shape (n_bins must be 161, 2 <= n_mels <= 128, n >= 0, 1 <= tmax and mask row stride <= 2^24)";
         case AAS_LMFB_E_FLAGS: return "aas_lmfb: invalid mask/cmvn flags";
         case AAS_LMFB_E_MEL:   return "aas_lmfb: mel basis is not banded (each bin may feed at most two adjacent, frequency-ordered filters)";
         case AAS_LMFB_E_NOMEM: return "aas_lmfb: host allocation failed";
@@ -269,12 +299,16 @@ extern "C" aas_lmfb_plan* aas_lmfb_plan_create(const float* mel, int n_mels, int
     aas_lmfb_plan* p = nullptr;
     do {
         if (!mel) { st = AAS_LMFB_E_NULL; break; }
-        if (n_bins != kBins || n_mels < 1 || n_mels > kMaxMels) { st = AAS_LMFB_E_SHAPE; break; }
+        if (n_bins != kBins || n_mels < 2 || n_mels > kMaxMels) { st = AAS_LMFB_E_SHAPE; break; }
         p = new (std::nothrow) aas_lmfb_plan;
         if (!p) { st = AAS_LMFB_E_NOMEM; break; }
         memset(p, 0, sizeof(*p));
         p->n_mels = n_mels;
-        if (build_mel_band(mel, n_mels, kWFwd, &p->band) != 0) st = AAS_LMFB_E_MEL;
+        p->vfwd = pick_variant("AAS_LMFB_WARPS_FWD", kDefaultFwdVariant);
+        p->vbwd = pick_variant("AAS_LMFB_WARPS_BWD", kDefaultBwdVariant);
+        int ml[kBins];
+        if (build_mel_band(mel, n_mels, kVariants[p->vfwd].warps, &p->fwd, ml) != 0) { st = AAS_LMFB_E_MEL; break; }
+        make_bwd_band(p->fwd, ml, &p->bwd, p->dlo);
     } while (0);
     if (st != AAS_LMFB_OK && p) { delete p; p = nullptr; }
     if (status) *status = st;
@@ -289,17 +323,6 @@ extern "C" size_t aas_lmfb_workspace_bytes(int n, int n_mels, int tmax, uint32_t
 }
 
 namespace {
-
-typedef void (*k1_fn)(const K1Args, const MelBand);
-
-k1_fn pick_k1(unsigned mask, bool bwd) {
-    switch (mask) {
-        case AAS_LMFB_MASK_NONE:  return bwd ? nullptr : (k1_fn)lmfb_k1<kMaskNone, false, kWFwd>;
-        case AAS_LMFB_MASK_REIM:  return bwd ? (k1_fn)lmfb_k1<kMaskReim, true, kWBwd>  : (k1_fn)lmfb_k1<kMaskReim, false, kWFwd>;
-        case AAS_LMFB_MASK_POWER: return bwd ? (k1_fn)lmfb_k1<kMaskPower, true, kWBwd> : (k1_fn)lmfb_k1<kMaskPower, false, kWFwd>;
-    }
-    return nullptr;
-}
 
 // cudaFuncSetAttribute is per (function, device); do it once each so that launches inside
 // a CUDA-graph capture are pure stream work.
@@ -320,7 +343,8 @@ int ensure_attrs(k1_fn fn) {
     return 0;
 }
 
-int launch_k1(k1_fn fn, int warps, K1Args& a, const MelBand& mb, int n, cudaStream_t stream) {
+int launch_k1(const K1Variant& v, k1_fn fn, K1Args& a, const MelBand& mb, int n, cudaStream_t stream) {
+    if (!fn) return AAS_LMFB_E_FLAGS;
     const int rc = ensure_attrs(fn);
     if (rc) return rc;
     const long long total = (long long)n * a.tiles_per_utt;
@@ -331,9 +355,10 @@ int launch_k1(k1_fn fn, int warps, K1Args& a, const MelBand& mb, int n, cudaStre
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    const long long resident = (long long)sms * kCtasPerSM;       // one CTA per scratch slot
+    const int per_sm = v.ctas < kScratchPerSM ? v.ctas : kScratchPerSM;
+    const long long resident = (long long)sms * per_sm;           // one persistent CTA per scratch slot
     const unsigned blocks = (unsigned)(total < resident ? total : resident);
-    fn<<<blocks, kTile * warps, kScratchBytes, stream>>>(a, mb);
+    fn<<<blocks, kTile * v.warps, kScratchBytes, stream>>>(a, mb);
     return (int)cudaPeekAtLastError();
 }
 
@@ -381,8 +406,11 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
     a.tiles_per_utt = (tmax + kTile - 1) / kTile;
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
 
+    MelBand band = plan->fwd;
+    patch_strides(&band, a.msf, nullptr, 0);
+    const K1Variant& v = kVariants[plan->vfwd];
     rec(prof, 0, stream);
-    rc = launch_k1(pick_k1(mask, false), kWFwd, a, plan->band, n, stream);
+    rc = launch_k1(v, v.fwd[mask], a, band, n, stream);
     rec(prof, 1, stream);
     if (rc) return rc;
     rec(prof, 2, stream);
@@ -434,8 +462,11 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     a.tiles_per_utt = (tmax + kTile - 1) / kTile;
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
 
+    MelBand band = plan->bwd;
+    patch_strides(&band, a.msf, plan->dlo, (unsigned)tmax);
+    const K1Variant& v = kVariants[plan->vbwd];
     rec(prof, 0, stream);
-    rc = launch_k1(pick_k1(mask, true), kWBwd, a, plan->band, n, stream);
+    rc = launch_k1(v, v.bwd[mask], a, band, n, stream);
     rec(prof, 1, stream);
     return rc;
 }

@@ -15,6 +15,30 @@ inline uint32_t kBinOffHost(int f) {
 // Returns 0 on success, -1 if some bin feeds a filter outside the two live ones (basis not
 // banded / not frequency-ordered).  ml_out (optional, kBins ints) receives the lower filter of
 // every bin (n_mels for bins above the last filter).
+inline void split_filters(MelBand* out, int warps);
+
+// Per-launch patch: row offsets depend on the caller's strides.
+//   fwd: ent[f].moff = f * msf.   bwd: additionally ent[f].off = dlo[f] * sem.
+inline void patch_strides(MelBand* band, unsigned msf, const uint8_t* dlo /*nullable*/, unsigned sem) {
+    for (int f = 0; f < kBins; ++f) {
+        band->ent[f].moff = (uint32_t)f * msf;
+        if (dlo) band->ent[f].off = (uint32_t)dlo[f] * sem;
+    }
+}
+
+// Backward table from the forward one: weights re-expressed on the always-valid row pair
+// (dlo, dlo+1) of dE.  Needs n_mels >= 2.
+inline void make_bwd_band(const MelBand& fwd, const int* ml, MelBand* bwd, uint8_t* dlo) {
+    *bwd = fwd;
+    const int n_mels = fwd.n_mels;
+    for (int f = 0; f < kBins; ++f) {
+        BinEnt& e = bwd->ent[f];
+        if (ml[f] <= n_mels - 2)      { dlo[f] = (uint8_t)ml[f]; }
+        else if (ml[f] == n_mels - 1) { dlo[f] = (uint8_t)(n_mels - 2); e.wh = fwd.ent[f].wl; e.wl = 0.0f; }
+        else                          { dlo[f] = 0; e.wl = e.wh = 0.0f; }
+    }
+}
+
 inline int build_mel_band(const float* mel, int n_mels, int warps, MelBand* out, int* ml_out = nullptr) {
     int hi[kMaxMels];                 // last bin with a non-zero weight, per filter (-1: empty)
     for (int m = 0; m < n_mels; ++m) {
@@ -33,14 +57,18 @@ inline int build_mel_band(const float* mel, int n_mels, int warps, MelBand* out,
         e.wl = ml < n_mels ? 0.25f * mel[ml * kBins + f] : 0.0f;
         e.wh = ml + 1 < n_mels ? 0.25f * mel[(ml + 1) * kBins + f] : 0.0f;
         e.off = kBinOffHost(f);
-        const uint32_t dlo = ml < n_mels ? (uint32_t)ml : 0u;            // weights are 0 where clamped
-        const uint32_t dhi = ml + 1 < n_mels ? (uint32_t)(ml + 1) : 0u;
-        e.dd = dlo | (dhi << 8);
+        e.moff = 0;
         for (int m = ml; m < n_mels; ++m) out->fend[m] = (uint8_t)(f + 1);
     }
     // now fend[m] = one past the last bin whose lower filter is <= m (empty ranges repeat the value)
 
-    // split the filters between the warps of the forward kernel, balancing bins*6 + 40 per filter
+    split_filters(out, warps);
+    return 0;
+}
+
+// split the filters between the warps of the forward kernel, balancing bins*6 + 40 per filter
+inline void split_filters(MelBand* out, int warps) {
+    const int n_mels = out->n_mels;
     if (warps < 1) warps = 1;
     if (warps > kMaxW) warps = kMaxW;
     int cost[kMaxMels], total = 0;
@@ -57,7 +85,6 @@ inline int build_mel_band(const float* mel, int n_mels, int warps, MelBand* out,
         while (m < n_mels && acc + cost[m] / 2 < target) acc += cost[m++];
         out->mbeg[w] = (uint8_t)m;
     }
-    return 0;
 }
 
 }  // namespace aas_lmfb

@@ -13,7 +13,7 @@ namespace {
 
 template <int W, int MASK, bool BWD>
 void emu_tile(const float* wave_row, int len, int t0, const float* window, bool vec_ok,
-              const MelBand& mb, const float* mr, const float* mi, unsigned sf,
+              const MelBand& mb, const float* mr, const float* mi, unsigned /*sf*/,
               const float* dE, float* out, unsigned som, float* gr, float* gi, int tmax, int T,
               std::vector<float2>& S) {
     for (int w = 0; w < W; ++w)
@@ -29,8 +29,12 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
             const int t = t0 + lane;
             const bool inrow = t < tmax;
             const long long clamp = inrow ? 0 : (long long)(tmax - 1 - t);
-            fft_pass2<W, MASK, BWD>(w, S.data() + lane, mb, mr ? mr + t + clamp : nullptr,
-                                    mi ? mi + t + clamp : nullptr, sf, dE ? dE + t + clamp : nullptr, som,
+            const float* mrp = mr ? mr + t + clamp : nullptr;
+            const float* mip = mi ? mi + t + clamp : nullptr;
+            const float* dep = dE ? dE + t + clamp : nullptr;
+            StepIn<MASK, BWD> first;
+            load_step<MASK, BWD>(w, mb, mrp, mip, dep, som, first);
+            fft_pass2<W, MASK, BWD>(w, S.data() + lane, mb, first, mrp, mip, dep, som,
                                     gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
         }
     if (!BWD)
@@ -87,9 +91,18 @@ int emu_k1_w(int bwd, int mask_mode, const float* wave, const int* lengths, int 
              long long wave_stride, const float* mask_r, const float* mask_i,
              long long msn, long long msf, const float* window, const float* mel, int n_mels,
              float* out, const float* dE, float* gr, float* gi, int tmax, int vec_ok) {
-    MelBand mb;
+    MelBand mb, mbb;
     memset(&mb, 0, sizeof(mb));
-    if (build_mel_band(mel, n_mels, W, &mb) != 0) return -5;
+    int ml[kBins];
+    uint8_t dlo[kBins];
+    if (build_mel_band(mel, n_mels, W, &mb, ml) != 0) return -5;
+    if (bwd) {
+        make_bwd_band(mb, ml, &mbb, dlo);
+        mb = mbb;
+        patch_strides(&mb, (unsigned)msf, dlo, (unsigned)tmax);
+    } else {
+        patch_strides(&mb, (unsigned)msf, nullptr, 0);
+    }
     switch (mask_mode) {
         case kMaskNone:  emu_k1_impl<W, kMaskNone>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
         case kMaskReim:  emu_k1_impl<W, kMaskReim>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;

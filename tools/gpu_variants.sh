@@ -1,0 +1,17 @@
+#!/bin/bash
+# compare warps-per-tile variants on the sweep workload (and chime) -- no ncu
+mkdir -p gpurun_out
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for wf in 4 2 3 5; do for wb in 3 2 4; do
+  if [ "$wf" != "4" ] && [ "$wb" != "3" ]; then continue; fi
+  for wl in sweep_256x10s chime4_30x6s; do
+    AAS_LMFB_WARPS_FWD=$wf AAS_LMFB_WARPS_BWD=$wb timeout 300 python bench.py --workload $wl --steps 200 --warmup 5 --no-cpu > gpurun_out/v.json 2> gpurun_out/v.err || tail -3 gpurun_out/v.err
+    python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/v.json")); r=d["roofline"]; k=r["kernels_ms"]
+    print("wf=$wf wb=$wb %-14s value %.3e step_frac %.3f  k1f %.4f ms (frac %.3f)  k1b %.4f ms (frac %.3f)" % ("$wl", d["value"], r["step_frac"], k["k1_fwd"], r["k1_fwd_frac"], k["k1_bwd"], r["frac"]))
+except Exception as e: print("failed", e)
+PY
+  done
+done; done
