@@ -257,7 +257,7 @@ struct K1Variant { int warps, ctas; k1_fn fwd[3], bwd[3]; };   // indexed by mas
 static const K1Variant kVariants[] = {
     LMFB_VARIANT(4, 5), LMFB_VARIANT(2, 5), LMFB_VARIANT(3, 5), LMFB_VARIANT(5, 4), LMFB_VARIANT(1, 5),
 };
-constexpr int kDefaultFwdVariant = 0;       // 4 warps
+constexpr int kDefaultFwdVariant = 2;       // 3 warps: measured best (128 registers, no spills)
 constexpr int kDefaultBwdVariant = 2;       // 3 warps (two register sets of 40 prefetched values)
 
 static int pick_variant(const char* env, int dflt) {
