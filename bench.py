@@ -306,7 +306,7 @@ def run_ours(args):
                      "avg_launch_ms": k_avg["k1_bwd"],
                      "kernels_ms": k_avg,
                      "k1_fwd_frac": frames * B_K1_FWD / (k_avg["k1_fwd"] / 1e3) / 1e9 / peak,
-                     "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak / world},
+                     "step_algorithmic_gbs_per_gpu": step_gbs, "step_frac": step_gbs / peak},
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(n, samples, budget_s=12.0)
@@ -322,52 +322,87 @@ def ctypes_array(handles):
 
 
 def measure_e2e(fe, n, samples, tmax, n_mels, audio_s, dev, steps, world):
+    """End to end through the public autograd API with HOST buffers: every step copies wave,
+    lengths, both masks and grad_out from pinned host memory, runs forward + backward, and copies
+    the features and both mask gradients back to pinned host memory.  Copies and compute of
+    consecutive steps overlap on three streams (double-buffered), as a data loader would."""
     import torch.distributed as dist
     gen = torch.Generator()
     gen.manual_seed(123)
-    h_wave = (0.1 * torch.randn(n, samples, generator=gen)).clamp_(-1, 1).pin_memory()
-    h_len = torch.full((n,), samples, dtype=torch.int32).pin_memory()
-    h_mr = torch.rand(n, 161, tmax, generator=gen).pin_memory()
-    h_mi = torch.rand(n, 161, tmax, generator=gen).pin_memory()
-    h_g = torch.randn(n, n_mels, tmax, generator=gen).pin_memory()
-    h_z = torch.empty(n, n_mels, tmax).pin_memory()
-    h_gr = torch.empty(n, 161, tmax).pin_memory()
-    h_gi = torch.empty(n, 161, tmax).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in (h_wave, h_len, h_mr, h_mi, h_g))
-    d2h = sum(t.numel() * t.element_size() for t in (h_z, h_gr, h_gi))
+    nbuf = 2
+    host_in = []
+    for _ in range(nbuf):
+        host_in.append(dict(
+            wave=(0.1 * torch.randn(n, samples, generator=gen)).clamp_(-1, 1).pin_memory(),
+            lens=torch.full((n,), samples, dtype=torch.int32).pin_memory(),
+            mr=torch.rand(n, 161, tmax, generator=gen).pin_memory(),
+            mi=torch.rand(n, 161, tmax, generator=gen).pin_memory(),
+            g=torch.randn(n, n_mels, tmax, generator=gen).pin_memory()))
+    host_out = [dict(z=torch.empty(n, n_mels, tmax).pin_memory(),
+                     gr=torch.empty(n, 161, tmax).pin_memory(),
+                     gi=torch.empty(n, 161, tmax).pin_memory()) for _ in range(nbuf)]
+    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in host_in[0].items()} for _ in range(nbuf)]
+    h2d = sum(t.numel() * t.element_size() for t in host_in[0].values())
+    d2h = sum(t.numel() * t.element_size() for t in host_out[0].values())
+    s_in, s_c, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_c = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_free = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_done = [torch.cuda.Event() for _ in range(nbuf)]
+    keep = [None] * nbuf
 
-    def one():
-        wave = h_wave.to(dev, non_blocking=True)
-        lens = h_len.to(dev, non_blocking=True)
-        mr = h_mr.to(dev, non_blocking=True).requires_grad_(True)
-        mi = h_mi.to(dev, non_blocking=True).requires_grad_(True)
-        g = h_g.to(dev, non_blocking=True)
-        z, _ = fe(wave, lens, mr, mi)
-        z.backward(g)
-        h_z.copy_(z.detach(), non_blocking=True)
-        h_gr.copy_(mr.grad, non_blocking=True)
-        h_gi.copy_(mi.grad, non_blocking=True)
+    def one(i):
+        b = i % nbuf
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[b])                      # compute of step i-nbuf has consumed the buffer
+            for k in dev_in[b]:
+                dev_in[b][k].copy_(host_in[b][k], non_blocking=True)
+            ev_in[b].record(s_in)
+        with torch.cuda.stream(s_c):
+            s_c.wait_event(ev_in[b])
+            s_c.wait_event(ev_done[b])                       # D2H of step i-nbuf has read the old results
+            mr = dev_in[b]["mr"].detach().requires_grad_(True)
+            mi = dev_in[b]["mi"].detach().requires_grad_(True)
+            z, _ = fe(dev_in[b]["wave"], dev_in[b]["lens"], mr, mi)
+            z.backward(dev_in[b]["g"])
+            keep[b] = (z, mr, mi)
+            ev_c[b].record(s_c)
+            ev_free[b].record(s_c)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_c[b])
+            z, mr, mi = keep[b]
+            for t in (z, mr.grad, mi.grad):
+                t.record_stream(s_out)
+            host_out[b]["z"].copy_(z.detach(), non_blocking=True)
+            host_out[b]["gr"].copy_(mr.grad, non_blocking=True)
+            host_out[b]["gi"].copy_(mi.grad, non_blocking=True)
+            ev_done[b].record(s_out)
 
-    for _ in range(3):
-        one()
+    for i in range(4):
+        one(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        one()
-    e1.record()
+    e0.record(s_in)
+    for i in range(steps):
+        one(i)
+    s_out.wait_stream(s_c)
+    e1.record(s_out)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = max(e0.elapsed_time(e1), 0.0)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return {"value": world * audio_s * steps / (ms / 1e3), "unit": "audio-s/s",
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
-            "api": "LMFBFrontEnd.forward + autograd backward; pinned host buffers in, features "
-                   "and both mask gradients copied back to pinned host"}
+            "wall_ms": wall_ms,
+            "api": "LMFBFrontEnd.forward + autograd backward; wave, lengths, both masks and grad_out "
+                   "copied from pinned host memory, features and both mask gradients copied back to "
+                   "pinned host memory, every step; copies of neighbouring steps overlap on 3 streams"}
 
 
 # ------------------------------------------------------------------------------- CPU arm
