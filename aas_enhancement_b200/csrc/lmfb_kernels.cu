@@ -236,6 +236,107 @@ cmvn_bwd(const float* __restrict__ z, const float* __restrict__ stats,
     }
 }
 
+// ---- warp-per-row variants (per-bin CMVN / no CMVN): the row is read ONCE into registers ----
+// One warp owns one (utterance, mel) row of up to 32*KMAX frames; no block barrier, no re-read.
+constexpr int kRowWarps = 4;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(32 * kRowWarps)
+cmvn_fwd_rows(float* __restrict__ out, float* __restrict__ stats, const int32_t* __restrict__ lengths,
+              int n_mels, int rows, int tmax, float eps) {
+    const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int n = row / n_mels;
+    const int T = frames_of(lengths, n, tmax);
+    float* base = out + (long long)row * tmax;
+    if (T == 0) {
+        if (lane == 0) { stats[2 * (long long)row] = 0.0f; stats[2 * (long long)row + 1] = 1.0f; }
+        return;
+    }
+    float v[KMAX];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int t = lane + 32 * k;
+        v[k] = t < T ? base[t] : 0.0f;
+        s += v[k];
+    }
+    const float mean = (float)(warp_sum((double)s) / (double)T);
+    float q = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const float d = (lane + 32 * k) < T ? v[k] - mean : 0.0f;
+        q = fmaf(d, d, q);
+    }
+    const double var = warp_sum((double)q) / (double)(T - 1);
+    const float rstd = 1.0f / ((float)sqrt(var) + eps);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int t = lane + 32 * k;
+        if (t < T) base[t] = (v[k] - mean) * rstd;
+    }
+    if (lane == 0) { stats[2 * (long long)row] = mean; stats[2 * (long long)row + 1] = rstd; }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(32 * kRowWarps)
+cmvn_bwd_rows(const float* __restrict__ z, const float* __restrict__ stats,
+              const float* __restrict__ grad_out, float* __restrict__ dE,
+              const int32_t* __restrict__ lengths, int n_mels, int rows, int tmax, float eps, int mode) {
+    const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int n = row / n_mels;
+    const int T = frames_of(lengths, n, tmax);
+    const float* zb = z + (long long)row * tmax;
+    const float* gb = grad_out + (long long)row * tmax;
+    float* eb = dE + (long long)row * tmax;
+    float g[KMAX], zz[KMAX];
+    float sg = 0.0f, sgz = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int t = lane + 32 * k;
+        g[k] = t < T ? gb[t] : 0.0f;
+        zz[k] = t < T ? zb[t] : 0.0f;
+        sg += g[k];
+        sgz = fmaf(g[k], zz[k], sgz);
+    }
+    float c1 = 0.0f, kk = 0.0f, mean = 0.0f, rstd = 1.0f;
+    if (mode != 0 && T > 0) {
+        const double sg_d = warp_sum((double)sg), sgz_d = warp_sum((double)sgz);
+        mean = stats[2 * (long long)row];
+        rstd = stats[2 * (long long)row + 1];
+        const double sigma = 1.0 / (double)rstd - (double)eps;
+        c1 = (float)(sg_d / (double)T);
+        kk = (float)(sgz_d / ((double)(T - 1) * sigma));
+    }
+    const float inv_rstd = 1.0f / rstd;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int t = lane + 32 * k;
+        if (t < tmax) {
+            float r = 0.0f;
+            if (t < T) {
+                if (mode != 0) {
+                    const float dy = fmaf(rstd, g[k] - c1, -zz[k] * kk);
+                    const float y = fmaf(zz[k], inv_rstd, mean);
+                    r = dy * expf(-y);
+                } else {
+                    r = g[k] * expf(-zz[k]);
+                }
+            }
+            eb[t] = r;
+        }
+    }
+}
+
 }  // namespace aas_lmfb
 
 // ======================================================================================
@@ -257,8 +358,12 @@ struct K1Variant { int warps, ctas; k1_fn fwd[3], bwd[3]; };   // indexed by mas
 static const K1Variant kVariants[] = {
     LMFB_VARIANT(4, 5), LMFB_VARIANT(2, 5), LMFB_VARIANT(3, 5), LMFB_VARIANT(5, 4), LMFB_VARIANT(1, 5),
 };
-constexpr int kDefaultFwdVariant = 2;       // 3 warps: measured best (128 registers, no spills)
-constexpr int kDefaultBwdVariant = 2;       // 3 warps (two register sets of 40 prefetched values)
+// Defaults measured on B200 (profiles/): in the throughput regime (more tiles than resident CTAs)
+// 3 warps per tile win for both directions (128 registers, no spills); in the latency regime (a
+// launch that does not fill the resident slots, e.g. 30 x 6 s) the forward prefers 4 warps and
+// the backward 2 (168 registers, nothing spilled, shortest per-tile critical path).
+constexpr int kFwdVariantBig = 2, kFwdVariantSmall = 0;
+constexpr int kBwdVariantBig = 2, kBwdVariantSmall = 1;
 
 static int pick_variant(const char* env, int dflt) {
     const char* v = getenv(env);            // tuning knob: warps per tile
@@ -304,10 +409,10 @@ extern "C" aas_lmfb_plan* aas_lmfb_plan_create(const float* mel, int n_mels, int
         if (!p) { st = AAS_LMFB_E_NOMEM; break; }
         memset(p, 0, sizeof(*p));
         p->n_mels = n_mels;
-        p->vfwd = pick_variant("AAS_LMFB_WARPS_FWD", kDefaultFwdVariant);
-        p->vbwd = pick_variant("AAS_LMFB_WARPS_BWD", kDefaultBwdVariant);
+        p->vfwd = pick_variant("AAS_LMFB_WARPS_FWD", -1);       // -1: choose by problem size at launch
+        p->vbwd = pick_variant("AAS_LMFB_WARPS_BWD", -1);
         int ml[kBins];
-        if (build_mel_band(mel, n_mels, kVariants[p->vfwd].warps, &p->fwd, ml) != 0) { st = AAS_LMFB_E_MEL; break; }
+        if (build_mel_band(mel, n_mels, 1, &p->fwd, ml) != 0) { st = AAS_LMFB_E_MEL; break; }
         make_bwd_band(p->fwd, ml, &p->bwd, p->dlo);
     } while (0);
     if (st != AAS_LMFB_OK && p) { delete p; p = nullptr; }
@@ -406,17 +511,29 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
     a.tiles_per_utt = (tmax + kTile - 1) / kTile;
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
 
+    const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
+    const K1Variant& v = kVariants[plan->vfwd >= 0 ? plan->vfwd : (small ? kFwdVariantSmall : kFwdVariantBig)];
     MelBand band = plan->fwd;
     patch_strides(&band, a.msf, nullptr, 0);
-    const K1Variant& v = kVariants[plan->vfwd];
+    split_filters(&band, v.warps);
     rec(prof, 0, stream);
     rc = launch_k1(v, v.fwd[mask], a, band, n, stream);
     rec(prof, 1, stream);
     if (rc) return rc;
     rec(prof, 2, stream);
     if (cm != 0) {
-        dim3 grid(cm == 1 ? plan->n_mels : 1, n);
-        cmvn_fwd<<<grid, kRowThreads, 0, stream>>>(out, stats, lengths, plan->n_mels, tmax, eps, (int)cm);
+        const int rows = n * plan->n_mels;
+        const unsigned blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
+        if (cm == 1 && tmax <= 32 * 8) {
+            cmvn_fwd_rows<8><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps);
+        } else if (cm == 1 && tmax <= 32 * 24) {
+            cmvn_fwd_rows<24><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps);
+        } else if (cm == 1 && tmax <= 32 * 48) {
+            cmvn_fwd_rows<48><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps);
+        } else {
+            dim3 grid(cm == 1 ? plan->n_mels : 1, n);
+            cmvn_fwd<<<grid, kRowThreads, 0, stream>>>(out, stats, lengths, plan->n_mels, tmax, eps, (int)cm);
+        }
         rc = (int)cudaPeekAtLastError();
     }
     rec(prof, 3, stream);
@@ -447,8 +564,18 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
 
     rec(prof, 2, stream);
     {
-        dim3 grid(cm == 2 ? 1 : plan->n_mels, n);
-        cmvn_bwd<<<grid, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm);
+        const int rows = n * plan->n_mels;
+        const unsigned blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
+        if (cm != 2 && tmax <= 32 * 8) {
+            cmvn_bwd_rows<8><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, rows, tmax, eps, (int)cm);
+        } else if (cm != 2 && tmax <= 32 * 24) {
+            cmvn_bwd_rows<24><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, rows, tmax, eps, (int)cm);
+        } else if (cm != 2 && tmax <= 32 * 48) {
+            cmvn_bwd_rows<48><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, rows, tmax, eps, (int)cm);
+        } else {
+            dim3 grid(cm == 2 ? 1 : plan->n_mels, n);
+            cmvn_bwd<<<grid, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm);
+        }
         rc = (int)cudaPeekAtLastError();
     }
     rec(prof, 3, stream);
@@ -462,9 +589,10 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     a.tiles_per_utt = (tmax + kTile - 1) / kTile;
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
 
+    const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
+    const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
     MelBand band = plan->bwd;
     patch_strides(&band, a.msf, plan->dlo, (unsigned)tmax);
-    const K1Variant& v = kVariants[plan->vbwd];
     rec(prof, 0, stream);
     rc = launch_k1(v, v.bwd[mask], a, band, n, stream);
     rec(prof, 1, stream);

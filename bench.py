@@ -265,7 +265,7 @@ def run_ours(args):
     k_avg = {k: sum(v) / len(v) for k, v in k_ms.items()}
 
     # ---- e2e: public autograd API, pinned host buffers, copies inside the timed region
-    e2e = measure_e2e(fe, n, samples, tmax, n_mels, audio_s, dev, min(max(args.steps, 5), 40), world)
+    e2e = measure_e2e(fe, n, samples, tmax, n_mels, audio_s, dev, min(max(args.steps, 20), 200), world)
 
     if rank != 0:
         if world > 1:
@@ -378,7 +378,7 @@ def measure_e2e(fe, n, samples, tmax, n_mels, audio_s, dev, steps, world):
             host_out[b]["gi"].copy_(mi.grad, non_blocking=True)
             ev_done[b].record(s_out)
 
-    for i in range(4):
+    for i in range(16):                                      # allocator / autograd paths settle slowly
         one(i)
     torch.cuda.synchronize()
     if world > 1:
