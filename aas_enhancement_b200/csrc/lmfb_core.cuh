@@ -400,12 +400,11 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb, StepI
 
 // ---------------------------------------------------------------------------------------
 // phase 3 (forward): banded mel accumulation filter by filter (E[m] parked in the free .y of
-// slot 1+m), then log1p (or, when a CMVN kernel follows, the raw E) + store in a second sweep.  Warp w owns filters
+// slot 1+m), then log1p + store in an unrolled second sweep.  Warp w owns filters
 // [mbeg[w], mbeg[w+1]); to get the upper-weight contributions of its first filter it starts
 // one filter early and discards that filter's (partial) sum.
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
-template <bool LOG>
 LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const MelBand& mb,
                         float* __restrict__ out, unsigned som, bool inrow, bool valid) {
     float* colf = reinterpret_cast<float*>(col);
@@ -440,8 +439,7 @@ LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const MelBand& mb,
     float* op = out + (unsigned)m_lo * som;
 #pragma unroll 4
     for (m = m_lo; m < m_hi; ++m) {
-        const float e = *eq;
-        const float y = valid ? (LOG ? log1pf(e) : e) : 0.0f;     // !LOG: the CMVN kernel applies log1p
+        const float y = valid ? log1pf(*eq) : 0.0f;
         st_if(op, y, inrow);
         eq += 2 * kPitch;
         op += som;

@@ -41,7 +41,6 @@ struct K1Args {
     int            tiles_per_utt;
     int            total_tiles;
     int            vec_ok;
-    int            raw_e;      // forward: write E instead of log1p(E) (the CMVN kernel takes the log)
 };
 
 constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
@@ -115,8 +114,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         fft_pass2<W, MASK, BWD>(w, col, mb, first, mr, mi, de, som, a.gr + moff, a.gi + moff, inrow);
         if (!BWD) {
             __syncthreads();
-            if (a.raw_e) phase3_fwd<false>(w, col, mb, a.out + row_nm, som, inrow, valid);
-            else         phase3_fwd<true>(w, col, mb, a.out + row_nm, som, inrow, valid);
+            phase3_fwd(w, col, mb, a.out + row_nm, som, inrow, valid);
         }
         __syncthreads();                            // the scratch is free for the next tile
     }
@@ -163,12 +161,7 @@ cmvn_fwd(float* __restrict__ out, float* __restrict__ stats, const int32_t* __re
     }
     float s = 0.0f;
     for (int m = m0; m < m1; ++m)
-        for (int t = threadIdx.x; t < T; t += kRowThreads) {
-            const long long i = (long long)m * tmax + t;
-            const float y = log1pf(base[i]);             // K1 left the raw mel energies E
-            base[i] = y;
-            s += y;
-        }
+        for (int t = threadIdx.x; t < T; t += kRowThreads) s += base[(long long)m * tmax + t];
     const double mean_d = block_sum((double)s, red) / (double)cnt;
     const float mean = (float)mean_d;
     float v = 0.0f;
@@ -272,7 +265,7 @@ cmvn_fwd_rows(float* __restrict__ out, float* __restrict__ stats, const int32_t*
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         const int t = lane + 32 * k;
-        v[k] = t < T ? log1pf(base[t]) : 0.0f;            // K1 left the raw mel energies E
+        v[k] = t < T ? base[t] : 0.0f;
         s += v[k];
     }
     const float mean = (float)(warp_sum((double)s) / (double)T);
@@ -515,7 +508,6 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
     a.wave = wave; a.lengths = lengths; a.wave_stride = wave_stride;
     a.mask_r = mask_r; a.mask_i = mask_i; a.msn = mask_stride_n; a.msf = (unsigned)mask_stride_f;
     a.window = window; a.out = out; a.tmax = tmax;
-    a.raw_e = cm != 0 ? 1 : 0;
     a.tiles_per_utt = (tmax + kTile - 1) / kTile;
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
 

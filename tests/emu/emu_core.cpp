@@ -41,7 +41,7 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
         for (int w = 0; w < W; ++w)
             for (int lane = 0; lane < 32; ++lane) {
                 const int t = t0 + lane;
-                phase3_fwd<true>(w, S.data() + lane, mb, out + t, som, t < tmax, t < T);
+                phase3_fwd(w, S.data() + lane, mb, out + t, som, t < tmax, t < T);
             }
 }
 
