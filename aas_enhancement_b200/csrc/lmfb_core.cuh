@@ -38,7 +38,12 @@
 #ifdef __CUDACC__
 #  define LMFB_LDG(p) __ldg(p)
 #  define LMFB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+// make a pointer opaque to the optimiser: it is then kept as one 64-bit register pair and
+// "pointer + 32-bit byte offset" costs one or two instructions instead of a re-derived 64-bit
+// element-offset chain (shift + add + add).
+#  define LMFB_OPAQUE(p) asm volatile("" : "+l"(p))
 #else
+#  define LMFB_OPAQUE(p) ((void)0)
 #  define LMFB_LDG(p) (*(p))
 #  define LMFB_PREFETCH_L2(p) ((void)(p))
 struct float2 { float x, y; };
@@ -70,8 +75,8 @@ enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2 };
 struct BinEnt {
     float    wl, wh;   // forward: weights into filters ml, ml+1.  backward: weights of dE rows dlo, dlo+1
     uint32_t off;      // forward: float offset of the bin's masked power inside a scratch column
-                       // backward: dlo * (floats per dE row), dlo+1 always being a valid row
-    uint32_t moff;     // f * (floats per mask row)
+                       // backward: dlo * (BYTES per dE row), dlo+1 always being a valid row
+    uint32_t moff;     // f * (BYTES per mask row)
 };
 struct MelBand {
     BinEnt  ent[kBins];
@@ -94,6 +99,14 @@ LMFB_HD int reflect_index(int i, int len) {
     int j = i % period;
     if (j < 0) j += period;
     return j >= len ? period - j : j;
+}
+
+// pointer + byte offset (offsets come from the per-launch tables, in bytes, and fit 32 bits)
+LMFB_HD const float* at_bytes(const float* p, uint32_t bytes) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p) + bytes);
+}
+LMFB_HD float* at_bytes(float* p, uint32_t bytes) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(p) + bytes);
 }
 
 #ifdef __CUDACC__
@@ -302,20 +315,19 @@ struct StepIn {
 
 template <int MASK, bool BWD>
 LMFB_HD void load_step(int k2, const MelBand& mb, const float* __restrict__ mr, const float* __restrict__ mi,
-                       const float* __restrict__ dE, unsigned sem, StepIn<MASK, BWD>& in) {
+                       const float* __restrict__ dE, unsigned sem_bytes, StepIn<MASK, BWD>& in) {
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
         const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
-        const unsigned of = mb.ent[f].moff, op = mb.ent[fp].moff;
-        if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(mr + of); in.vr[5 + k1] = LMFB_LDG(mr + op); }
-        if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(mi + of); in.vi[5 + k1] = LMFB_LDG(mi + op); }
+        const uint32_t of = mb.ent[f].moff, op = mb.ent[fp].moff;
+        if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(at_bytes(mr, of)); in.vr[5 + k1] = LMFB_LDG(at_bytes(mr, op)); }
+        if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(at_bytes(mi, of)); in.vi[5 + k1] = LMFB_LDG(at_bytes(mi, op)); }
         if (BWD) {
-            const float* pf = dE + mb.ent[f].off;
-            const float* pp = dE + mb.ent[fp].off;
-            in.d0[k1]     = LMFB_LDG(pf);
-            in.d1[k1]     = LMFB_LDG(pf + sem);
-            in.d0[5 + k1] = LMFB_LDG(pp);
-            in.d1[5 + k1] = LMFB_LDG(pp + sem);
+            const uint32_t df = mb.ent[f].off, dp = mb.ent[fp].off;
+            in.d0[k1]     = LMFB_LDG(at_bytes(dE, df));
+            in.d1[k1]     = LMFB_LDG(at_bytes(dE, df + sem_bytes));
+            in.d0[5 + k1] = LMFB_LDG(at_bytes(dE, dp));
+            in.d1[5 + k1] = LMFB_LDG(at_bytes(dE, dp + sem_bytes));
         }
     }
 }
@@ -360,17 +372,17 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, con
             cb[kp * 32 * kPitch] = sp2;
         } else {
             const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
-            const unsigned of = mb.ent[f].moff, op = mb.ent[fp].moff;
+            const uint32_t of = mb.ent[f].moff, op = mb.ent[fp].moff;
             const float dpf = fmaf(mb.ent[f].wh, in.d1[k1], mb.ent[f].wl * in.d0[k1]);
             const float dpp = fmaf(mb.ent[fp].wh, in.d1[5 + k1], mb.ent[fp].wl * in.d0[5 + k1]);
             if (MASK == kMaskReim) {
-                st_if(gr + of, 2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
-                st_if(gi + of, 2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
-                st_if(gr + op, 2.0f * in.vr[5 + k1] * xp.x * xp.x * dpp, inrow);
-                st_if(gi + op, 2.0f * in.vi[5 + k1] * xp.y * xp.y * dpp, inrow);
+                st_if(at_bytes(gr, of), 2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
+                st_if(at_bytes(gi, of), 2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
+                st_if(at_bytes(gr, op), 2.0f * in.vr[5 + k1] * xp.x * xp.x * dpp, inrow);
+                st_if(at_bytes(gi, op), 2.0f * in.vi[5 + k1] * xp.y * xp.y * dpp, inrow);
             } else {
-                st_if(gr + of, fmaf(xf.x, xf.x, xf.y * xf.y) * dpf, inrow);
-                st_if(gr + op, fmaf(xp.x, xp.x, xp.y * xp.y) * dpp, inrow);
+                st_if(at_bytes(gr, of), fmaf(xf.x, xf.x, xf.y * xf.y) * dpf, inrow);
+                st_if(at_bytes(gr, op), fmaf(xp.x, xp.x, xp.y * xp.y) * dpp, inrow);
             }
         }
     }
@@ -383,16 +395,16 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, con
 template <int W, int MASK, bool BWD>
 LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb, StepIn<MASK, BWD>& a,
                        const float* __restrict__ mr, const float* __restrict__ mi,
-                       const float* __restrict__ dE, unsigned sem,
+                       const float* __restrict__ dE, unsigned sem_bytes,
                        float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
     StepIn<MASK, BWD> b;
 #pragma unroll 1
     for (int k2 = w; k2 <= 16; k2 += 2 * W) {
         const bool has_b = k2 + W <= 16;
-        if (has_b) load_step<MASK, BWD>(k2 + W, mb, mr, mi, dE, sem, b);
+        if (has_b) load_step<MASK, BWD>(k2 + W, mb, mr, mi, dE, sem_bytes, b);
         pass2_step<MASK, BWD>(col, k2, mb, a, gr, gi, inrow);
         if (has_b) {
-            if (k2 + 2 * W <= 16) load_step<MASK, BWD>(k2 + 2 * W, mb, mr, mi, dE, sem, a);
+            if (k2 + 2 * W <= 16) load_step<MASK, BWD>(k2 + 2 * W, mb, mr, mi, dE, sem_bytes, a);
             pass2_step<MASK, BWD>(col, k2 + W, mb, b, gr, gi, inrow);
         }
     }
@@ -406,7 +418,7 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb, StepI
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
 LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const MelBand& mb,
-                        float* __restrict__ out, unsigned som, bool inrow, bool valid) {
+                        float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid) {
     float* colf = reinterpret_cast<float*>(col);
     const int m_lo = mb.mbeg[w], m_hi = mb.mbeg[w + 1];
     if (m_lo >= m_hi) return;
@@ -436,13 +448,13 @@ LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const MelBand& mb,
         acc0 = acc1; acc1 = 0.0f;
     }
     const float* eq = colf + (1 + m_lo) * 2 * kPitch + 1;
-    float* op = out + (unsigned)m_lo * som;
+    float* op = at_bytes(out, (uint32_t)m_lo * som_bytes);
 #pragma unroll 4
     for (m = m_lo; m < m_hi; ++m) {
         const float y = valid ? log1pf(*eq) : 0.0f;
         st_if(op, y, inrow);
         eq += 2 * kPitch;
-        op += som;
+        op = at_bytes(op, som_bytes);
     }
 }
 

@@ -108,13 +108,17 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         const float* mr = a.mask_r + moff + clamp;
         const float* mi = a.mask_i + moff + clamp;
         const float* de = a.dE + row_nm + clamp;
+        float* gr = a.gr + moff;
+        float* gi = a.gi + moff;
+        float* po = a.out + row_nm;
+        LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
         StepIn<MASK, BWD> first;                    // issued before the barrier: its latency hides behind it
-        load_step<MASK, BWD>(w, mb, mr, mi, de, som, first);
+        load_step<MASK, BWD>(w, mb, mr, mi, de, som * 4u, first);
         __syncthreads();
-        fft_pass2<W, MASK, BWD>(w, col, mb, first, mr, mi, de, som, a.gr + moff, a.gi + moff, inrow);
+        fft_pass2<W, MASK, BWD>(w, col, mb, first, mr, mi, de, som * 4u, gr, gi, inrow);
         if (!BWD) {
             __syncthreads();
-            phase3_fwd(w, col, mb, a.out + row_nm, som, inrow, valid);
+            phase3_fwd(w, col, mb, po, som * 4u, inrow, valid);
         }
         __syncthreads();                            // the scratch is free for the next tile
     }
@@ -389,7 +393,7 @@ extern "C" const char* aas_lmfb_strerror(int code) {
         case AAS_LMFB_OK:      return "ok";
         case AAS_LMFB_E_NULL:  return "aas_lmfb: required pointer is NULL";
         case AAS_LMFB_E_ALIGN: return "aas_lmfb: buffer is not sufficiently aligned";
-        case AAS_LMFB_E_SHAPE: return "aas_lmfb: unsupported shape (n_bins must be 161, 2 <= n_mels <= 128, n >= 0, 1 <= tmax and mask row stride <= 2^24)";
+        case AAS_LMFB_E_SHAPE: return "aas_lmfb: unsupported shape (n_bins must be 161, 2 <= n_mels <= 128, n >= 0, 1 <= tmax and mask row stride <= 2^22)";
         case AAS_LMFB_E_FLAGS: return "aas_lmfb: invalid mask/cmvn flags";
         case AAS_LMFB_E_MEL:   return "aas_lmfb: mel basis is not banded (each bin may feed at most two adjacent, frequency-ordered filters)";
         case AAS_LMFB_E_NOMEM: return "aas_lmfb: host allocation failed";
@@ -471,7 +475,7 @@ int check_common(const aas_lmfb_plan* plan, const float* wave, const int32_t* le
                  const float* mask_r, const float* mask_i, const float* window, int tmax,
                  uint32_t flags) {
     if (!plan || !window || (n > 0 && (!wave || !lengths))) return AAS_LMFB_E_NULL;
-    if (n < 0 || tmax < 1 || tmax > (1 << 24)) return AAS_LMFB_E_SHAPE;
+    if (n < 0 || tmax < 1 || tmax > (1 << 22)) return AAS_LMFB_E_SHAPE;
     const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
     if (mask > 2u || cm > 2u || (flags >> 4)) return AAS_LMFB_E_FLAGS;
     if (mask != AAS_LMFB_MASK_NONE && !mask_r) return AAS_LMFB_E_NULL;
@@ -498,7 +502,7 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
     if (rc) return rc;
     if (n == 0) return AAS_LMFB_OK;
     const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
-    if (mask != AAS_LMFB_MASK_NONE && (mask_stride_f < tmax || mask_stride_f > (1 << 24))) return AAS_LMFB_E_SHAPE;
+    if (mask != AAS_LMFB_MASK_NONE && (mask_stride_f < tmax || mask_stride_f > (1 << 22))) return AAS_LMFB_E_SHAPE;
     if (!out || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
     if (((uintptr_t)out | (uintptr_t)stats) & 3u) return AAS_LMFB_E_ALIGN;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
@@ -554,7 +558,7 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     if (n == 0) return AAS_LMFB_OK;
     const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
     if (mask == AAS_LMFB_MASK_NONE) return AAS_LMFB_E_FLAGS;        // nothing to differentiate into
-    if (mask_stride_f < tmax || mask_stride_f > (1 << 24)) return AAS_LMFB_E_SHAPE;
+    if (mask_stride_f < tmax || mask_stride_f > (1 << 22)) return AAS_LMFB_E_SHAPE;
     if (!out || !grad_out || !workspace || !grad_mask_r || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
     if (mask == AAS_LMFB_MASK_REIM && !grad_mask_i) return AAS_LMFB_E_NULL;
     if (((uintptr_t)out | (uintptr_t)grad_out | (uintptr_t)workspace | (uintptr_t)grad_mask_r |

@@ -18,11 +18,12 @@ inline uint32_t kBinOffHost(int f) {
 inline void split_filters(MelBand* out, int warps);
 
 // Per-launch patch: row offsets depend on the caller's strides.
-//   fwd: ent[f].moff = f * msf.   bwd: additionally ent[f].off = dlo[f] * sem.
+//   fwd: ent[f].moff = f * msf * 4 bytes.   bwd: additionally ent[f].off = dlo[f] * sem * 4 bytes.
+// msf <= 2^22 and sem <= 2^22 keep both below 2^32.
 inline void patch_strides(MelBand* band, unsigned msf, const uint8_t* dlo /*nullable*/, unsigned sem) {
     for (int f = 0; f < kBins; ++f) {
-        band->ent[f].moff = (uint32_t)f * msf;
-        if (dlo) band->ent[f].off = (uint32_t)dlo[f] * sem;
+        band->ent[f].moff = (uint32_t)f * msf * 4u;
+        if (dlo) band->ent[f].off = (uint32_t)dlo[f] * sem * 4u;
     }
 }
 

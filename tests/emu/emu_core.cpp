@@ -33,15 +33,15 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
             const float* mip = mi ? mi + t + clamp : nullptr;
             const float* dep = dE ? dE + t + clamp : nullptr;
             StepIn<MASK, BWD> first;
-            load_step<MASK, BWD>(w, mb, mrp, mip, dep, som, first);
-            fft_pass2<W, MASK, BWD>(w, S.data() + lane, mb, first, mrp, mip, dep, som,
+            load_step<MASK, BWD>(w, mb, mrp, mip, dep, som * 4u, first);
+            fft_pass2<W, MASK, BWD>(w, S.data() + lane, mb, first, mrp, mip, dep, som * 4u,
                                     gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
         }
     if (!BWD)
         for (int w = 0; w < W; ++w)
             for (int lane = 0; lane < 32; ++lane) {
                 const int t = t0 + lane;
-                phase3_fwd(w, S.data() + lane, mb, out + t, som, t < tmax, t < T);
+                phase3_fwd(w, S.data() + lane, mb, out + t, som * 4u, t < tmax, t < T);
             }
 }
 
