@@ -306,29 +306,33 @@ LMFB_HD float masked_power(float2 x, float mr, float mi) {
 
 // what pass 2 needs from global memory for the ten bins of column pair k2: index k1 -> bin f,
 // index 5+k1 -> bin 160-f.  All pointers are readable for every lane (out-of-row lanes are
-// clamped by the caller), so no load is predicated; row strides fit 32 bits.
-template <int MASK, bool BWD>
-struct StepIn {
-    float vr[10], vi[10];     // mask values
-    float d0[10], d1[10];     // backward: dE rows that the bin's two mel weights multiply
-};
+// clamped by the caller), so no load is predicated; offsets come from the per-launch tables.
+struct StepMasks { float vr[10], vi[10]; };              // mask values (prefetched one step ahead)
+struct StepD     { float d0[10], d1[10]; };              // backward: the two dE rows of each bin
 
 template <int MASK, bool BWD>
-LMFB_HD void load_step(int k2, const MelBand& mb, const float* __restrict__ mr, const float* __restrict__ mi,
-                       const float* __restrict__ dE, unsigned sem_bytes, StepIn<MASK, BWD>& in) {
+LMFB_HD void load_masks(int k2, const MelBand& mb, const float* __restrict__ mr, const float* __restrict__ mi,
+                        StepMasks& in) {
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
         const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
         const uint32_t of = mb.ent[f].moff, op = mb.ent[fp].moff;
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(at_bytes(mr, of)); in.vr[5 + k1] = LMFB_LDG(at_bytes(mr, op)); }
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(at_bytes(mi, of)); in.vi[5 + k1] = LMFB_LDG(at_bytes(mi, op)); }
-        if (BWD) {
-            const uint32_t df = mb.ent[f].off, dp = mb.ent[fp].off;
-            in.d0[k1]     = LMFB_LDG(at_bytes(dE, df));
-            in.d1[k1]     = LMFB_LDG(at_bytes(dE, df + sem_bytes));
-            in.d0[5 + k1] = LMFB_LDG(at_bytes(dE, dp));
-            in.d1[5 + k1] = LMFB_LDG(at_bytes(dE, dp + sem_bytes));
-        }
+    }
+}
+
+// issued at the start of the step that consumes it: the two 5-point DFTs and the split (about
+// 200 instructions that need nothing from global memory) run while these loads are in flight
+LMFB_HD void load_d(int k2, const MelBand& mb, const float* __restrict__ dE, unsigned sem_bytes, StepD& in) {
+#pragma unroll
+    for (int k1 = 0; k1 < 5; ++k1) {
+        const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
+        const uint32_t df = mb.ent[f].off, dp = mb.ent[fp].off;
+        in.d0[k1]     = LMFB_LDG(at_bytes(dE, df));
+        in.d1[k1]     = LMFB_LDG(at_bytes(dE, df + sem_bytes));
+        in.d0[5 + k1] = LMFB_LDG(at_bytes(dE, dp));
+        in.d1[5 + k1] = LMFB_LDG(at_bytes(dE, dp + sem_bytes));
     }
 }
 
@@ -341,8 +345,11 @@ LMFB_HD void load_step(int k2, const MelBand& mb, const float* __restrict__ mr, 
 //             stored to gr/gi (+ f*gsf); every lane's pointers are valid, `inrow` gates the store
 // ---------------------------------------------------------------------------------------
 template <int MASK, bool BWD>
-LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, const StepIn<MASK, BWD>& in,
+LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, const StepMasks& in,
+                        const float* __restrict__ dE, unsigned sem_bytes,
                         float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
+    StepD d;
+    if (BWD) load_d(k2, mb, dE, sem_bytes, d);
     const int kb = (32 - k2) & 31;
     float2* ca = col + k2 * kPitch;
     float2* cb = col + kb * kPitch;
@@ -373,8 +380,8 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, con
         } else {
             const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
             const uint32_t of = mb.ent[f].moff, op = mb.ent[fp].moff;
-            const float dpf = fmaf(mb.ent[f].wh, in.d1[k1], mb.ent[f].wl * in.d0[k1]);
-            const float dpp = fmaf(mb.ent[fp].wh, in.d1[5 + k1], mb.ent[fp].wl * in.d0[5 + k1]);
+            const float dpf = fmaf(mb.ent[f].wh, d.d1[k1], mb.ent[f].wl * d.d0[k1]);
+            const float dpp = fmaf(mb.ent[fp].wh, d.d1[5 + k1], mb.ent[fp].wl * d.d0[5 + k1]);
             if (MASK == kMaskReim) {
                 st_if(at_bytes(gr, of), 2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
                 st_if(at_bytes(gi, of), 2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
@@ -390,22 +397,22 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, con
 
 // pass 2 over the 17 column pairs, dealt round-robin to the W warps; the global inputs of a
 // warp's next step are loaded into a second register set while the current step is computed.
-// `a` must already hold the inputs of the warp's first step (k2 = w): the caller issues that
+// `a` must already hold the masks of the warp's first step (k2 = w): the caller issues that
 // load before the block barrier that ends pass 1, so its latency hides behind the barrier.
 template <int W, int MASK, bool BWD>
-LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb, StepIn<MASK, BWD>& a,
+LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb, StepMasks& a,
                        const float* __restrict__ mr, const float* __restrict__ mi,
                        const float* __restrict__ dE, unsigned sem_bytes,
                        float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
-    StepIn<MASK, BWD> b;
+    StepMasks b;
 #pragma unroll 1
     for (int k2 = w; k2 <= 16; k2 += 2 * W) {
         const bool has_b = k2 + W <= 16;
-        if (has_b) load_step<MASK, BWD>(k2 + W, mb, mr, mi, dE, sem_bytes, b);
-        pass2_step<MASK, BWD>(col, k2, mb, a, gr, gi, inrow);
+        if (has_b) load_masks<MASK, BWD>(k2 + W, mb, mr, mi, b);
+        pass2_step<MASK, BWD>(col, k2, mb, a, dE, sem_bytes, gr, gi, inrow);
         if (has_b) {
-            if (k2 + 2 * W <= 16) load_step<MASK, BWD>(k2 + 2 * W, mb, mr, mi, dE, sem_bytes, a);
-            pass2_step<MASK, BWD>(col, k2 + W, mb, b, gr, gi, inrow);
+            if (k2 + 2 * W <= 16) load_masks<MASK, BWD>(k2 + 2 * W, mb, mr, mi, a);
+            pass2_step<MASK, BWD>(col, k2 + W, mb, b, dE, sem_bytes, gr, gi, inrow);
         }
     }
 }

@@ -112,8 +112,8 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         float* gi = a.gi + moff;
         float* po = a.out + row_nm;
         LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
-        StepIn<MASK, BWD> first;                    // issued before the barrier: its latency hides behind it
-        load_step<MASK, BWD>(w, mb, mr, mi, de, som * 4u, first);
+        StepMasks first;                            // issued before the barrier: its latency hides behind it
+        load_masks<MASK, BWD>(w, mb, mr, mi, first);
         __syncthreads();
         fft_pass2<W, MASK, BWD>(w, col, mb, first, mr, mi, de, som * 4u, gr, gi, inrow);
         if (!BWD) {

@@ -32,8 +32,8 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
             const float* mrp = mr ? mr + t + clamp : nullptr;
             const float* mip = mi ? mi + t + clamp : nullptr;
             const float* dep = dE ? dE + t + clamp : nullptr;
-            StepIn<MASK, BWD> first;
-            load_step<MASK, BWD>(w, mb, mrp, mip, dep, som * 4u, first);
+            StepMasks first;
+            load_masks<MASK, BWD>(w, mb, mrp, mip, first);
             fft_pass2<W, MASK, BWD>(w, S.data() + lane, mb, first, mrp, mip, dep, som * 4u,
                                     gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
         }
