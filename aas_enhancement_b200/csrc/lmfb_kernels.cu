@@ -41,6 +41,7 @@ struct K1Args {
     int            tiles_per_utt;
     int            total_tiles;
     int            vec_ok;
+    long long*     timeline;   // debug builds (-DLMFB_TIMELINE) only: per-warp phase clocks
 };
 
 constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
@@ -100,8 +101,17 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
             }
         }
 
+#ifdef LMFB_TIMELINE
+        long long tl[8];
+#define LMFB_TICK(i) tl[i] = clock64()
+#else
+#define LMFB_TICK(i) ((void)0)
+#endif
+        LMFB_TICK(0);
         stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
+        LMFB_TICK(1);
         __syncthreads();
+        LMFB_TICK(2);
         fft_pass1<W>(w, col);
         // loads of out-of-row lanes are redirected to the last column of the row (always readable)
         const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
@@ -114,13 +124,27 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
         StepMasks first;                            // issued before the barrier: its latency hides behind it
         load_masks<MASK, BWD>(w, mb, mr, mi, first);
+        LMFB_TICK(3);
         __syncthreads();
+        LMFB_TICK(4);
         fft_pass2<W, MASK, BWD>(w, col, mb, first, mr, mi, de, som * 4u, gr, gi, inrow);
+        LMFB_TICK(5);
         if (!BWD) {
             __syncthreads();
+            LMFB_TICK(6);
             phase3_fwd(w, col, mb, po, som * 4u, inrow, valid);
         }
+#ifdef LMFB_TIMELINE
+        else tl[6] = tl[5];
+#endif
+        LMFB_TICK(7);
         __syncthreads();                            // the scratch is free for the next tile
+#ifdef LMFB_TIMELINE
+        if (a.timeline && lane == 0 && blockIdx.x < 64 && tile < (int)gridDim.x * 8) {
+            long long* dst = a.timeline + ((long long)(tile / gridDim.x) * 64 + blockIdx.x) * (W * 8) + w * 8;
+            for (int i = 0; i < 8; ++i) dst[i] = tl[i];
+        }
+#endif
     }
 }
 
@@ -514,6 +538,9 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
     a.window = window; a.out = out; a.tmax = tmax;
     a.tiles_per_utt = (tmax + kTile - 1) / kTile;
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
+#ifdef LMFB_TIMELINE
+    { const char* e = getenv(false ? "AAS_LMFB_TIMELINE_BWD" : "AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+#endif
 
     const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
     const K1Variant& v = kVariants[plan->vfwd >= 0 ? plan->vfwd : (small ? kFwdVariantSmall : kFwdVariantBig)];
@@ -590,6 +617,9 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     a.window = window; a.dE = dE; a.gr = grad_mask_r; a.gi = grad_mask_i; a.tmax = tmax;
     a.tiles_per_utt = (tmax + kTile - 1) / kTile;
     a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
+#ifdef LMFB_TIMELINE
+    { const char* e = getenv(true ? "AAS_LMFB_TIMELINE_BWD" : "AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+#endif
 
     const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
     const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];

@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""Per-phase clock timeline of the K1 kernels (debug build with -DLMFB_TIMELINE into a scratch .so).
+Run on the GPU box:  python tools/timeline.py [workload]"""
+import os, subprocess, sys, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from aas_enhancement_b200 import build as B
+lib_dbg = os.path.join(ROOT, "gpurun_out", "libaas_lmfb_timeline.so")
+os.makedirs(os.path.dirname(lib_dbg), exist_ok=True)
+subprocess.check_call([B.find_nvcc()] + B.NVCC_FLAGS + ["-DLMFB_TIMELINE", B.SRC, "-o", lib_dbg])
+from aas_enhancement_b200 import _lib
+_lib.LIB_PATH = lib_dbg
+from aas_enhancement_b200 import LMFBFrontEnd
+wl = sys.argv[1] if len(sys.argv) > 1 else "sweep"
+n, samples = (256, 160000) if wl == "sweep" else (30, 96000)
+tmax = 1 + samples // 160
+dev = torch.device("cuda", 0)
+W = 3
+buf_f = torch.zeros(8 * 64 * 8 * 8, dtype=torch.int64, device=dev)
+buf_b = torch.zeros(8 * 64 * 8 * 8, dtype=torch.int64, device=dev)
+os.environ["AAS_LMFB_TIMELINE_FWD"] = str(buf_f.data_ptr())
+os.environ["AAS_LMFB_TIMELINE_BWD"] = str(buf_b.data_ptr())
+os.environ["AAS_LMFB_WARPS_FWD"] = str(W)
+os.environ["AAS_LMFB_WARPS_BWD"] = str(W)
+fe = LMFBFrontEnd(mask_mode="reim", cmvn_mode="per_bin").to(dev)
+wave = (0.1 * torch.randn(n, samples, device=dev)).clamp_(-1, 1)
+lens = torch.full((n,), samples, dtype=torch.int32, device=dev)
+mr = torch.rand(n, 161, tmax, device=dev, requires_grad=True)
+mi = torch.rand(n, 161, tmax, device=dev, requires_grad=True)
+g = torch.randn(n, 40, tmax, device=dev)
+for _ in range(3):
+    z, _ = fe(wave, lens, mr, mi); z.backward(g)
+torch.cuda.synchronize()
+names = ["stage", "wait1", "pass1+ld", "wait2", "pass2", "wait3", "phase3"]
+for label, buf in (("fwd", buf_f), ("bwd", buf_b)):
+    t = buf.cpu().view(8, 64, -1)[:, :, :W * 8].reshape(8, 64, W, 8).double()
+    valid = t[..., 7] > 0
+    d = t[..., 1:] - t[..., :-1]
+    print(label, "cycles per phase, mean over", int(valid.sum()), "warp-tiles; per warp index")
+    for w in range(W):
+        m = valid[:, :, w]
+        row = [float(d[:, :, w, i][m].mean()) for i in range(7)]
+        tot = float((t[:, :, w, 7] - t[:, :, w, 0])[m].mean())
+        print("  warp", w, " ".join(f"{nm}={v:8.0f}" for nm, v in zip(names, row)), f" total={tot:9.0f}")
+    # tile-to-tile period of one CTA
+    per = (t[1:, :, 0, 0] - t[:-1, :, 0, 0])[valid[1:, :, 0] & valid[:-1, :, 0]]
+    if per.numel():
+        print("  tile period (start to next start, same CTA): mean %.0f cycles" % float(per.mean()))
