@@ -86,6 +86,44 @@ struct MelBand {
     int     n_mels;
 };
 
+// Shared-memory copy of every table the tile loop indexes at run time.  Indexed constant-bank
+// loads (LDC with a register index) miss the small indexed-constant cache about one time in
+// five on this kernel and each miss stalls the warp for hundreds of cycles (ncu:
+// idc__request_hit_rate 79 %); shared memory has a fixed ~30-cycle latency and broadcasts.
+// Filled once per (persistent) CTA by tables_fill().
+struct Tables {
+    float    wl[kBins + 3], wh[kBins + 3];
+    uint32_t off[kBins + 3];      // forward: float offset of the bin's masked power in a scratch column
+                                  // backward: byte offset of dE row dlo (dlo+1 always valid)
+    float    ssin[88], scos[88];  // real-split twiddles [k2*5 + k1]
+    uint8_t  binof[88];           // bin produced by pass-2 step k2, output k1 [k2*5 + k1]
+    uint8_t  fend[kMaxMels];
+    uint8_t  mbeg[kMaxW + 1];
+    uint8_t  pad_[3];
+    int      n_mels;
+    uint32_t msf_bytes;           // bytes per mask row
+    uint32_t pad2_[2];
+};
+constexpr int kTablesBytes = (int)((sizeof(Tables) + 15) / 16 * 16);
+constexpr int kSmemBytes = kScratchBytes + kTablesBytes;
+
+// cooperative copy: thread `tid` of `nthreads`
+LMFB_HD void tables_fill(Tables* tb, const MelBand& mb, uint32_t msf_bytes, int tid, int nthreads) {
+    for (int f = tid; f < kBins; f += nthreads) {
+        tb->wl[f] = mb.ent[f].wl;
+        tb->wh[f] = mb.ent[f].wh;
+        tb->off[f] = mb.ent[f].off;
+    }
+    for (int i = tid; i < 85; i += nthreads) {
+        tb->ssin[i] = kSplitSin[i / 5][i % 5];
+        tb->scos[i] = kSplitCos[i / 5][i % 5];
+        tb->binof[i] = kBinOf[i / 5][i % 5];
+    }
+    for (int m = tid; m < kMaxMels; m += nthreads) tb->fend[m] = mb.fend[m];
+    for (int i = tid; i <= kMaxW; i += nthreads) tb->mbeg[i] = mb.mbeg[i];
+    if (tid == 0) { tb->n_mels = mb.n_mels; tb->msf_bytes = msf_bytes; }
+}
+
 LMFB_HD int slot_of_packed(int j) {            // j in [0,160): packed-sample index -> PFA input slot
     const int n1 = (3 * (j % 5)) % 5;
     const int n2 = (13 * (j & 31)) & 31;
@@ -311,12 +349,13 @@ struct StepMasks { float vr[10], vi[10]; };              // mask values (prefetc
 struct StepD     { float d0[10], d1[10]; };              // backward: the two dE rows of each bin
 
 template <int MASK, bool BWD>
-LMFB_HD void load_masks(int k2, const MelBand& mb, const float* __restrict__ mr, const float* __restrict__ mi,
+LMFB_HD void load_masks(int k2, const Tables& tb, const float* __restrict__ mr, const float* __restrict__ mi,
                         StepMasks& in) {
+    const uint32_t msf = tb.msf_bytes;
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
-        const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
-        const uint32_t of = mb.ent[f].moff, op = mb.ent[fp].moff;
+        const unsigned f = tb.binof[k2 * 5 + k1], fp = kBins - 1 - f;
+        const uint32_t of = f * msf, op = fp * msf;
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(at_bytes(mr, of)); in.vr[5 + k1] = LMFB_LDG(at_bytes(mr, op)); }
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(at_bytes(mi, of)); in.vi[5 + k1] = LMFB_LDG(at_bytes(mi, op)); }
     }
@@ -324,11 +363,11 @@ LMFB_HD void load_masks(int k2, const MelBand& mb, const float* __restrict__ mr,
 
 // issued at the start of the step that consumes it: the two 5-point DFTs and the split (about
 // 200 instructions that need nothing from global memory) run while these loads are in flight
-LMFB_HD void load_d(int k2, const MelBand& mb, const float* __restrict__ dE, unsigned sem_bytes, StepD& in) {
+LMFB_HD void load_d(int k2, const Tables& tb, const float* __restrict__ dE, unsigned sem_bytes, StepD& in) {
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
-        const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
-        const uint32_t df = mb.ent[f].off, dp = mb.ent[fp].off;
+        const unsigned f = tb.binof[k2 * 5 + k1], fp = kBins - 1 - f;
+        const uint32_t df = tb.off[f], dp = tb.off[fp];
         in.d0[k1]     = LMFB_LDG(at_bytes(dE, df));
         in.d1[k1]     = LMFB_LDG(at_bytes(dE, df + sem_bytes));
         in.d0[5 + k1] = LMFB_LDG(at_bytes(dE, dp));
@@ -345,11 +384,11 @@ LMFB_HD void load_d(int k2, const MelBand& mb, const float* __restrict__ dE, uns
 //             stored to gr/gi (+ f*gsf); every lane's pointers are valid, `inrow` gates the store
 // ---------------------------------------------------------------------------------------
 template <int MASK, bool BWD>
-LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, const StepMasks& in,
+LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const Tables& tb, const StepMasks& in,
                         const float* __restrict__ dE, unsigned sem_bytes,
                         float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
     StepD d;
-    if (BWD) load_d(k2, mb, dE, sem_bytes, d);
+    if (BWD) load_d(k2, tb, dE, sem_bytes, d);
     const int kb = (32 - k2) & 31;
     float2* ca = col + k2 * kPitch;
     float2* cb = col + kb * kPitch;
@@ -365,7 +404,7 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, con
     for (int k1 = 0; k1 < 5; ++k1) {
         const int kp = (5 - k1) % 5;
         float2 xf, xp;
-        split_pair(Ar[k1], Ai[k1], Br[kp], Bi[kp], kSplitSin[k2][k1], kSplitCos[k2][k1], xf, xp);
+        split_pair(Ar[k1], Ai[k1], Br[kp], Bi[kp], tb.ssin[k2 * 5 + k1], tb.scos[k2 * 5 + k1], xf, xp);
         if (!BWD) {
             float pf = masked_power<MASK>(xf, in.vr[k1], in.vi[k1]);
             float pp = masked_power<MASK>(xp, in.vr[5 + k1], in.vi[5 + k1]);
@@ -378,10 +417,10 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, con
             ca[k1 * 32 * kPitch] = sf2;
             cb[kp * 32 * kPitch] = sp2;
         } else {
-            const unsigned f = kBinOf[k2][k1], fp = kBins - 1 - f;
-            const uint32_t of = mb.ent[f].moff, op = mb.ent[fp].moff;
-            const float dpf = fmaf(mb.ent[f].wh, d.d1[k1], mb.ent[f].wl * d.d0[k1]);
-            const float dpp = fmaf(mb.ent[fp].wh, d.d1[5 + k1], mb.ent[fp].wl * d.d0[5 + k1]);
+            const unsigned f = tb.binof[k2 * 5 + k1], fp = kBins - 1 - f;
+            const uint32_t of = f * tb.msf_bytes, op = fp * tb.msf_bytes;
+            const float dpf = fmaf(tb.wh[f], d.d1[k1], tb.wl[f] * d.d0[k1]);
+            const float dpp = fmaf(tb.wh[fp], d.d1[5 + k1], tb.wl[fp] * d.d0[5 + k1]);
             if (MASK == kMaskReim) {
                 st_if(at_bytes(gr, of), 2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
                 st_if(at_bytes(gi, of), 2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
@@ -400,7 +439,7 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const MelBand& mb, con
 // `a` must already hold the masks of the warp's first step (k2 = w): the caller issues that
 // load before the block barrier that ends pass 1, so its latency hides behind the barrier.
 template <int W, int MASK, bool BWD>
-LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb, StepMasks& a,
+LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const Tables& tb, StepMasks& a,
                        const float* __restrict__ mr, const float* __restrict__ mi,
                        const float* __restrict__ dE, unsigned sem_bytes,
                        float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
@@ -408,11 +447,11 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb, StepM
 #pragma unroll 1
     for (int k2 = w; k2 <= 16; k2 += 2 * W) {
         const bool has_b = k2 + W <= 16;
-        if (has_b) load_masks<MASK, BWD>(k2 + W, mb, mr, mi, b);
-        pass2_step<MASK, BWD>(col, k2, mb, a, dE, sem_bytes, gr, gi, inrow);
+        if (has_b) load_masks<MASK, BWD>(k2 + W, tb, mr, mi, b);
+        pass2_step<MASK, BWD>(col, k2, tb, a, dE, sem_bytes, gr, gi, inrow);
         if (has_b) {
-            if (k2 + 2 * W <= 16) load_masks<MASK, BWD>(k2 + 2 * W, mb, mr, mi, a);
-            pass2_step<MASK, BWD>(col, k2 + W, mb, b, dE, sem_bytes, gr, gi, inrow);
+            if (k2 + 2 * W <= 16) load_masks<MASK, BWD>(k2 + 2 * W, tb, mr, mi, a);
+            pass2_step<MASK, BWD>(col, k2 + W, tb, b, dE, sem_bytes, gr, gi, inrow);
         }
     }
 }
@@ -424,40 +463,33 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const MelBand& mb, StepM
 // one filter early and discards that filter's (partial) sum.
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
-LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const MelBand& mb,
+LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const Tables& tb,
                         float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid) {
     float* colf = reinterpret_cast<float*>(col);
-    const int m_lo = mb.mbeg[w], m_hi = mb.mbeg[w + 1];
+    const int m_lo = tb.mbeg[w], m_hi = tb.mbeg[w + 1];
     if (m_lo >= m_hi) return;
     const int m_first = m_lo > 0 ? m_lo - 1 : 0;
-    const int f_lo = m_first > 0 ? (int)mb.fend[m_first - 1] : 0;
-    const int f_hi = mb.fend[m_hi - 1];
-    int m = m_first;
-    int fe = mb.fend[m];
+    int f = m_first > 0 ? (int)tb.fend[m_first - 1] : 0;
     float acc0 = 0.0f, acc1 = 0.0f;
     float* ep = colf + (1 + m_first) * 2 * kPitch + 1;     // E[m] -> .y of slot 1+m
-#pragma unroll 4
-    for (int f = f_lo; f < f_hi; ++f) {
-        while (f >= fe) {                                  // filter m is complete (rare: ~1 bin in 4)
-            if (m >= m_lo) *ep = acc0;                     // the early filter m_lo-1 belongs to another warp
-            ep += 2 * kPitch;
-            acc0 = acc1; acc1 = 0.0f;
-            fe = mb.fend[++m];
-        }
-        const float p = colf[mb.ent[f].off];
-        acc0 = fmaf(mb.ent[f].wl, p, acc0);
-        acc1 = fmaf(mb.ent[f].wh, p, acc1);
-    }
 #pragma unroll 1
-    for (; m < m_hi; ++m) {                                // the last filter(s), incl. empty ones
-        if (m >= m_lo) *ep = acc0;
+    for (int m = m_first; m < m_hi; ++m) {
+        const int fe = tb.fend[m];
+#pragma unroll 4
+        for (; f < fe; ++f) {                              // no branch inside: the loads overlap
+            const float p = colf[tb.off[f]];
+            acc0 = fmaf(tb.wl[f], p, acc0);
+            acc1 = fmaf(tb.wh[f], p, acc1);
+        }
+        if (m >= m_lo) *ep = acc0;                         // the early filter m_lo-1 belongs to another warp
         ep += 2 * kPitch;
-        acc0 = acc1; acc1 = 0.0f;
+        acc0 = acc1;
+        acc1 = 0.0f;
     }
     const float* eq = colf + (1 + m_lo) * 2 * kPitch + 1;
     float* op = at_bytes(out, (uint32_t)m_lo * som_bytes);
 #pragma unroll 4
-    for (m = m_lo; m < m_hi; ++m) {
+    for (int m = m_lo; m < m_hi; ++m) {
         const float y = valid ? log1pf(*eq) : 0.0f;
         st_if(op, y, inrow);
         eq += 2 * kPitch;

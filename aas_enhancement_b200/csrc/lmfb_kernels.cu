@@ -50,9 +50,11 @@ template <int MASK, bool BWD, int W, int CTAS>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     extern __shared__ __align__(16) float2 S[];
+    Tables& tb = *reinterpret_cast<Tables*>(reinterpret_cast<char*>(S) + kScratchBytes);
     const int lane = threadIdx.x & 31;
     const int w    = threadIdx.x >> 5;
     const int n_mels = mb.n_mels;
+    tables_fill(&tb, mb, a.msf * 4u, threadIdx.x, kTile * W);   // visible after the first block barrier
     StageLane sl;
     stage_lane_init(lane, a.window, sl);
     float2* col = S + lane;
@@ -123,16 +125,16 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         float* po = a.out + row_nm;
         LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
         StepMasks first;                            // issued before the barrier: its latency hides behind it
-        load_masks<MASK, BWD>(w, mb, mr, mi, first);
+        load_masks<MASK, BWD>(w, tb, mr, mi, first);
         LMFB_TICK(3);
         __syncthreads();
         LMFB_TICK(4);
-        fft_pass2<W, MASK, BWD>(w, col, mb, first, mr, mi, de, som * 4u, gr, gi, inrow);
+        fft_pass2<W, MASK, BWD>(w, col, tb, first, mr, mi, de, som * 4u, gr, gi, inrow);
         LMFB_TICK(5);
         if (!BWD) {
             __syncthreads();
             LMFB_TICK(6);
-            phase3_fwd(w, col, mb, po, som * 4u, inrow, valid);
+            phase3_fwd(w, col, tb, po, som * 4u, inrow, valid);
         }
 #ifdef LMFB_TIMELINE
         else tl[6] = tl[5];
@@ -468,7 +470,7 @@ int ensure_attrs(k1_fn fn) {
     std::lock_guard<std::mutex> lock(mu);
     const std::pair<const void*, int> key((const void*)fn, dev);
     if (done.count(key)) return 0;
-    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kScratchBytes);
+    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return (int)e;
@@ -491,7 +493,7 @@ int launch_k1(const K1Variant& v, k1_fn fn, K1Args& a, const MelBand& mb, int n,
     const int per_sm = v.ctas < kScratchPerSM ? v.ctas : kScratchPerSM;
     const long long resident = (long long)sms * per_sm;           // one persistent CTA per scratch slot
     const unsigned blocks = (unsigned)(total < resident ? total : resident);
-    fn<<<blocks, kTile * v.warps, kScratchBytes, stream>>>(a, mb);
+    fn<<<blocks, kTile * v.warps, kSmemBytes, stream>>>(a, mb);
     return (int)cudaPeekAtLastError();
 }
 

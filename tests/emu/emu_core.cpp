@@ -16,6 +16,8 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
               const MelBand& mb, const float* mr, const float* mi, unsigned /*sf*/,
               const float* dE, float* out, unsigned som, float* gr, float* gi, int tmax, int T,
               std::vector<float2>& S) {
+    Tables tb;
+    tables_fill(&tb, mb, mb.ent[1].moff, 0, 1);            // ent[1].moff == bytes per mask row
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
             StageLane sl;
@@ -33,15 +35,15 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
             const float* mip = mi ? mi + t + clamp : nullptr;
             const float* dep = dE ? dE + t + clamp : nullptr;
             StepMasks first;
-            load_masks<MASK, BWD>(w, mb, mrp, mip, first);
-            fft_pass2<W, MASK, BWD>(w, S.data() + lane, mb, first, mrp, mip, dep, som * 4u,
+            load_masks<MASK, BWD>(w, tb, mrp, mip, first);
+            fft_pass2<W, MASK, BWD>(w, S.data() + lane, tb, first, mrp, mip, dep, som * 4u,
                                     gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
         }
     if (!BWD)
         for (int w = 0; w < W; ++w)
             for (int lane = 0; lane < 32; ++lane) {
                 const int t = t0 + lane;
-                phase3_fwd(w, S.data() + lane, mb, out + t, som * 4u, t < tmax, t < T);
+                phase3_fwd(w, S.data() + lane, tb, out + t, som * 4u, t < tmax, t < T);
             }
 }
 
