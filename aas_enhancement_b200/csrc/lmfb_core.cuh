@@ -219,17 +219,16 @@ LMFB_HD void stage_rows_slow(int lane, const StageLane& sl, const float* __restr
     }
 }
 
-// hop-row r feeds frame r (first half, r < 32) and frame r-1 (second half, r >= 1).  The 33 rows
-// are dealt to the warps in contiguous shares and each warp issues its loads in one or two
-// batches (every load of a batch in flight before the first store): one or two memory round
-// trips per tile instead of one per row.
+// hop-row r feeds frame r (first half, r < 32) and frame r-1 (second half, r >= 1).  The 31 rows
+// 1..31 feed two frames each and are dealt to the warps in equal shares, loaded in one batch per
+// warp without any per-row predicate; rows 0 and 32 (one frame each) go to warps 0 and W-1.
 template <int W>
 LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
                         int t0, float2* __restrict__ S, bool vec_ok) {
-    constexpr int kShare = (kTile + 1 + W - 1) / W;               // rows per warp
-    constexpr int kBatch = kShare <= 9 ? kShare : (kShare + 1) / 2;    // <= 27 loads in flight per lane
-    const int r_lo = w * kShare;
-    const int r_hi = r_lo + kShare < kTile + 1 ? r_lo + kShare : kTile + 1;
+    constexpr int kShare = (kTile - 1 + W - 1) / W;               // rows per warp (last warp may have fewer)
+    constexpr int kBatch = kShare <= 8 ? kShare : 8;
+    const int r_lo = 1 + w * kShare;
+    const int r_hi = r_lo + kShare < kTile ? r_lo + kShare : kTile;
 #pragma unroll 1
     for (int r0 = r_lo; r0 < r_hi; r0 += kBatch) {
         const int r1 = r0 + kBatch < r_hi ? r0 + kBatch : r_hi;
@@ -238,21 +237,50 @@ LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __res
             continue;
         }
         const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r0 - 1) * kHop) + lane;
+        float2* da0 = S + sl.slot_a[0] + r0; float2* db0 = S + sl.slot_b[0] + r0 - 1;
+        float2* da1 = S + sl.slot_a[1] + r0; float2* db1 = S + sl.slot_b[1] + r0 - 1;
+        float2* da2 = S + sl.slot_a[2] + r0; float2* db2 = S + sl.slot_b[2] + r0 - 1;
         float2 v[kBatch][3];
+        if (r1 - r0 == kBatch) {                                  // full batch: no predicates at all
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            if (r0 + i < r1) {                                    // warp-uniform
+            for (int i = 0; i < kBatch; ++i) {
                 v[i][0] = LMFB_LDG(src + i * 80);
                 v[i][1] = LMFB_LDG(src + i * 80 + 32);
                 if (lane < 16) v[i][2] = LMFB_LDG(src + i * 80 + 64);
             }
-        }
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            if (r0 + i < r1) {
-                stage_store(sl, S, r0 + i, 0, v[i][0]);
-                stage_store(sl, S, r0 + i, 1, v[i][1]);
-                if (lane < 16) stage_store(sl, S, r0 + i, 2, v[i][2]);
+            for (int i = 0; i < kBatch; ++i) {
+                da0[i] = make_float2(v[i][0].x * sl.wa0[0], v[i][0].y * sl.wa1[0]);
+                db0[i] = make_float2(v[i][0].x * sl.wb0[0], v[i][0].y * sl.wb1[0]);
+                da1[i] = make_float2(v[i][1].x * sl.wa0[1], v[i][1].y * sl.wa1[1]);
+                db1[i] = make_float2(v[i][1].x * sl.wb0[1], v[i][1].y * sl.wb1[1]);
+                if (lane < 16) {
+                    da2[i] = make_float2(v[i][2].x * sl.wa0[2], v[i][2].y * sl.wa1[2]);
+                    db2[i] = make_float2(v[i][2].x * sl.wb0[2], v[i][2].y * sl.wb1[2]);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int r = r0; r < r1; ++r) {
+                const float2* s2 = src + (r - r0) * 80;
+                stage_store(sl, S, r, 0, LMFB_LDG(s2));
+                stage_store(sl, S, r, 1, LMFB_LDG(s2 + 32));
+                if (lane < 16) stage_store(sl, S, r, 2, LMFB_LDG(s2 + 64));
+            }
+        }
+    }
+    // the two half rows
+    const int r_edge = w == 0 ? 0 : (w == W - 1 ? kTile : -1);
+    if (W == 1 || r_edge >= 0) {
+#pragma unroll 1
+        for (int r = (W == 1 ? 0 : r_edge); r <= (W == 1 ? kTile : r_edge); r += kTile) {
+            if (!rows_interior(t0 + r - 1, t0 + r, len, vec_ok)) {
+                stage_rows_slow(lane, sl, wave_row, len, t0, S, r, r + 1);
+            } else {
+                const float2* s2 = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r - 1) * kHop) + lane;
+                stage_store(sl, S, r, 0, LMFB_LDG(s2));
+                stage_store(sl, S, r, 1, LMFB_LDG(s2 + 32));
+                if (lane < 16) stage_store(sl, S, r, 2, LMFB_LDG(s2 + 64));
             }
         }
     }
