@@ -362,7 +362,9 @@ LMFB_HD void load_masks(int k2, const Tables& tb, const float* __restrict__ mr, 
 }
 
 // issued at the start of the step that consumes it: the two 5-point DFTs and the split (about
-// 200 instructions that need nothing from global memory) run while these loads are in flight
+// 200 instructions that need nothing from global memory) run while these loads are in flight.
+// `dE` is either the global column (row stride sem_bytes) or, in the variants that stage the
+// tile's dE rows in shared memory, that staged column (row stride 128 bytes).
 LMFB_HD void load_d(int k2, const Tables& tb, const float* __restrict__ dE, unsigned sem_bytes, StepD& in) {
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {

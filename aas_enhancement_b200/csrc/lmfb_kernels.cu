@@ -46,11 +46,12 @@ struct K1Args {
 
 constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
 
-template <int MASK, bool BWD, int W, int CTAS>
+template <int MASK, bool BWD, int W, int CTAS, bool DSMEM>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     extern __shared__ __align__(16) float2 S[];
     Tables& tb = *reinterpret_cast<Tables*>(reinterpret_cast<char*>(S) + kScratchBytes);
+    float* dEs = reinterpret_cast<float*>(reinterpret_cast<char*>(S) + kSmemBytes);   // DSMEM: [n_mels][32]
     const int lane = threadIdx.x & 31;
     const int w    = threadIdx.x >> 5;
     const int n_mels = mb.n_mels;
@@ -92,7 +93,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs ...
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
-        if (BWD) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
+        if (BWD && !DSMEM) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
         // ... and the next tile's samples, so that its staging loads hit L2
         {
             const int nt = tile + gridDim.x;
@@ -110,16 +111,22 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
 #define LMFB_TICK(i) ((void)0)
 #endif
         LMFB_TICK(0);
+        // loads of out-of-row lanes are redirected to the last column of the row (always readable)
+        const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
+        if (BWD && DSMEM) {                         // this tile's dE rows -> shared memory, lanes along T
+            const float* src = a.dE + row_nm + clamp;
+#pragma unroll 4
+            for (int m = w; m < n_mels; m += W) dEs[m * kTile + lane] = LMFB_LDG(src + (unsigned)m * som);
+        }
         stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
         LMFB_TICK(1);
         __syncthreads();
         LMFB_TICK(2);
         fft_pass1<W>(w, col);
-        // loads of out-of-row lanes are redirected to the last column of the row (always readable)
-        const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
         const float* mr = a.mask_r + moff + clamp;
         const float* mi = a.mask_i + moff + clamp;
-        const float* de = a.dE + row_nm + clamp;
+        const float* de = (BWD && DSMEM) ? dEs + lane : a.dE + row_nm + clamp;
+        const unsigned de_stride = (BWD && DSMEM) ? (unsigned)(kTile * 4) : som * 4u;
         float* gr = a.gr + moff;
         float* gi = a.gi + moff;
         float* po = a.out + row_nm;
@@ -129,7 +136,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         LMFB_TICK(3);
         __syncthreads();
         LMFB_TICK(4);
-        fft_pass2<W, MASK, BWD>(w, col, tb, first, mr, mi, de, som * 4u, gr, gi, inrow);
+        fft_pass2<W, MASK, BWD>(w, col, tb, first, mr, mi, de, de_stride, gr, gi, inrow);
         LMFB_TICK(5);
         if (!BWD) {
             __syncthreads();
@@ -376,18 +383,20 @@ using namespace aas_lmfb;
 
 typedef void (*k1_fn)(const K1Args, const MelBand);
 
-struct K1Variant { int warps, ctas; k1_fn fwd[3], bwd[3]; };   // indexed by mask mode
+struct K1Variant { int warps, ctas, dsmem; k1_fn fwd[3], bwd[3]; };   // indexed by mask mode
 
-#define LMFB_VARIANT(W, C)                                                                       \
-    { W, C,                                                                                      \
-      { (k1_fn)lmfb_k1<kMaskNone, false, W, C>, (k1_fn)lmfb_k1<kMaskReim, false, W, C>,          \
-        (k1_fn)lmfb_k1<kMaskPower, false, W, C> },                                               \
-      { nullptr, (k1_fn)lmfb_k1<kMaskReim, true, W, C>, (k1_fn)lmfb_k1<kMaskPower, true, W, C> } }
+#define LMFB_VARIANT(W, C, D)                                                                    \
+    { W, C, D,                                                                                   \
+      { (k1_fn)lmfb_k1<kMaskNone, false, W, C, D>, (k1_fn)lmfb_k1<kMaskReim, false, W, C, D>,    \
+        (k1_fn)lmfb_k1<kMaskPower, false, W, C, D> },                                            \
+      { nullptr, (k1_fn)lmfb_k1<kMaskReim, true, W, C, D>, (k1_fn)lmfb_k1<kMaskPower, true, W, C, D> } }
 
-// (warps per tile, resident CTAs per SM the register budget is sized for)
+// (warps per tile, resident CTAs per SM the register budget is sized for, dE tile staged in smem)
 static const K1Variant kVariants[] = {
-    LMFB_VARIANT(4, 5), LMFB_VARIANT(2, 5), LMFB_VARIANT(3, 5), LMFB_VARIANT(5, 4), LMFB_VARIANT(1, 5),
+    LMFB_VARIANT(4, 5, false), LMFB_VARIANT(2, 5, false), LMFB_VARIANT(3, 5, false),
+    LMFB_VARIANT(5, 4, false), LMFB_VARIANT(1, 5, false), LMFB_VARIANT(4, 4, true),
 };
+constexpr int kVariantDsmem = 5;
 // Defaults measured on B200 (profiles/): in the throughput regime (more tiles than resident CTAs)
 // 3 warps per tile win for both directions (128 registers, no spills); in the latency regime (a
 // launch that does not fill the resident slots, e.g. 30 x 6 s) the forward prefers 4 warps and
@@ -396,11 +405,12 @@ constexpr int kFwdVariantBig = 2, kFwdVariantSmall = 0;
 constexpr int kBwdVariantBig = 2, kBwdVariantSmall = 1;
 
 static int pick_variant(const char* env, int dflt) {
-    const char* v = getenv(env);            // tuning knob: warps per tile
+    const char* v = getenv(env);            // tuning knob: warps per tile; 44 = 4 warps, 4 CTAs/SM, dE in smem
     if (v) {
         const int wanted = atoi(v);
+        if (wanted == 44) return kVariantDsmem;
         for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
-            if (kVariants[i].warps == wanted) return (int)i;
+            if (kVariants[i].warps == wanted && !kVariants[i].dsmem) return (int)i;
     }
     return dflt;
 }
@@ -470,7 +480,7 @@ int ensure_attrs(k1_fn fn) {
     std::lock_guard<std::mutex> lock(mu);
     const std::pair<const void*, int> key((const void*)fn, dev);
     if (done.count(key)) return 0;
-    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + kMaxMels * kTile * 4);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return (int)e;
@@ -490,10 +500,13 @@ int launch_k1(const K1Variant& v, k1_fn fn, K1Args& a, const MelBand& mb, int n,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    const int per_sm = v.ctas < kScratchPerSM ? v.ctas : kScratchPerSM;
+    const int smem = kSmemBytes + (v.dsmem ? mb.n_mels * kTile * 4 : 0);
+    int per_sm = 233472 / (smem + 1024);                           // shared memory per SM / per-CTA footprint
+    if (per_sm > v.ctas) per_sm = v.ctas;
+    if (per_sm < 1) per_sm = 1;
     const long long resident = (long long)sms * per_sm;           // one persistent CTA per scratch slot
     const unsigned blocks = (unsigned)(total < resident ? total : resident);
-    fn<<<blocks, kTile * v.warps, kSmemBytes, stream>>>(a, mb);
+    fn<<<blocks, kTile * v.warps, smem, stream>>>(a, mb);
     return (int)cudaPeekAtLastError();
 }
 
@@ -626,7 +639,7 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
     const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
     MelBand band = plan->bwd;
-    patch_strides(&band, a.msf, plan->dlo, (unsigned)tmax);
+    patch_strides(&band, a.msf, plan->dlo, v.dsmem ? (unsigned)kTile : (unsigned)tmax);
     rec(prof, 0, stream);
     rc = launch_k1(v, v.bwd[mask], a, band, n, stream);
     rec(prof, 1, stream);

@@ -1,0 +1,19 @@
+#!/bin/bash
+# A/B: backward variants.  usage: tools/gpu_ab.sh "<wb list>" "<wf list>"
+mkdir -p gpurun_out
+WBS=${1:-"3 44"}; WFS=${2:-"3"}
+for wb in $WBS; do
+  echo "== pytest gpu with AAS_LMFB_WARPS_BWD=$wb"; AAS_LMFB_WARPS_BWD=$wb timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+done
+for wf in $WFS; do for wb in $WBS; do
+  for wl in sweep_256x10s chime4_30x6s; do
+    AAS_LMFB_WARPS_FWD=$wf AAS_LMFB_WARPS_BWD=$wb timeout 300 python bench.py --workload $wl --steps 200 --warmup 5 --no-cpu > gpurun_out/v.json 2> gpurun_out/v.err || tail -3 gpurun_out/v.err
+    python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/v.json")); r=d["roofline"]; k=r["kernels_ms"]
+    print("wf=$wf wb=$wb %-14s value %.3e step_frac %.3f  k1f %.4f ms (frac %.3f)  k1b %.4f ms (frac %.3f)" % ("$wl", d["value"], r["step_frac"], k["k1_fwd"], r["k1_fwd_frac"], k["k1_bwd"], r["frac"]))
+except Exception as e: print("failed", e)
+PY
+  done
+done; done
