@@ -365,15 +365,23 @@ LMFB_HD void load_masks(int k2, const Tables& tb, const float* __restrict__ mr, 
 // 200 instructions that need nothing from global memory) run while these loads are in flight.
 // `dE` is either the global column (row stride sem_bytes) or, in the variants that stage the
 // tile's dE rows in shared memory, that staged column (row stride 128 bytes).
+template <bool DSMEM>
 LMFB_HD void load_d(int k2, const Tables& tb, const float* __restrict__ dE, unsigned sem_bytes, StepD& in) {
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
         const unsigned f = tb.binof[k2 * 5 + k1], fp = kBins - 1 - f;
         const uint32_t df = tb.off[f], dp = tb.off[fp];
-        in.d0[k1]     = LMFB_LDG(at_bytes(dE, df));
-        in.d1[k1]     = LMFB_LDG(at_bytes(dE, df + sem_bytes));
-        in.d0[5 + k1] = LMFB_LDG(at_bytes(dE, dp));
-        in.d1[5 + k1] = LMFB_LDG(at_bytes(dE, dp + sem_bytes));
+        if (DSMEM) {                                           // shared memory: plain loads
+            in.d0[k1]     = *at_bytes(dE, df);
+            in.d1[k1]     = *at_bytes(dE, df + sem_bytes);
+            in.d0[5 + k1] = *at_bytes(dE, dp);
+            in.d1[5 + k1] = *at_bytes(dE, dp + sem_bytes);
+        } else {
+            in.d0[k1]     = LMFB_LDG(at_bytes(dE, df));
+            in.d1[k1]     = LMFB_LDG(at_bytes(dE, df + sem_bytes));
+            in.d0[5 + k1] = LMFB_LDG(at_bytes(dE, dp));
+            in.d1[5 + k1] = LMFB_LDG(at_bytes(dE, dp + sem_bytes));
+        }
     }
 }
 
@@ -385,12 +393,12 @@ LMFB_HD void load_d(int k2, const Tables& tb, const float* __restrict__ dE, unsi
 //   backward: gradients = (2 Mr Re'^2, 2 Mi Im'^2) * dP, or (Re'^2 + Im'^2) * dP for 'power',
 //             stored to gr/gi (+ f*gsf); every lane's pointers are valid, `inrow` gates the store
 // ---------------------------------------------------------------------------------------
-template <int MASK, bool BWD>
+template <int MASK, bool BWD, bool DSMEM>
 LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const Tables& tb, const StepMasks& in,
                         const float* __restrict__ dE, unsigned sem_bytes,
                         float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
     StepD d;
-    if (BWD) load_d(k2, tb, dE, sem_bytes, d);
+    if (BWD) load_d<DSMEM>(k2, tb, dE, sem_bytes, d);
     const int kb = (32 - k2) & 31;
     float2* ca = col + k2 * kPitch;
     float2* cb = col + kb * kPitch;
@@ -440,7 +448,7 @@ LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const Tables& tb, cons
 // warp's next step are loaded into a second register set while the current step is computed.
 // `a` must already hold the masks of the warp's first step (k2 = w): the caller issues that
 // load before the block barrier that ends pass 1, so its latency hides behind the barrier.
-template <int W, int MASK, bool BWD>
+template <int W, int MASK, bool BWD, bool DSMEM>
 LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const Tables& tb, StepMasks& a,
                        const float* __restrict__ mr, const float* __restrict__ mi,
                        const float* __restrict__ dE, unsigned sem_bytes,
@@ -450,10 +458,10 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const Tables& tb, StepMa
     for (int k2 = w; k2 <= 16; k2 += 2 * W) {
         const bool has_b = k2 + W <= 16;
         if (has_b) load_masks<MASK, BWD>(k2 + W, tb, mr, mi, b);
-        pass2_step<MASK, BWD>(col, k2, tb, a, dE, sem_bytes, gr, gi, inrow);
+        pass2_step<MASK, BWD, DSMEM>(col, k2, tb, a, dE, sem_bytes, gr, gi, inrow);
         if (has_b) {
             if (k2 + 2 * W <= 16) load_masks<MASK, BWD>(k2 + 2 * W, tb, mr, mi, a);
-            pass2_step<MASK, BWD>(col, k2 + W, tb, b, dE, sem_bytes, gr, gi, inrow);
+            pass2_step<MASK, BWD, DSMEM>(col, k2 + W, tb, b, dE, sem_bytes, gr, gi, inrow);
         }
     }
 }

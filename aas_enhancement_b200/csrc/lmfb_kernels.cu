@@ -136,7 +136,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         LMFB_TICK(3);
         __syncthreads();
         LMFB_TICK(4);
-        fft_pass2<W, MASK, BWD>(w, col, tb, first, mr, mi, de, de_stride, gr, gi, inrow);
+        fft_pass2<W, MASK, BWD, DSMEM>(w, col, tb, first, mr, mi, de, de_stride, gr, gi, inrow);
         LMFB_TICK(5);
         if (!BWD) {
             __syncthreads();

@@ -36,7 +36,7 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
             const float* dep = dE ? dE + t + clamp : nullptr;
             StepMasks first;
             load_masks<MASK, BWD>(w, tb, mrp, mip, first);
-            fft_pass2<W, MASK, BWD>(w, S.data() + lane, tb, first, mrp, mip, dep, som * 4u,
+            fft_pass2<W, MASK, BWD, false>(w, S.data() + lane, tb, first, mrp, mip, dep, som * 4u,
                                     gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
         }
     if (!BWD)
