@@ -98,6 +98,7 @@ struct Tables {
     float    ssin[88], scos[88];  // real-split twiddles [k2*5 + k1]
     uint8_t  binof[88];           // bin produced by pass-2 step k2, output k1 [k2*5 + k1]
     uint8_t  fend[kMaxMels];
+    uint8_t  mlb[kBins + 3];      // lower filter ml(f) of every bin (n_mels above the last filter)
     uint8_t  mbeg[kMaxW + 1];
     uint8_t  pad_[3];
     int      n_mels;
@@ -120,6 +121,11 @@ LMFB_HD void tables_fill(Tables* tb, const MelBand& mb, uint32_t msf_bytes, int 
         tb->binof[i] = kBinOf[i / 5][i % 5];
     }
     for (int m = tid; m < kMaxMels; m += nthreads) tb->fend[m] = mb.fend[m];
+    for (int f = tid; f < kBins; f += nthreads) {
+        int c = 0;                                   // ml(f) = number of filters that end at or before f
+        for (int m = 0; m < mb.n_mels; ++m) c += (mb.fend[m] <= f) ? 1 : 0;
+        tb->mlb[f] = (uint8_t)c;
+    }
     for (int i = tid; i <= kMaxW; i += nthreads) tb->mbeg[i] = mb.mbeg[i];
     if (tid == 0) { tb->n_mels = mb.n_mels; tb->msf_bytes = msf_bytes; }
 }
@@ -150,6 +156,10 @@ LMFB_HD float* at_bytes(float* p, uint32_t bytes) {
 #ifdef __CUDACC__
 // predicated 4-byte global store (keeps the store a single predicated instruction)
 __device__ __forceinline__ void st_if(float* p, float v, bool pred) {
+#ifdef LMFB_DBG_NOSTORE
+    if (v == 1.2345e-30f) *p = v;      // experiment: keep the value live, never store
+    return;
+#endif
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}"
                  :: "l"(p), "f"(v), "r"((int)pred));
 }
@@ -356,6 +366,10 @@ LMFB_HD void load_masks(int k2, const Tables& tb, const float* __restrict__ mr, 
     for (int k1 = 0; k1 < 5; ++k1) {
         const unsigned f = tb.binof[k2 * 5 + k1], fp = kBins - 1 - f;
         const uint32_t of = f * msf, op = fp * msf;
+#ifdef LMFB_DBG_NOMASKLOAD
+        in.vr[k1] = in.vr[5 + k1] = 0.5f + 1e-9f * of; in.vi[k1] = in.vi[5 + k1] = 0.25f + 1e-9f * op;   // experiment
+        continue;
+#endif
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(at_bytes(mr, of)); in.vr[5 + k1] = LMFB_LDG(at_bytes(mr, op)); }
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(at_bytes(mi, of)); in.vi[5 + k1] = LMFB_LDG(at_bytes(mi, op)); }
     }
@@ -474,28 +488,52 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const Tables& tb, StepMa
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
 LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const Tables& tb,
-                        float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid) {
+                        float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid
+#ifdef LMFB_TIMELINE
+                        , long long* g_tl_mid = nullptr
+#endif
+                        ) {
     float* colf = reinterpret_cast<float*>(col);
     const int m_lo = tb.mbeg[w], m_hi = tb.mbeg[w + 1];
     if (m_lo >= m_hi) return;
     const int m_first = m_lo > 0 ? m_lo - 1 : 0;
-    int f = m_first > 0 ? (int)tb.fend[m_first - 1] : 0;
+    const int f_lo = m_first > 0 ? (int)tb.fend[m_first - 1] : 0;
+    const int f_hi = tb.fend[m_hi - 1];
+    // Flat walk over the bins: everything a bin needs (offset, two weights, "a filter ends here")
+    // is read with loads whose addresses do not depend on the running sums, and the hand-over
+    // from one filter to the next is a predicated store plus two selects -- no branch in the loop
+    // (except when several filters end at the same bin, which only very dense bases produce).
+    int m = m_first;
     float acc0 = 0.0f, acc1 = 0.0f;
     float* ep = colf + (1 + m_first) * 2 * kPitch + 1;     // E[m] -> .y of slot 1+m
-#pragma unroll 1
-    for (int m = m_first; m < m_hi; ++m) {
-        const int fe = tb.fend[m];
-#pragma unroll 4
-        for (; f < fe; ++f) {                              // no branch inside: the loads overlap
-            const float p = colf[tb.off[f]];
-            acc0 = fmaf(tb.wl[f], p, acc0);
-            acc1 = fmaf(tb.wh[f], p, acc1);
+#pragma unroll 8
+    for (int f = f_lo; f < f_hi; ++f) {
+        int fl = (int)tb.mlb[f] - m;                       // filters that are complete before this bin
+        const float p = colf[tb.off[f]];
+        const float wl = tb.wl[f], wh = tb.wh[f];
+        while (fl > 1) {                                   // rare: an empty filter in between
+            if (m >= m_lo) *ep = acc0;
+            ep += 2 * kPitch; acc0 = acc1; acc1 = 0.0f; ++m; --fl;
         }
-        if (m >= m_lo) *ep = acc0;                         // the early filter m_lo-1 belongs to another warp
+        const bool flush = fl != 0;
+        if (flush && m >= m_lo) *ep = acc0;                // the early filter m_lo-1 belongs to another warp
+        ep += flush ? 2 * kPitch : 0;
+        m += flush ? 1 : 0;
+        acc0 = flush ? acc1 : acc0;
+        acc1 = flush ? 0.0f : acc1;
+        acc0 = fmaf(wl, p, acc0);
+        acc1 = fmaf(wh, p, acc1);
+    }
+#pragma unroll 1
+    for (; m < m_hi; ++m) {                                // the last filter(s), incl. empty ones
+        if (m >= m_lo) *ep = acc0;
         ep += 2 * kPitch;
         acc0 = acc1;
         acc1 = 0.0f;
     }
+#ifdef LMFB_TIMELINE
+    if (g_tl_mid) *g_tl_mid = clock64();
+#endif
     const float* eq = colf + (1 + m_lo) * 2 * kPitch + 1;
     float* op = at_bytes(out, (uint32_t)m_lo * som_bytes);
 #pragma unroll 4

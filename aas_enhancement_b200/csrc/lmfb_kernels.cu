@@ -90,6 +90,20 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
             continue;
         }
 
+#ifndef LMFB_DBG_NOPREFETCH
+#ifdef LMFB_DBG_PREFETCH_NEXT
+        {   // experiment: prefetch the NEXT tile's rows (a whole tile ahead)
+            const int nt = tile + gridDim.x;
+            if (nt < a.total_tiles) {
+                const int nn = nt / a.tiles_per_utt;
+                const int nt0 = (nt - nn * a.tiles_per_utt) * kTile;
+                if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)nn * a.msn, a.msf, kBins, nt0, a.tmax);
+                if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)nn * a.msn, a.msf, kBins, nt0, a.tmax);
+                if (BWD && !DSMEM) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)nn * n_mels * som, som, n_mels, nt0, a.tmax);
+                prefetch_wave_l2(threadIdx.x, kTile * W, a.wave + (long long)nn * a.wave_stride, a.lengths[nn], nt0);
+            }
+        }
+#else
         // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs ...
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
@@ -103,6 +117,8 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
                                  (nt - nn * a.tiles_per_utt) * kTile);
             }
         }
+#endif
+#endif
 
 #ifdef LMFB_TIMELINE
         long long tl[8];
@@ -141,7 +157,13 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         if (!BWD) {
             __syncthreads();
             LMFB_TICK(6);
+#ifdef LMFB_TIMELINE
+            long long mid = 0;
+            phase3_fwd(w, col, tb, po, som * 4u, inrow, valid, &mid);
+            tl[5] = mid;                        // (overwrites the pass-2 end stamp: phase 3 split A | B)
+#else
             phase3_fwd(w, col, tb, po, som * 4u, inrow, valid);
+#endif
         }
 #ifdef LMFB_TIMELINE
         else tl[6] = tl[5];

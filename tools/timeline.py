@@ -8,7 +8,9 @@ import torch
 from aas_enhancement_b200 import build as B
 lib_dbg = os.path.join(ROOT, "gpurun_out", "libaas_lmfb_timeline.so")
 os.makedirs(os.path.dirname(lib_dbg), exist_ok=True)
-subprocess.check_call([B.find_nvcc()] + B.NVCC_FLAGS + ["-DLMFB_TIMELINE", B.SRC, "-o", lib_dbg])
+extra = [a for a in sys.argv[2:] if a.startswith("-D")]
+subprocess.check_call([B.find_nvcc()] + B.NVCC_FLAGS + ["-DLMFB_TIMELINE"] + extra + [B.SRC, "-o", lib_dbg])
+print("debug build flags:", extra)
 from aas_enhancement_b200 import _lib
 _lib.LIB_PATH = lib_dbg
 from aas_enhancement_b200 import LMFBFrontEnd
@@ -16,7 +18,7 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "sweep"
 n, samples = (256, 160000) if wl == "sweep" else (30, 96000)
 tmax = 1 + samples // 160
 dev = torch.device("cuda", 0)
-W = 3
+W = int(os.environ.get("TL_W", "3"))
 buf_f = torch.zeros(8 * 64 * 8 * 8, dtype=torch.int64, device=dev)
 buf_b = torch.zeros(8 * 64 * 8 * 8, dtype=torch.int64, device=dev)
 os.environ["AAS_LMFB_TIMELINE_FWD"] = str(buf_f.data_ptr())
@@ -32,7 +34,7 @@ g = torch.randn(n, 40, tmax, device=dev)
 for _ in range(3):
     z, _ = fe(wave, lens, mr, mi); z.backward(g)
 torch.cuda.synchronize()
-names = ["stage", "wait1", "pass1+ld", "wait2", "pass2", "wait3", "phase3"]
+names = ["stage", "wait1", "pass1+ld", "wait2", "pass2*", "p3A(neg)", "p3B*"]  # fwd: tl5 = phase-3 mid stamp
 for label, buf in (("fwd", buf_f), ("bwd", buf_b)):
     t = buf.cpu().view(8, 64, -1)[:, :, :W * 8].reshape(8, 64, W, 8).double()
     valid = t[..., 7] > 0
@@ -42,6 +44,10 @@ for label, buf in (("fwd", buf_f), ("bwd", buf_b)):
         m = valid[:, :, w]
         row = [float(d[:, :, w, i][m].mean()) for i in range(7)]
         tot = float((t[:, :, w, 7] - t[:, :, w, 0])[m].mean())
+        if label == "fwd":
+            a = float((t[:, :, w, 5] - t[:, :, w, 6])[m].mean()); b = float((t[:, :, w, 7] - t[:, :, w, 5])[m].mean())
+            p2 = float((t[:, :, w, 6] - t[:, :, w, 4])[m].mean())
+            print(f"     fwd detail: pass2+barrier={p2:8.0f}  phase3 stageA={a:8.0f}  stageB={b:8.0f}")
         print("  warp", w, " ".join(f"{nm}={v:8.0f}" for nm, v in zip(names, row)), f" total={tot:9.0f}")
     # tile-to-tile period of one CTA
     per = (t[1:, :, 0, 0] - t[:-1, :, 0, 0])[valid[1:, :, 0] & valid[:-1, :, 0]]
