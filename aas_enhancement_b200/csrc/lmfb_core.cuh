@@ -163,8 +163,16 @@ __device__ __forceinline__ void st_if(float* p, float v, bool pred) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}"
                  :: "l"(p), "f"(v), "r"((int)pred));
 }
+// predicated shared-memory store that the optimiser does not see as a memory access: used for
+// the E[m] slots of phase 3, which can never alias the P[f] words the same loop reads, so that
+// those reads may be hoisted and overlapped freely.
+__device__ __forceinline__ void sts_if_noalias(float* p, float v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}"
+                 :: "r"((unsigned)__cvta_generic_to_shared(p)), "f"(v), "r"((int)pred));
+}
 #else
 static inline void st_if(float* p, float v, bool pred) { if (pred) *p = v; }
+static inline void sts_if_noalias(float* p, float v, bool pred) { if (pred) *p = v; }
 #endif
 
 // ---------------------------------------------------------------------------------------
@@ -506,17 +514,20 @@ LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const Tables& tb,
     int m = m_first;
     float acc0 = 0.0f, acc1 = 0.0f;
     float* ep = colf + (1 + m_first) * 2 * kPitch + 1;     // E[m] -> .y of slot 1+m
+    int f5 = f_lo % 5;                                     // slot of bin f = (f mod 5)*32 + (f mod 32), kept incrementally
 #pragma unroll 8
     for (int f = f_lo; f < f_hi; ++f) {
+        const int off = (f5 * 32 + (f & 31)) * (2 * kPitch) + (f == kBins - 1 ? 1 : 0);
+        f5 = f5 == 4 ? 0 : f5 + 1;
         int fl = (int)tb.mlb[f] - m;                       // filters that are complete before this bin
-        const float p = colf[tb.off[f]];
+        const float p = colf[off];
         const float wl = tb.wl[f], wh = tb.wh[f];
         while (fl > 1) {                                   // rare: an empty filter in between
-            if (m >= m_lo) *ep = acc0;
+            sts_if_noalias(ep, acc0, m >= m_lo);
             ep += 2 * kPitch; acc0 = acc1; acc1 = 0.0f; ++m; --fl;
         }
         const bool flush = fl != 0;
-        if (flush && m >= m_lo) *ep = acc0;                // the early filter m_lo-1 belongs to another warp
+        sts_if_noalias(ep, acc0, flush && m >= m_lo);      // the early filter m_lo-1 belongs to another warp
         ep += flush ? 2 * kPitch : 0;
         m += flush ? 1 : 0;
         acc0 = flush ? acc1 : acc0;
@@ -526,11 +537,15 @@ LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const Tables& tb,
     }
 #pragma unroll 1
     for (; m < m_hi; ++m) {                                // the last filter(s), incl. empty ones
-        if (m >= m_lo) *ep = acc0;
+        sts_if_noalias(ep, acc0, m >= m_lo);
         ep += 2 * kPitch;
         acc0 = acc1;
         acc1 = 0.0f;
     }
+#ifdef __CUDACC__
+    __syncwarp();                                          // order the asm stores before the reads below
+    asm volatile("" ::: "memory");
+#endif
 #ifdef LMFB_TIMELINE
     if (g_tl_mid) *g_tl_mid = clock64();
 #endif
