@@ -505,47 +505,23 @@ LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const Tables& tb,
     const int m_lo = tb.mbeg[w], m_hi = tb.mbeg[w + 1];
     if (m_lo >= m_hi) return;
     const int m_first = m_lo > 0 ? m_lo - 1 : 0;
-    const int f_lo = m_first > 0 ? (int)tb.fend[m_first - 1] : 0;
-    const int f_hi = tb.fend[m_hi - 1];
-    // Flat walk over the bins: everything a bin needs (offset, two weights, "a filter ends here")
-    // is read with loads whose addresses do not depend on the running sums, and the hand-over
-    // from one filter to the next is a predicated store plus two selects -- no branch in the loop
-    // (except when several filters end at the same bin, which only very dense bases produce).
-    int m = m_first;
+    int f = m_first > 0 ? (int)tb.fend[m_first - 1] : 0;
     float acc0 = 0.0f, acc1 = 0.0f;
     float* ep = colf + (1 + m_first) * 2 * kPitch + 1;     // E[m] -> .y of slot 1+m
-    int f5 = f_lo % 5;                                     // slot of bin f = (f mod 5)*32 + (f mod 32), kept incrementally
-#pragma unroll 8
-    for (int f = f_lo; f < f_hi; ++f) {
-        const int off = (f5 * 32 + (f & 31)) * (2 * kPitch) + (f == kBins - 1 ? 1 : 0);
-        f5 = f5 == 4 ? 0 : f5 + 1;
-        int fl = (int)tb.mlb[f] - m;                       // filters that are complete before this bin
-        const float p = colf[off];
-        const float wl = tb.wl[f], wh = tb.wh[f];
-        while (fl > 1) {                                   // rare: an empty filter in between
-            sts_if_noalias(ep, acc0, m >= m_lo);
-            ep += 2 * kPitch; acc0 = acc1; acc1 = 0.0f; ++m; --fl;
-        }
-        const bool flush = fl != 0;
-        sts_if_noalias(ep, acc0, flush && m >= m_lo);      // the early filter m_lo-1 belongs to another warp
-        ep += flush ? 2 * kPitch : 0;
-        m += flush ? 1 : 0;
-        acc0 = flush ? acc1 : acc0;
-        acc1 = flush ? 0.0f : acc1;
-        acc0 = fmaf(wl, p, acc0);
-        acc1 = fmaf(wh, p, acc1);
-    }
 #pragma unroll 1
-    for (; m < m_hi; ++m) {                                // the last filter(s), incl. empty ones
-        sts_if_noalias(ep, acc0, m >= m_lo);
+    for (int m = m_first; m < m_hi; ++m) {
+        const int fe = tb.fend[m];
+#pragma unroll 4
+        for (; f < fe; ++f) {                              // no branch inside: the loads overlap
+            const float p = colf[tb.off[f]];
+            acc0 = fmaf(tb.wl[f], p, acc0);
+            acc1 = fmaf(tb.wh[f], p, acc1);
+        }
+        if (m >= m_lo) *ep = acc0;                         // the early filter m_lo-1 belongs to another warp
         ep += 2 * kPitch;
         acc0 = acc1;
         acc1 = 0.0f;
     }
-#ifdef __CUDACC__
-    __syncwarp();                                          // order the asm stores before the reads below
-    asm volatile("" ::: "memory");
-#endif
 #ifdef LMFB_TIMELINE
     if (g_tl_mid) *g_tl_mid = clock64();
 #endif

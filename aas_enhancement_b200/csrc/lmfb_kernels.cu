@@ -42,6 +42,7 @@ struct K1Args {
     int            total_tiles;
     int            vec_ok;
     long long*     timeline;   // debug builds (-DLMFB_TIMELINE) only: per-warp phase clocks
+    int            stagger_ns; // delay of the k-th resident CTA of an SM before its first tile
 };
 
 constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
@@ -60,6 +61,12 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     stage_lane_init(lane, a.window, sl);
     float2* col = S + lane;
 
+    // CTAs that start together would run their phases in lockstep (all staging, then all FFT, ...)
+    // and leave the load/store and math pipes idle in turn; de-phase the co-resident CTAs once.
+    if (a.stagger_ns > 0) {
+        const unsigned k = blockIdx.x / 148u;
+        if (k > 0) __nanosleep(k * (unsigned)a.stagger_ns);
+    }
     // persistent CTA: tiles are dealt round-robin, neighbouring tiles run at the same time
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int n   = tile / a.tiles_per_utt;
@@ -122,7 +129,10 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
 
 #ifdef LMFB_TIMELINE
         long long tl[8];
-#define LMFB_TICK(i) tl[i] = clock64()
+// after a barrier the clock is only meaningful once something protected by the barrier has been
+// touched (BAR.SYNC is deferred-blocking): read a shared word first
+#define LMFB_TICK(i) do { volatile float* vs_ = reinterpret_cast<volatile float*>(S); float x_ = vs_[lane]; \
+                          asm volatile("" :: "f"(x_) : "memory"); tl[i] = clock64(); } while (0)
 #else
 #define LMFB_TICK(i) ((void)0)
 #endif
@@ -442,6 +452,7 @@ struct aas_lmfb_plan {
     uint8_t dlo[kBins];
     int     n_mels;
     int     vfwd, vbwd;
+    int     stagger_ns;
 };
 
 extern "C" int aas_lmfb_abi_version(void) { return AAS_LMFB_ABI_VERSION; }
@@ -473,6 +484,7 @@ extern "C" aas_lmfb_plan* aas_lmfb_plan_create(const float* mel, int n_mels, int
         p->n_mels = n_mels;
         p->vfwd = pick_variant("AAS_LMFB_WARPS_FWD", -1);       // -1: choose by problem size at launch
         p->vbwd = pick_variant("AAS_LMFB_WARPS_BWD", -1);
+        { const char* e = getenv("AAS_LMFB_STAGGER_NS"); p->stagger_ns = e ? atoi(e) : 0; }
         int ml[kBins];
         if (build_mel_band(mel, n_mels, 1, &p->fwd, ml) != 0) { st = AAS_LMFB_E_MEL; break; }
         make_bwd_band(p->fwd, ml, &p->bwd, p->dlo);
@@ -578,6 +590,7 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
 #ifdef LMFB_TIMELINE
     { const char* e = getenv(false ? "AAS_LMFB_TIMELINE_BWD" : "AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
 #endif
+    a.stagger_ns = plan->stagger_ns;
 
     const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
     const K1Variant& v = kVariants[plan->vfwd >= 0 ? plan->vfwd : (small ? kFwdVariantSmall : kFwdVariantBig)];
@@ -657,6 +670,7 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
 #ifdef LMFB_TIMELINE
     { const char* e = getenv(true ? "AAS_LMFB_TIMELINE_BWD" : "AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
 #endif
+    a.stagger_ns = plan->stagger_ns;
 
     const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
     const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
