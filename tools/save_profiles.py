@@ -117,5 +117,12 @@ for k, lines in blocks.items():
         short = "k1_bwd_reim_w3" if "Lb1" in k else "k1_fwd_reim_w3"
         with open(os.path.join(P, f"{tag}_sass_{short}.txt"), "w") as f:
             f.write(f"# {k}\n")
-            f.write("\n".join(l for l in lines if "/* 0x" not in l or "*/ " in l.split("/* 0x")[0]) + "\n")
+            import re as _re
+            keep = []
+            for l in lines:
+                if _re.match(r"\s+/\*[0-9a-f]{4}\*/", l):            # instruction line: drop the hex encoding
+                    keep.append(_re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip())
+                elif l.strip().startswith(".") or "headerflags" in l:
+                    keep.append(l.rstrip())
+            f.write("\n".join(keep) + "\n")
 print("saved", sorted(x for x in os.listdir(P) if x.startswith(tag) or x == "traffic.json"))
