@@ -508,12 +508,15 @@ LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const Tables& tb,
     int f = m_first > 0 ? (int)tb.fend[m_first - 1] : 0;
     float acc0 = 0.0f, acc1 = 0.0f;
     float* ep = colf + (1 + m_first) * 2 * kPitch + 1;     // E[m] -> .y of slot 1+m
+    int fe = tb.fend[m_first];
 #pragma unroll 1
     for (int m = m_first; m < m_hi; ++m) {
-        const int fe = tb.fend[m];
+        const int fe_next = m + 1 < m_hi ? (int)tb.fend[m + 1] : fe;     // fetched one filter ahead
 #pragma unroll 4
-        for (; f < fe; ++f) {                              // no branch inside: the loads overlap
-            const float p = colf[tb.off[f]];
+        for (; f < fe; ++f) {
+            // slot of bin f computed, not looked up: the P read does not wait for a table read
+            const int off = ((f % 5) * 32 + (f & 31)) * (2 * kPitch) + (f == kBins - 1 ? 1 : 0);
+            const float p = colf[off];
             acc0 = fmaf(tb.wl[f], p, acc0);
             acc1 = fmaf(tb.wh[f], p, acc1);
         }
@@ -521,6 +524,7 @@ LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const Tables& tb,
         ep += 2 * kPitch;
         acc0 = acc1;
         acc1 = 0.0f;
+        fe = fe_next;
     }
 #ifdef LMFB_TIMELINE
     if (g_tl_mid) *g_tl_mid = clock64();
