@@ -427,13 +427,16 @@ struct K1Variant { int warps, ctas, dsmem; k1_fn fwd[3], bwd[3]; };   // indexed
 static const K1Variant kVariants[] = {
     LMFB_VARIANT(4, 5, false), LMFB_VARIANT(2, 5, false), LMFB_VARIANT(3, 5, false),
     LMFB_VARIANT(5, 4, false), LMFB_VARIANT(1, 5, false), LMFB_VARIANT(4, 4, true),
+    LMFB_VARIANT(4, 4, false),
 };
 constexpr int kVariantDsmem = 5;
+constexpr int kVariant44 = 6;
 // Defaults measured on B200 (profiles/): in the throughput regime (more tiles than resident CTAs)
 // 3 warps per tile win for both directions (128 registers, no spills); in the latency regime (a
-// launch that does not fill the resident slots, e.g. 30 x 6 s) the forward prefers 4 warps and
-// the backward 2 (168 registers, nothing spilled, shortest per-tile critical path).
-constexpr int kFwdVariantBig = 2, kFwdVariantSmall = 0;
+// launch that does not fill the resident slots, e.g. 30 x 6 s) the forward prefers 4 warps with
+// the register budget of 4 CTAs/SM (128 registers) and the backward 2 warps (168 registers):
+// nothing spilled, shortest per-tile critical path.
+constexpr int kFwdVariantBig = 2, kFwdVariantSmall = 6;
 constexpr int kBwdVariantBig = 2, kBwdVariantSmall = 1;
 
 static int pick_variant(const char* env, int dflt) {
@@ -441,8 +444,9 @@ static int pick_variant(const char* env, int dflt) {
     if (v) {
         const int wanted = atoi(v);
         if (wanted == 44) return kVariantDsmem;
+        if (wanted == 40) return kVariant44;           // 4 warps, register budget for 4 CTAs/SM
         for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
-            if (kVariants[i].warps == wanted && !kVariants[i].dsmem) return (int)i;
+            if (kVariants[i].warps == wanted && kVariants[i].ctas == (wanted == 5 ? 4 : 5) && !kVariants[i].dsmem) return (int)i;
     }
     return dflt;
 }

@@ -275,14 +275,16 @@ def run_ours(args):
     peak, peak_src = peaks()
     ms_per_step = ms / args.steps
     value = world * audio_s * args.steps / (ms / 1e3)
-    k1b = k_avg["k1_bwd"] / 1e3
-    achieved = frames * B_K1_BWD / k1b / 1e9
+    # the dominant kernel is whichever K1 launch takes longer on this workload
+    dom = "k1_bwd" if k_avg["k1_bwd"] >= k_avg["k1_fwd"] else "k1_fwd"
+    dom_bytes = B_K1_BWD if dom == "k1_bwd" else B_K1_FWD
+    achieved = frames * dom_bytes / (k_avg[dom] / 1e3) / 1e9
     step_gbs = frames * (B_FWD + B_BWD) / (ms_per_step / 1e3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("k1_bwd_dram_bytes")
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(dom + "_dram_bytes")
         except Exception:
             traffic = None
     line = {
@@ -299,13 +301,15 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": 4 * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "lmfb_k1<reim,bwd>", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "lmfb_k1<reim,%s>" % ("bwd" if dom == "k1_bwd" else "fwd"),
+                     "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": frames * B_K1_BWD,
-                     "avg_launch_ms": k_avg["k1_bwd"],
+                     "algorithmic_bytes_per_launch": frames * dom_bytes,
+                     "avg_launch_ms": k_avg[dom],
                      "kernels_ms": k_avg,
                      "k1_fwd_frac": frames * B_K1_FWD / (k_avg["k1_fwd"] / 1e3) / 1e9 / peak,
+                     "k1_bwd_frac": frames * B_K1_BWD / (k_avg["k1_bwd"] / 1e3) / 1e9 / peak,
                      "step_algorithmic_gbs_per_gpu": step_gbs, "step_frac": step_gbs / peak},
     }
     if world == 1 and not args.no_cpu:

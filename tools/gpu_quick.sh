@@ -8,7 +8,7 @@ import json
 for f in ("gpurun_out/bench_$TAG.json",):
     try:
         d=json.load(open(f)); r=d["roofline"]
-        print("value %.3e audio-s/s  ms/step %.4f  k1b frac %.3f k1f frac %.3f step frac %.3f e2e %.3e" % (d["value"], d["ms_per_step"], r["frac"], r["k1_fwd_frac"], r["step_frac"], d["e2e"]["value"]), r["kernels_ms"])
+        print("value %.3e audio-s/s  ms/step %.4f  dom frac %.3f k1f frac %.3f step frac %.3f e2e %.3e" % (d["value"], d["ms_per_step"], r["frac"], r["k1_fwd_frac"], r["step_frac"], d["e2e"]["value"]), r["kernels_ms"])
     except Exception as e: print("bench parse failed", e)
 PY
 echo "== bench sweep"; timeout 600 python bench.py --workload sweep_256x10s --steps 40 --warmup 5 --no-cpu > gpurun_out/bench_sweep_$TAG.json 2> gpurun_out/bench_sweep_$TAG.err; tail -3 gpurun_out/bench_sweep_$TAG.err; python - <<PY
@@ -16,7 +16,7 @@ import json
 for f in ("gpurun_out/bench_sweep_$TAG.json",):
     try:
         d=json.load(open(f)); r=d["roofline"]
-        print("value %.3e audio-s/s  ms/step %.4f  k1b frac %.3f k1f frac %.3f step frac %.3f e2e %.3e" % (d["value"], d["ms_per_step"], r["frac"], r["k1_fwd_frac"], r["step_frac"], d["e2e"]["value"]), r["kernels_ms"])
+        print("value %.3e audio-s/s  ms/step %.4f  dom frac %.3f k1f frac %.3f step frac %.3f e2e %.3e" % (d["value"], d["ms_per_step"], r["frac"], r["k1_fwd_frac"], r["step_frac"], d["e2e"]["value"]), r["kernels_ms"])
     except Exception as e: print("bench parse failed", e)
 PY
 if [ "$2" != "noncu" ]; then

@@ -75,11 +75,12 @@ for wl, rep in (("chime4_30x6s", f"prof_chime_{tag}.ncu-rep"), ("sweep_256x10s",
                 if w in hdr:
                     i = hdr.index(w)
                     f.write(f"   {w:70s} {r[i]:>16s} {units[i]}\n")
-            if "1, 1" in name or "(bool)1" in name:
+            key = "k1_bwd_dram_bytes" if ("<1, 1" in name or "(bool)1" in name) else "k1_fwd_dram_bytes"
+            if True:
                 def val(m):
                     i = hdr.index(m); x = float(r[i].replace(",", "")); u = units[i].lower()
                     return x * (1e9 if u.startswith("g") else 1e6 if u.startswith("m") else 1e3 if u.startswith("k") else 1)
-                traffic.setdefault(wl, {})["k1_bwd_dram_bytes"] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+                traffic.setdefault(wl, {})[key] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
                 traffic[wl]["tag"] = tag
     src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     st = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_stalls.py"), "15"], input=src,
