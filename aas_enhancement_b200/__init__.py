@@ -6,9 +6,10 @@ C ABI (``include/aas_lmfb.h``), plus the host-side mirror of the reference's bat
 """
 from .lmfb import (LMFB, LMFBFrontEnd, MelPlan, hamming_window, slaney_mel_basis,
                    N_FFT, HOP, N_BINS)
+from .losses import L1Loss_mask
 from .collate import (collate_wave, collate_wave_paired, ctc_sizes, frame_count,
                       shard_utterances, get_variable_nograd)
 
-__all__ = ["LMFB", "LMFBFrontEnd", "MelPlan", "hamming_window", "slaney_mel_basis",
+__all__ = ["LMFB", "LMFBFrontEnd", "MelPlan", "L1Loss_mask", "hamming_window", "slaney_mel_basis",
            "collate_wave", "collate_wave_paired", "ctc_sizes", "frame_count",
            "shard_utterances", "get_variable_nograd", "N_FFT", "HOP", "N_BINS"]

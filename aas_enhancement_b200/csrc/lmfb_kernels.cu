@@ -685,3 +685,94 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     rec(prof, 1, stream);
     return rc;
 }
+
+// ======================================================================================
+// L1Loss_mask (Speech_enhancement_by_AAS/model.py:19-31): the loss every trainer applies to the
+// LMFB features right after this front-end (trainer_AAS.py:146-161, :176-181; trainer_DCE.py).
+//   loss = sum |input - target| / nElement,   nElement = numel(mask) - sum(mask)  (unmasked FRAMES)
+// The reference's masked_fill is not in-place, i.e. a no-op: padded frames DO contribute.  That
+// behaviour is reproduced when `mask` is NULL; passing the byte mask zeroes the padded frames
+// (the evident intent), as an opt-in.
+// ======================================================================================
+namespace aas_lmfb {
+
+constexpr int kL1Threads = 256;
+constexpr int kL1MaxBlocks = 1184;           // 148 SMs x 8
+
+__global__ void __launch_bounds__(kL1Threads)
+l1_abs_partial(const float* __restrict__ a, const float* __restrict__ b, const uint8_t* __restrict__ mask,
+               long long total, int c, int tmax, float* __restrict__ partial) {
+    __shared__ double red[kL1Threads / 32];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * kL1Threads + threadIdx.x; i < total;
+         i += (long long)gridDim.x * kL1Threads) {
+        float d = fabsf(a[i] - b[i]);
+        if (mask) {
+            const long long n = i / ((long long)c * tmax);
+            const int t = (int)(i % tmax);
+            if (mask[n * tmax + t]) d = 0.0f;
+        }
+        s += (double)d;
+    }
+    const double tot = block_sum(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = (float)tot;
+}
+
+__global__ void __launch_bounds__(kL1Threads)
+l1_abs_final(const float* __restrict__ partial, int count, float* __restrict__ out) {
+    __shared__ double red[kL1Threads / 32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += kL1Threads) s += (double)partial[i];   // fixed order: deterministic
+    const double tot = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = (float)tot;
+}
+
+__global__ void __launch_bounds__(kL1Threads)
+l1_abs_grad(const float* __restrict__ a, const float* __restrict__ b, const uint8_t* __restrict__ mask,
+            long long total, int c, int tmax, const float* __restrict__ scale,
+            float* __restrict__ ga, float* __restrict__ gb) {
+    const float sc = scale[0];
+    for (long long i = (long long)blockIdx.x * kL1Threads + threadIdx.x; i < total;
+         i += (long long)gridDim.x * kL1Threads) {
+        const float d = a[i] - b[i];
+        float g = d > 0.0f ? sc : (d < 0.0f ? -sc : 0.0f);            // torch: sign(0) = 0
+        if (mask) {
+            const long long n = i / ((long long)c * tmax);
+            const int t = (int)(i % tmax);
+            if (mask[n * tmax + t]) g = 0.0f;
+        }
+        if (ga) ga[i] = g;
+        if (gb) gb[i] = -g;
+    }
+}
+
+}  // namespace aas_lmfb
+
+extern "C" int aas_l1_partial_count(void) { return kL1MaxBlocks; }
+
+extern "C" int aas_l1_abs_sum(const float* a, const float* b, const uint8_t* mask, int n, int c, int tmax,
+                              float* partial, float* out, void* cuda_stream) {
+    if (!a || !b || !partial || !out) return AAS_LMFB_E_NULL;
+    if (n < 0 || c < 1 || tmax < 1) return AAS_LMFB_E_SHAPE;
+    const long long total = (long long)n * c * tmax;
+    long long blocks = (total + kL1Threads - 1) / kL1Threads;
+    if (blocks > kL1MaxBlocks) blocks = kL1MaxBlocks;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    l1_abs_partial<<<(unsigned)blocks, kL1Threads, 0, stream>>>(a, b, mask, total, c, tmax, partial);
+    l1_abs_final<<<1, kL1Threads, 0, stream>>>(partial, (int)blocks, out);
+    return (int)cudaPeekAtLastError();
+}
+
+extern "C" int aas_l1_abs_grad(const float* a, const float* b, const uint8_t* mask, int n, int c, int tmax,
+                               const float* scale, float* grad_a, float* grad_b, void* cuda_stream) {
+    if (!a || !b || !scale || (!grad_a && !grad_b)) return AAS_LMFB_E_NULL;
+    if (n < 0 || c < 1 || tmax < 1) return AAS_LMFB_E_SHAPE;
+    const long long total = (long long)n * c * tmax;
+    if (total == 0) return AAS_LMFB_OK;
+    long long blocks = (total + kL1Threads - 1) / kL1Threads;
+    if (blocks > kL1MaxBlocks) blocks = kL1MaxBlocks;
+    l1_abs_grad<<<(unsigned)blocks, kL1Threads, 0, (cudaStream_t)cuda_stream>>>(a, b, mask, total, c, tmax, scale,
+                                                                               grad_a, grad_b);
+    return (int)cudaPeekAtLastError();
+}

@@ -1,0 +1,84 @@
+"""``L1Loss_mask`` -- the loss every trainer of the reference applies to the LMFB features right
+after the front-end (Speech_enhancement_by_AAS/model.py:19-31; call sites trainer_AAS.py:146-161,
+:176-181, trainer_DCE.py, trainer_FSEGAN.py).  Same name, call signature and return value
+``(loss, nElement)``; the sum and its gradient run in CUDA kernels behind the C ABI
+(``aas_l1_abs_sum`` / ``aas_l1_abs_grad``), deterministically.
+
+Reference quirks, reproduced by default (``fix_masking=False``):
+* ``err.masked_fill(mask, 0)`` is not in-place, i.e. a no-op: padded frames contribute to the sum;
+* the divisor is ``mask.nelement() - mask.sum()``: the number of unmasked FRAMES, not elements;
+* ``nElement`` is only defined when ``mask[0][0][0] == 0`` (the reference raises otherwise).
+``fix_masking=True`` zeroes the padded frames, which is the evident intent.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class _L1AbsSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, target, mask_or_none):
+        if not input.is_cuda:
+            raise RuntimeError("L1Loss_mask is CUDA-only (sm_100a); there is no CPU fallback")
+        lib = _lib.load()
+        a = input.contiguous().float()
+        b = target.contiguous().float()
+        if a.shape != b.shape or a.dim() != 3:
+            raise ValueError("input and target must both be (N, C, Tmax)")
+        n, c, tmax = a.shape
+        m = None
+        if mask_or_none is not None:
+            m = mask_or_none.contiguous().to(torch.uint8)
+            if m.shape != (n, 1, tmax):
+                raise ValueError("mask must be (N, 1, Tmax)")
+        partial = torch.empty(lib.aas_l1_partial_count(), dtype=torch.float32, device=a.device)
+        out = torch.empty(1, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            rc = lib.aas_l1_abs_sum(a.data_ptr(), b.data_ptr(), None if m is None else m.data_ptr(),
+                                    n, c, tmax, partial.data_ptr(), out.data_ptr(),
+                                    torch.cuda.current_stream(a.device).cuda_stream)
+        _lib.check(rc)
+        ctx.save_for_backward(a, b, m)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        a, b, m = ctx.saved_tensors
+        lib = _lib.load()
+        n, c, tmax = a.shape
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ga = torch.empty_like(a) if need_a else None
+        gb = torch.empty_like(b) if need_b else None
+        if ga is None and gb is None:
+            return None, None, None
+        scale = grad.reshape(1).to(torch.float32).contiguous()
+        with torch.cuda.device(a.device):
+            rc = lib.aas_l1_abs_grad(a.data_ptr(), b.data_ptr(), None if m is None else m.data_ptr(),
+                                     n, c, tmax, scale.data_ptr(),
+                                     None if ga is None else ga.data_ptr(),
+                                     None if gb is None else gb.data_ptr(),
+                                     torch.cuda.current_stream(a.device).cuda_stream)
+        _lib.check(rc)
+        return ga, gb, None
+
+
+class L1Loss_mask(torch.nn.Module):
+    """Drop-in for the reference's ``L1Loss_mask`` (model.py:19-31): ``forward(input, target, mask)``
+    returns ``(loss, nElement)``."""
+
+    def __init__(self, fix_masking: bool = False):
+        super().__init__()
+        self.fix_masking = fix_masking
+
+    def forward(self, input, target, mask):
+        mask_sum = mask.sum()
+        if bool(mask[0][0][0] == 0):                      # data_as_0 = True (model.py:25)
+            n_element = mask.nelement() - mask_sum
+        else:                                             # the reference hits an UnboundLocalError here
+            raise RuntimeError("L1Loss_mask: mask[0][0][0] != 0 -- nElement is undefined in the reference "
+                               "(model.py:25-26); batches are length-sorted, so the first frame is never padding")
+        err_sum = _L1AbsSum.apply(input, target, mask if self.fix_masking else None)
+        loss = err_sum / n_element
+        return loss, n_element

@@ -99,6 +99,21 @@ int aas_lmfb_backward(const aas_lmfb_plan* plan,
                       void* workspace, int tmax,
                       uint32_t flags, float eps, void* cuda_stream, void* const* prof);
 
+/* ---- L1Loss_mask: the loss applied to the features right after this front-end --------------
+ * Replaces Speech_enhancement_by_AAS/model.py:19-31 (called at trainer_AAS.py:146-161, :176-181,
+ * trainer_DCE.py, trainer_FSEGAN.py): sum |a - b| over (N, C, Tmax), deterministic two-stage sum.
+ *   mask  NULL reproduces the reference exactly (its masked_fill is a no-op, so padded frames
+ *         contribute); a (N, 1, Tmax) byte mask (1 = padding) zeroes the padded frames instead.
+ *   partial  scratch of aas_l1_partial_count() floats;  out  one float (the un-normalised sum).
+ * The division by nElement = numel(mask) - sum(mask) (frames, not elements) is host-side glue. */
+int aas_l1_partial_count(void);
+int aas_l1_abs_sum(const float* a, const float* b, const uint8_t* mask, int n, int c, int tmax,
+                   float* partial, float* out, void* cuda_stream);
+/* d/da and d/db of scale * sum|a - b|: grad_a = scale * sign(a - b), grad_b = -grad_a (either may be
+ * NULL); `scale` is a device scalar so that no host sync is needed. */
+int aas_l1_abs_grad(const float* a, const float* b, const uint8_t* mask, int n, int c, int tmax,
+                    const float* scale, float* grad_a, float* grad_b, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

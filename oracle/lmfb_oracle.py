@@ -375,6 +375,22 @@ def ctc_sizes(input_percentages: np.ndarray, t_out: int) -> np.ndarray:
     return (pct * np.float32(int(t_out))).astype(np.int32)
 
 
+def l1loss_mask(input, target, mask, fix_masking: bool = False):
+    """Speech_enhancement_by_AAS/model.py:19-31 restated: returns (loss, nElement).
+
+    The reference's ``err.masked_fill(mask, 0)`` is not in-place (a no-op), so padded frames
+    contribute; the divisor is the number of unmasked FRAMES ``numel(mask) - sum(mask)``.
+    ``fix_masking=True`` applies the mask for real (opt-in, not the reference's behaviour)."""
+    mask = np.asarray(mask)
+    if mask[0][0][0] != 0:
+        raise RuntimeError("nElement is undefined in the reference when mask[0][0][0] != 0")
+    n_element = mask.size - int(mask.sum())
+    err = np.abs(np.asarray(input, dtype=np.float64) - np.asarray(target, dtype=np.float64))
+    if fix_masking:
+        err = np.where(mask.astype(bool), 0.0, err)
+    return err.sum() / n_element, n_element
+
+
 def rel_err(a, b) -> float:
     """max|a-b| / max(|b|, rms(b)) elementwise (hard part 4)."""
     a = np.asarray(a, dtype=np.float64)

@@ -10,6 +10,7 @@ Fixtures written
                       autograd gradients w.r.t. both masks are stored.
   ref_glue_on_stft.npz  LIVE REFERENCE: the same tail fed with the oracle's STFT of a seeded wave,
                       so the CUDA path (STFT included) can be compared with the reference output.
+  ref_l1loss.npz      LIVE REFERENCE: L1Loss_mask (model.py:19-31) loss, nElement and gradients.
   ref_collate.npz     LIVE REFERENCE: _collate_fn / _collate_fn_paired outputs
                       (loader_functions.py:47-105) for a seeded ragged batch.
   ref_ctc_sizes.npz   LIVE torch semantics of trainer_AAS.py:165-167 on a grid of (T, Tmax, T').
@@ -119,6 +120,28 @@ def make_ref_glue_on_stft():
     sys.path.remove(REF)
 
 
+def make_ref_l1loss():
+    """LIVE REFERENCE: L1Loss_mask.forward (model.py:19-31) + autograd on a padded, length-sorted batch."""
+    sys.path.insert(0, REF)
+    import model as ref_model
+    rs = np.random.RandomState(99)
+    n, c, tmax = 4, 40, 37
+    lens = [37, 30, 22, 9]
+    a = torch.from_numpy(rs.randn(n, c, tmax).astype(np.float32)).requires_grad_(True)
+    b = torch.from_numpy(rs.randn(n, c, tmax).astype(np.float32)).requires_grad_(True)
+    mask = torch.zeros(n, 1, tmax, dtype=torch.uint8)
+    for i, l in enumerate(lens):
+        mask[i, :, l:] = 1
+    # torch >= 1.2 rejects the reference's ByteTensor mask inside masked_fill (model.py:29), so the
+    # reference is run with the same mask as bool; every other line executes unmodified
+    loss, n_element = ref_model.L1Loss_mask()(a, b, mask.bool())
+    (loss * 3.0).backward()
+    np.savez_compressed(os.path.join(HERE, "ref_l1loss.npz"), seed=99, lens=np.asarray(lens),
+                        loss=loss.detach().numpy(), n_element=int(n_element),
+                        grad_input=a.grad.numpy(), grad_target=b.grad.numpy(), upstream=3.0)
+    sys.path.remove(REF)
+
+
 def make_ref_collate():
     sys.path.insert(0, REF)
     import loader_functions as lf
@@ -187,6 +210,7 @@ def make_oracle_cases():
 if __name__ == "__main__":
     make_ref_glue()
     make_ref_glue_on_stft()
+    make_ref_l1loss()
     make_ref_collate()
     make_ref_ctc_sizes()
     make_oracle_cases()

@@ -20,7 +20,7 @@ def lib():
 def _declared_functions():
     text = open(os.path.join(ROOT, "include", "aas_lmfb.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(aas_lmfb_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(aas_(?:lmfb|l1)_[a-z_0-9]+)\s*\(", text)))
 
 
 def test_exports_match_header(lib):

@@ -325,3 +325,46 @@ def test_every_kernel_variant(be, warps, monkeypatch):
     b = _synth.make_batch(4, 11000, seed=33, ragged=True)
     for mm in ("reim", "power"):
         _check(be, b, mm, "per_bin")
+
+
+# ------------------------------------------------------------------ L1Loss_mask
+def test_l1loss_mask_against_live_reference(be):
+    g = np.load(os.path.join(GOLD, "ref_l1loss.npz"))
+    rs = np.random.RandomState(int(g["seed"]))
+    n, c, tmax = 4, 40, 37
+    a = torch.from_numpy(rs.randn(n, c, tmax).astype(np.float32)).cuda().requires_grad_(True)
+    b = torch.from_numpy(rs.randn(n, c, tmax).astype(np.float32)).cuda().requires_grad_(True)
+    mask = torch.zeros(n, 1, tmax, dtype=torch.uint8, device="cuda")
+    for i, l in enumerate(g["lens"]):
+        mask[i, :, int(l):] = 1
+    loss, n_element = be.L1Loss_mask()(a, b, mask)
+    (loss * float(g["upstream"])).backward()
+    assert int(n_element) == int(g["n_element"])                       # bit-exact count (frames)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    assert orc.rel_err(a.grad.cpu().numpy(), g["grad_input"]) < 1e-6
+    assert orc.rel_err(b.grad.cpu().numpy(), g["grad_target"]) < 1e-6
+    # deterministic
+    loss2, _ = be.L1Loss_mask()(a.detach(), b.detach(), mask)
+    assert float(loss2) == float(loss)
+    # opt-in fix of the reference's no-op masking
+    fixed, _ = be.L1Loss_mask(fix_masking=True)(a.detach(), b.detach(), mask)
+    ref_fixed, _ = orc.l1loss_mask(a.detach().cpu().numpy(), b.detach().cpu().numpy(), mask.cpu().numpy(), True)
+    assert abs(float(fixed) - ref_fixed) < 1e-5 * ref_fixed
+
+
+def test_l1loss_on_front_end_output_full_size(be):
+    """AAS G-step shape: L1 between two feature tensors of the CHiME-4-shaped batch."""
+    b = _synth.make_batch(30, 96000, seed=3, ragged=True)
+    fe = _fe(be, "reim", "per_bin")
+    wave, lengths, mr, mi = _dev(b, "reim")
+    z, fl = fe(wave, lengths, mr, mi)
+    target = torch.randn_like(z)
+    mask = torch.zeros(30, 1, b["tmax"], dtype=torch.uint8, device="cuda")
+    for i in range(30):
+        mask[i, :, int(fl[i]):] = 1
+    loss, n_element = be.L1Loss_mask()(z, target, mask)
+    loss.backward()
+    want, want_n = orc.l1loss_mask(z.detach().cpu().numpy(), target.cpu().numpy(), mask.cpu().numpy())
+    assert int(n_element) == want_n
+    assert abs(float(loss) - want) < 1e-5 * want
+    assert mr.grad is not None and torch.isfinite(mr.grad).all()

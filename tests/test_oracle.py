@@ -184,3 +184,28 @@ def test_live_reference_collate_when_mounted():
     mine = orc.collate(batch)
     for a, b in zip(mine, ref):
         assert np.array_equal(a, b.numpy())
+
+
+def _l1_batch():
+    g = _load("ref_l1loss.npz")
+    rs = np.random.RandomState(int(g["seed"]))
+    n, c, tmax = 4, 40, 37
+    a = rs.randn(n, c, tmax).astype(np.float32)
+    b = rs.randn(n, c, tmax).astype(np.float32)
+    mask = np.zeros((n, 1, tmax), dtype=np.uint8)
+    for i, l in enumerate(g["lens"]):
+        mask[i, :, l:] = 1
+    return g, a, b, mask
+
+
+def test_l1loss_mask_matches_live_reference_fixture():
+    g, a, b, mask = _l1_batch()
+    loss, n_element = orc.l1loss_mask(a, b, mask)
+    assert n_element == int(g["n_element"]) == 37 + 30 + 22 + 9      # frames, not elements
+    assert abs(loss - float(g["loss"])) < 2e-6 * abs(float(g["loss"]))
+    # the no-op masked_fill: padded frames contribute (fixing it changes the value)
+    fixed, _ = orc.l1loss_mask(a, b, mask, fix_masking=True)
+    assert fixed < loss
+    with pytest.raises(RuntimeError):
+        bad = mask.copy(); bad[0, 0, 0] = 1
+        orc.l1loss_mask(a, b, bad)
