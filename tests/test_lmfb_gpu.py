@@ -340,7 +340,7 @@ def test_l1loss_mask_against_live_reference(be):
     loss, n_element = be.L1Loss_mask()(a, b, mask)
     (loss * float(g["upstream"])).backward()
     assert int(n_element) == int(g["n_element"])                       # bit-exact count (frames)
-    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
     assert orc.rel_err(a.grad.cpu().numpy(), g["grad_input"]) < 1e-6
     assert orc.rel_err(b.grad.cpu().numpy(), g["grad_target"]) < 1e-6
     # deterministic
@@ -366,5 +366,5 @@ def test_l1loss_on_front_end_output_full_size(be):
     loss.backward()
     want, want_n = orc.l1loss_mask(z.detach().cpu().numpy(), target.cpu().numpy(), mask.cpu().numpy())
     assert int(n_element) == want_n
-    assert abs(float(loss) - want) < 1e-5 * want
+    assert abs(loss.item() - want) < 1e-5 * want
     assert mr.grad is not None and torch.isfinite(mr.grad).all()
