@@ -304,6 +304,46 @@ LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __res
     }
 }
 
+// Variant used where registers allow (one-wave launches: 4 warps at 128 registers, 2 warps at
+// 168): all 33 rows are dealt in contiguous shares and a warp issues every load of its share (or
+// half of it) before the first store, so that staging costs one or two memory round trips instead
+// of one per leftover row.  Matters most when a launch is a single wave and nothing else hides
+// the DRAM latency.
+template <int W>
+LMFB_HD void stage_tile_batched(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row,
+                                int len, int t0, float2* __restrict__ S, bool vec_ok) {
+    constexpr int kShare = (kTile + 1 + W - 1) / W;               // rows per warp
+    constexpr int kBatch = kShare <= 9 ? kShare : (kShare + 1) / 2;
+    const int r_lo = w * kShare;
+    const int r_hi = r_lo + kShare < kTile + 1 ? r_lo + kShare : kTile + 1;
+#pragma unroll 1
+    for (int r0 = r_lo; r0 < r_hi; r0 += kBatch) {
+        const int r1 = r0 + kBatch < r_hi ? r0 + kBatch : r_hi;
+        if (!rows_interior(t0 + r0 - 1, t0 + r1 - 1, len, vec_ok)) {
+            stage_rows_slow(lane, sl, wave_row, len, t0, S, r0, r1);
+            continue;
+        }
+        const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r0 - 1) * kHop) + lane;
+        float2 v[kBatch][3];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            if (r0 + i < r1) {                                    // warp-uniform
+                v[i][0] = LMFB_LDG(src + i * 80);
+                v[i][1] = LMFB_LDG(src + i * 80 + 32);
+                if (lane < 16) v[i][2] = LMFB_LDG(src + i * 80 + 64);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            if (r0 + i < r1) {
+                stage_store(sl, S, r0 + i, 0, v[i][0]);
+                stage_store(sl, S, r0 + i, 1, v[i][1]);
+                if (lane < 16) stage_store(sl, S, r0 + i, 2, v[i][2]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // pass 1: the five in-register 32-point FFTs of a column, dealt round-robin to the W warps
 // ---------------------------------------------------------------------------------------

@@ -47,7 +47,7 @@ struct K1Args {
 
 constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
 
-template <int MASK, bool BWD, int W, int CTAS, bool DSMEM>
+template <int MASK, bool BWD, int W, int CTAS, bool DSMEM, bool BATCH>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     extern __shared__ __align__(16) float2 S[];
@@ -144,7 +144,8 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
 #pragma unroll 4
             for (int m = w; m < n_mels; m += W) dEs[m * kTile + lane] = LMFB_LDG(src + (unsigned)m * som);
         }
-        stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
+        if (BATCH) stage_tile_batched<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
+        else       stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
         LMFB_TICK(1);
         __syncthreads();
         LMFB_TICK(2);
@@ -417,18 +418,20 @@ typedef void (*k1_fn)(const K1Args, const MelBand);
 
 struct K1Variant { int warps, ctas, dsmem; k1_fn fwd[3], bwd[3]; };   // indexed by mask mode
 
-#define LMFB_VARIANT(W, C, D)                                                                    \
-    { W, C, D,                                                                                   \
-      { (k1_fn)lmfb_k1<kMaskNone, false, W, C, D>, (k1_fn)lmfb_k1<kMaskReim, false, W, C, D>,    \
-        (k1_fn)lmfb_k1<kMaskPower, false, W, C, D> },                                            \
-      { nullptr, (k1_fn)lmfb_k1<kMaskReim, true, W, C, D>, (k1_fn)lmfb_k1<kMaskPower, true, W, C, D> } }
+#define LMFB_VARIANT(W, C, D, B)                                                                       \
+    { W, C, D,                                                                                         \
+      { (k1_fn)lmfb_k1<kMaskNone, false, W, C, D, B>, (k1_fn)lmfb_k1<kMaskReim, false, W, C, D, B>,    \
+        (k1_fn)lmfb_k1<kMaskPower, false, W, C, D, B> },                                               \
+      { nullptr, (k1_fn)lmfb_k1<kMaskReim, true, W, C, D, B>, (k1_fn)lmfb_k1<kMaskPower, true, W, C, D, B> } }
 
 // (warps per tile, resident CTAs per SM the register budget is sized for, dE tile staged in smem)
 static const K1Variant kVariants[] = {
-    LMFB_VARIANT(4, 5, false), LMFB_VARIANT(2, 5, false), LMFB_VARIANT(3, 5, false),
-    LMFB_VARIANT(5, 4, false), LMFB_VARIANT(1, 5, false), LMFB_VARIANT(4, 4, true),
-    LMFB_VARIANT(4, 4, false),
+    LMFB_VARIANT(4, 5, false, false), LMFB_VARIANT(2, 5, false, false), LMFB_VARIANT(3, 5, false, false),
+    LMFB_VARIANT(5, 4, false, false), LMFB_VARIANT(1, 5, false, false), LMFB_VARIANT(4, 4, true, false),
+    LMFB_VARIANT(4, 4, false, false),
+    LMFB_VARIANT(4, 4, false, true),  LMFB_VARIANT(2, 5, false, true),          // batched staging
 };
+constexpr int kVariant44Batched = 7, kVariant2Batched = 8;
 constexpr int kVariantDsmem = 5;
 constexpr int kVariant44 = 6;
 // Defaults measured on B200 (profiles/): in the throughput regime (more tiles than resident CTAs)
@@ -445,8 +448,10 @@ static int pick_variant(const char* env, int dflt) {
         const int wanted = atoi(v);
         if (wanted == 44) return kVariantDsmem;
         if (wanted == 40) return kVariant44;           // 4 warps, register budget for 4 CTAs/SM
+        if (wanted == 41) return kVariant44Batched;    // ... with batched staging
+        if (wanted == 21) return kVariant2Batched;     // 2 warps with batched staging
         for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
-            if (kVariants[i].warps == wanted && kVariants[i].ctas == (wanted == 5 ? 4 : 5) && !kVariants[i].dsmem) return (int)i;
+            if (kVariants[i].warps == wanted && kVariants[i].ctas == (wanted == 5 ? 4 : 5) && !kVariants[i].dsmem) return (int)i;   // first match: unbatched
     }
     return dflt;
 }
