@@ -237,16 +237,32 @@ LMFB_HD void stage_rows_slow(int lane, const StageLane& sl, const float* __restr
     }
 }
 
-// hop-row r feeds frame r (first half, r < 32) and frame r-1 (second half, r >= 1).  The 31 rows
-// 1..31 feed two frames each and are dealt to the warps in equal shares, loaded in one batch per
-// warp without any per-row predicate; rows 0 and 32 (one frame each) go to warps 0 and W-1.
+// zero-fill of hop-rows that feed no valid frame (beyond the utterance's last frame): no loads
+LMFB_HD void stage_rows_zero(int lane, const StageLane& sl, float2* __restrict__ S, int r_lo, int r_hi) {
+    const float2 z = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+    for (int r = r_lo; r < r_hi; ++r) {
+        stage_store(sl, S, r, 0, z);
+        stage_store(sl, S, r, 1, z);
+        if (lane < 16) stage_store(sl, S, r, 2, z);
+    }
+}
+
+// hop-row r feeds frame r (first half, r < 32) and frame r-1 (second half, r >= 1).  Only rows
+// 0 .. n_rows-1 feed a frame that exists (n_rows = valid frames of the tile + 1); the others are
+// zero-filled without touching global memory -- in the last tile of an utterance that is most of
+// them, and they would otherwise all take the per-sample reflect path.  The 31 rows 1..31 feed two
+// frames each and are dealt to the warps in equal shares, loaded in batches without any per-row
+// predicate; rows 0 and 32 (one frame each) go to warps 0 and W-1.
 template <int W>
 LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
-                        int t0, float2* __restrict__ S, bool vec_ok) {
+                        int t0, int n_rows, float2* __restrict__ S, bool vec_ok) {
     constexpr int kShare = (kTile - 1 + W - 1) / W;               // rows per warp (last warp may have fewer)
     constexpr int kBatch = kShare <= 8 ? kShare : 8;
     const int r_lo = 1 + w * kShare;
-    const int r_hi = r_lo + kShare < kTile ? r_lo + kShare : kTile;
+    const int r_end = r_lo + kShare < kTile ? r_lo + kShare : kTile;
+    const int r_hi = r_end < n_rows ? r_end : n_rows;             // rows that need real samples
+    if (r_hi < r_end) stage_rows_zero(lane, sl, S, r_hi > r_lo ? r_hi : r_lo, r_end);
 #pragma unroll 1
     for (int r0 = r_lo; r0 < r_hi; r0 += kBatch) {
         const int r1 = r0 + kBatch < r_hi ? r0 + kBatch : r_hi;
@@ -292,7 +308,9 @@ LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __res
     if (W == 1 || r_edge >= 0) {
 #pragma unroll 1
         for (int r = (W == 1 ? 0 : r_edge); r <= (W == 1 ? kTile : r_edge); r += kTile) {
-            if (!rows_interior(t0 + r - 1, t0 + r, len, vec_ok)) {
+            if (r >= n_rows) {
+                stage_rows_zero(lane, sl, S, r, r + 1);
+            } else if (!rows_interior(t0 + r - 1, t0 + r, len, vec_ok)) {
                 stage_rows_slow(lane, sl, wave_row, len, t0, S, r, r + 1);
             } else {
                 const float2* s2 = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r - 1) * kHop) + lane;
@@ -311,23 +329,21 @@ LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __res
 // the DRAM latency.
 template <int W>
 LMFB_HD void stage_tile_batched(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row,
-                                int len, int t0, float2* __restrict__ S, bool vec_ok) {
+                                int len, int t0, int n_rows, float2* __restrict__ S, bool vec_ok) {
     constexpr int kShare = (kTile + 1 + W - 1) / W;               // rows per warp
     constexpr int kBatch = kShare <= 9 ? kShare : (kShare + 1) / 2;
     const int r_lo = w * kShare;
     const int r_hi = r_lo + kShare < kTile + 1 ? r_lo + kShare : kTile + 1;
 #pragma unroll 1
     for (int r0 = r_lo; r0 < r_hi; r0 += kBatch) {
-        const int r1 = r0 + kBatch < r_hi ? r0 + kBatch : r_hi;
-        if (!rows_interior(t0 + r0 - 1, t0 + r1 - 1, len, vec_ok)) {
-            stage_rows_slow(lane, sl, wave_row, len, t0, S, r0, r1);
-            continue;
-        }
         const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r0 - 1) * kHop) + lane;
         float2 v[kBatch][3];
+        // per row (all warp-uniform): 0 = not mine, 1 = zero-fill, 2 = vector loads, 3 = reflect path
 #pragma unroll
         for (int i = 0; i < kBatch; ++i) {
-            if (r0 + i < r1) {                                    // warp-uniform
+            const int r = r0 + i;
+            const bool fast = r < r_hi && r < n_rows && rows_interior(t0 + r - 1, t0 + r, len, vec_ok);
+            if (fast) {
                 v[i][0] = LMFB_LDG(src + i * 80);
                 v[i][1] = LMFB_LDG(src + i * 80 + 32);
                 if (lane < 16) v[i][2] = LMFB_LDG(src + i * 80 + 64);
@@ -335,10 +351,16 @@ LMFB_HD void stage_tile_batched(int w, int lane, const StageLane& sl, const floa
         }
 #pragma unroll
         for (int i = 0; i < kBatch; ++i) {
-            if (r0 + i < r1) {
-                stage_store(sl, S, r0 + i, 0, v[i][0]);
-                stage_store(sl, S, r0 + i, 1, v[i][1]);
-                if (lane < 16) stage_store(sl, S, r0 + i, 2, v[i][2]);
+            const int r = r0 + i;
+            if (r >= r_hi) continue;
+            if (r >= n_rows) {
+                stage_rows_zero(lane, sl, S, r, r + 1);
+            } else if (rows_interior(t0 + r - 1, t0 + r, len, vec_ok)) {
+                stage_store(sl, S, r, 0, v[i][0]);
+                stage_store(sl, S, r, 1, v[i][1]);
+                if (lane < 16) stage_store(sl, S, r, 2, v[i][2]);
+            } else {
+                stage_rows_slow(lane, sl, wave_row, len, t0, S, r, r + 1);
             }
         }
     }

@@ -144,8 +144,9 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
 #pragma unroll 4
             for (int m = w; m < n_mels; m += W) dEs[m * kTile + lane] = LMFB_LDG(src + (unsigned)m * som);
         }
-        if (BATCH) stage_tile_batched<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
-        else       stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, S, a.vec_ok != 0);
+        const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;          // hop-rows that feed a valid frame
+        if (BATCH) stage_tile_batched<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
+        else       stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
         LMFB_TICK(1);
         __syncthreads();
         LMFB_TICK(2);

@@ -22,7 +22,9 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
         for (int lane = 0; lane < 32; ++lane) {
             StageLane sl;
             stage_lane_init(lane, window, sl);
-            stage_tile<W>(w, lane, sl, wave_row, len, t0, S.data(), vec_ok);
+            const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;
+            if (W == 2 || W == 4) stage_tile_batched<W>(w, lane, sl, wave_row, len, t0, n_rows, S.data(), vec_ok);
+            else                  stage_tile<W>(w, lane, sl, wave_row, len, t0, n_rows, S.data(), vec_ok);
         }
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) fft_pass1<W>(w, S.data() + lane);
