@@ -218,22 +218,19 @@ LMFB_HD void stage_rows_slow(int lane, const StageLane& sl, const float* __restr
 #pragma unroll 1
     for (int r = r_lo; r < r_hi; ++r) {
         const int base = (t0 + r - 1) * kHop;
-#pragma unroll 1
-        for (int q = 0; q < 3; ++q) {
+        float2 v[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {                      // all six loads in flight before the stores
             const int c = lane + 32 * q;
-            if (c >= 80) continue;
-            float2 v;
-            v.x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
-            v.y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
-            const int sa = q == 0 ? sl.slot_a[0] : (q == 1 ? sl.slot_a[1] : sl.slot_a[2]);
-            const int sb = q == 0 ? sl.slot_b[0] : (q == 1 ? sl.slot_b[1] : sl.slot_b[2]);
-            const float wa0 = q == 0 ? sl.wa0[0] : (q == 1 ? sl.wa0[1] : sl.wa0[2]);
-            const float wa1 = q == 0 ? sl.wa1[0] : (q == 1 ? sl.wa1[1] : sl.wa1[2]);
-            const float wb0 = q == 0 ? sl.wb0[0] : (q == 1 ? sl.wb0[1] : sl.wb0[2]);
-            const float wb1 = q == 0 ? sl.wb1[0] : (q == 1 ? sl.wb1[1] : sl.wb1[2]);
-            if (r < kTile)  S[sa + r]     = make_float2(v.x * wa0, v.y * wa1);
-            if (r >= 1)     S[sb + r - 1] = make_float2(v.x * wb0, v.y * wb1);
+            v[q] = make_float2(0.0f, 0.0f);
+            if (c < 80) {
+                v[q].x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
+                v[q].y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
+            }
         }
+        stage_store(sl, S, r, 0, v[0]);
+        stage_store(sl, S, r, 1, v[1]);
+        if (lane < 16) stage_store(sl, S, r, 2, v[2]);
     }
 }
 

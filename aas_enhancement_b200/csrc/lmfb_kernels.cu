@@ -437,10 +437,9 @@ constexpr int kVariantDsmem = 5;
 constexpr int kVariant44 = 6;
 // Defaults measured on B200 (profiles/): in the throughput regime (more tiles than resident CTAs)
 // 3 warps per tile win for both directions (128 registers, no spills); in the latency regime (a
-// launch that does not fill the resident slots, e.g. 30 x 6 s) the forward prefers 4 warps with
-// the register budget of 4 CTAs/SM (128 registers) and the backward 2 warps (168 registers):
-// nothing spilled, shortest per-tile critical path.
-constexpr int kFwdVariantBig = 2, kFwdVariantSmall = 6;
+// launch that does not fill the resident slots, e.g. 30 x 6 s) the backward prefers 2 warps (168
+// registers, nothing spilled, shortest per-tile critical path); the forward stays at 3.
+constexpr int kFwdVariantBig = 2, kFwdVariantSmall = 2;
 constexpr int kBwdVariantBig = 2, kBwdVariantSmall = 1;
 
 static int pick_variant(const char* env, int dflt) {
