@@ -98,7 +98,6 @@ struct Tables {
     float    ssin[88], scos[88];  // real-split twiddles [k2*5 + k1]
     uint8_t  binof[88];           // bin produced by pass-2 step k2, output k1 [k2*5 + k1]
     uint8_t  fend[kMaxMels];
-    uint8_t  mlb[kBins + 3];      // lower filter ml(f) of every bin (n_mels above the last filter)
     uint8_t  mbeg[kMaxW + 1];
     uint8_t  pad_[3];
     int      n_mels;
@@ -108,26 +107,40 @@ struct Tables {
 constexpr int kTablesBytes = (int)((sizeof(Tables) + 15) / 16 * 16);
 constexpr int kSmemBytes = kScratchBytes + kTablesBytes;
 
-// cooperative copy: thread `tid` of `nthreads`
-LMFB_HD void tables_fill(Tables* tb, const MelBand& mb, uint32_t msf_bytes, int tid, int nthreads) {
-    for (int f = tid; f < kBins; f += nthreads) {
+// Cooperative copy, once per persistent CTA.  The source lives in constant banks (kernel
+// parameters and __constant__ tables), which only serve a warp quickly when all lanes read the
+// SAME address: every warp therefore walks a contiguous share of the entries with a warp-uniform
+// index and all lanes store the same value (a benign broadcast store).  A lane-indexed copy costs
+// ~5 us per CTA (32-way serialised constant reads); this one well under 1 us.
+LMFB_HD void tables_fill(Tables* tb, const MelBand& mb, uint32_t msf_bytes, int warp, int nwarps) {
+    const int per = (kBins + nwarps - 1) / nwarps;
+    const int f0 = warp * per, f1 = f0 + per < kBins ? f0 + per : kBins;
+#pragma unroll 4
+    for (int f = f0; f < f1; ++f) {
         tb->wl[f] = mb.ent[f].wl;
         tb->wh[f] = mb.ent[f].wh;
         tb->off[f] = mb.ent[f].off;
     }
-    for (int i = tid; i < 85; i += nthreads) {
-        tb->ssin[i] = kSplitSin[i / 5][i % 5];
-        tb->scos[i] = kSplitCos[i / 5][i % 5];
-        tb->binof[i] = kBinOf[i / 5][i % 5];
+    const int per2 = (85 + nwarps - 1) / nwarps;
+    const int i0 = warp * per2, i1 = i0 + per2 < 85 ? i0 + per2 : 85;
+    int k2 = i0 / 5, k1 = i0 - 5 * k2;
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) {
+        tb->ssin[i] = kSplitSin[k2][k1];
+        tb->scos[i] = kSplitCos[k2][k1];
+        tb->binof[i] = kBinOf[k2][k1];
+        if (++k1 == 5) { k1 = 0; ++k2; }
     }
-    for (int m = tid; m < kMaxMels; m += nthreads) tb->fend[m] = mb.fend[m];
-    for (int f = tid; f < kBins; f += nthreads) {
-        int c = 0;                                   // ml(f) = number of filters that end at or before f
-        for (int m = 0; m < mb.n_mels; ++m) c += (mb.fend[m] <= f) ? 1 : 0;
-        tb->mlb[f] = (uint8_t)c;
+    const int per3 = (kMaxMels + nwarps - 1) / nwarps;
+    const int m0 = warp * per3, m1 = m0 + per3 < kMaxMels ? m0 + per3 : kMaxMels;
+#pragma unroll 4
+    for (int m = m0; m < m1; ++m) tb->fend[m] = mb.fend[m];
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i <= kMaxW; ++i) tb->mbeg[i] = mb.mbeg[i];
+        tb->n_mels = mb.n_mels;
+        tb->msf_bytes = msf_bytes;
     }
-    for (int i = tid; i <= kMaxW; i += nthreads) tb->mbeg[i] = mb.mbeg[i];
-    if (tid == 0) { tb->n_mels = mb.n_mels; tb->msf_bytes = msf_bytes; }
 }
 
 LMFB_HD int slot_of_packed(int j) {            // j in [0,160): packed-sample index -> PFA input slot

@@ -51,12 +51,16 @@ template <int MASK, bool BWD, int W, int CTAS, bool DSMEM, bool BATCH>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     extern __shared__ __align__(16) float2 S[];
+#ifdef LMFB_TIMELINE
+    unsigned long long gt_entry;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_entry));
+#endif
     Tables& tb = *reinterpret_cast<Tables*>(reinterpret_cast<char*>(S) + kScratchBytes);
     float* dEs = reinterpret_cast<float*>(reinterpret_cast<char*>(S) + kSmemBytes);   // DSMEM: [n_mels][32]
     const int lane = threadIdx.x & 31;
     const int w    = threadIdx.x >> 5;
     const int n_mels = mb.n_mels;
-    tables_fill(&tb, mb, a.msf * 4u, threadIdx.x, kTile * W);   // visible after the first block barrier
+    tables_fill(&tb, mb, a.msf * 4u, w, W);                    // visible after the first block barrier
     StageLane sl;
     stage_lane_init(lane, a.window, sl);
     float2* col = S + lane;
@@ -137,6 +141,10 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
 #define LMFB_TICK(i) ((void)0)
 #endif
         LMFB_TICK(0);
+#ifdef LMFB_TIMELINE
+        unsigned long long gt_tile0 = 0;
+        if (tile == (int)blockIdx.x) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_tile0));
+#endif
         // loads of out-of-row lanes are redirected to the last column of the row (always readable)
         const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
         if (BWD && DSMEM) {                         // this tile's dE rows -> shared memory, lanes along T
@@ -186,6 +194,16 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         if (a.timeline && lane == 0 && blockIdx.x < 64 && tile < (int)gridDim.x * 8) {
             long long* dst = a.timeline + ((long long)(tile / gridDim.x) * 64 + blockIdx.x) * (W * 8) + w * 8;
             for (int i = 0; i < 8; ++i) dst[i] = tl[i];
+        }
+        // second view: every CTA's first tile, stamped with the global nanosecond timer
+        if (a.timeline && lane == 0 && w == 0 && tile == (int)blockIdx.x && blockIdx.x < 1024) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+            long long* dst = a.timeline + 8 * 64 * 8 * 8 + (long long)blockIdx.x * 4;
+            dst[0] = (long long)gt;                 // end of the tile (ns)
+            dst[1] = tl[7] - tl[0];                 // tile duration (cycles)
+            dst[2] = (long long)gt_entry;           // kernel entry of this CTA (ns)
+            dst[3] = (long long)gt_tile0;           // start of its first tile, after the prologue (ns)
         }
 #endif
     }

@@ -19,8 +19,8 @@ n, samples = (256, 160000) if wl == "sweep" else (30, 96000)
 tmax = 1 + samples // 160
 dev = torch.device("cuda", 0)
 W = int(os.environ.get("TL_W", "3"))
-buf_f = torch.zeros(8 * 64 * 8 * 8, dtype=torch.int64, device=dev)
-buf_b = torch.zeros(8 * 64 * 8 * 8, dtype=torch.int64, device=dev)
+buf_f = torch.zeros(8 * 64 * 8 * 8 + 4096, dtype=torch.int64, device=dev)
+buf_b = torch.zeros(8 * 64 * 8 * 8 + 4096, dtype=torch.int64, device=dev)
 os.environ["AAS_LMFB_TIMELINE_FWD"] = str(buf_f.data_ptr())
 os.environ["AAS_LMFB_TIMELINE_BWD"] = str(buf_b.data_ptr())
 os.environ["AAS_LMFB_WARPS_FWD"] = str(W)
@@ -36,7 +36,16 @@ for _ in range(3):
 torch.cuda.synchronize()
 names = ["stage", "wait1", "pass1+ld", "wait2", "pass2*", "p3A(neg)", "p3B*"]  # fwd: tl5 = phase-3 mid stamp
 for label, buf in (("fwd", buf_f), ("bwd", buf_b)):
-    t = buf.cpu().view(8, 64, -1)[:, :, :W * 8].reshape(8, 64, W, 8).double()
+    first = buf.cpu()[8 * 64 * 8 * 8:].view(1024, 4)
+    fv = first[first[:, 0] > 0]
+    if fv.numel():
+        end_ns = fv[:, 0].double(); dur = fv[:, 1].double()
+        print(label, 'first tile of each CTA: n=%d  duration cycles mean %.0f max %.0f  | end-time spread %.1f us' % (len(fv), dur.mean(), dur.max(), (end_ns.max() - end_ns.min()) / 1e3))
+        entry = fv[:, 2].double(); tile0 = fv[:, 3].double()
+        k0 = entry.min()
+        print('   ns from first CTA entry: entry mean %.0f max %.0f | prologue (entry->tile start) mean %.0f max %.0f | tile end mean %.0f max %.0f'
+              % ((entry - k0).mean(), (entry - k0).max(), (tile0 - entry).mean(), (tile0 - entry).max(), (end_ns - k0).mean(), (end_ns - k0).max()))
+    t = buf.cpu()[:8 * 64 * 8 * 8].view(8, 64, -1)[:, :, :W * 8].reshape(8, 64, W, 8).double()
     valid = t[..., 7] > 0
     d = t[..., 1:] - t[..., :-1]
     print(label, "cycles per phase, mean over", int(valid.sum()), "warp-tiles; per warp index")
