@@ -61,8 +61,15 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     const int w    = threadIdx.x >> 5;
     const int n_mels = mb.n_mels;
     tables_fill(&tb, mb, a.msf * 4u, w, W);                    // visible after the first block barrier
+#ifdef LMFB_TIMELINE
+    unsigned long long gt_p1, gt_p2;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_p1));
+#endif
     StageLane sl;
     stage_lane_init(lane, a.window, sl);
+#ifdef LMFB_TIMELINE
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_p2) : "f"(sl.wb1[2]));
+#endif
     float2* col = S + lane;
 
     // CTAs that start together would run their phases in lockstep (all staging, then all FFT, ...)
@@ -201,7 +208,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
             long long* dst = a.timeline + 8 * 64 * 8 * 8 + (long long)blockIdx.x * 4;
             dst[0] = (long long)gt;                 // end of the tile (ns)
-            dst[1] = tl[7] - tl[0];                 // tile duration (cycles)
+            dst[1] = ((long long)(gt_p1 - gt_entry) << 32) | (long long)(gt_p2 - gt_p1);   // prologue split (ns)
             dst[2] = (long long)gt_entry;           // kernel entry of this CTA (ns)
             dst[3] = (long long)gt_tile0;           // start of its first tile, after the prologue (ns)
         }

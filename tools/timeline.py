@@ -39,8 +39,8 @@ for label, buf in (("fwd", buf_f), ("bwd", buf_b)):
     first = buf.cpu()[8 * 64 * 8 * 8:].view(1024, 4)
     fv = first[first[:, 0] > 0]
     if fv.numel():
-        end_ns = fv[:, 0].double(); dur = fv[:, 1].double()
-        print(label, 'first tile of each CTA: n=%d  duration cycles mean %.0f max %.0f  | end-time spread %.1f us' % (len(fv), dur.mean(), dur.max(), (end_ns.max() - end_ns.min()) / 1e3))
+        end_ns = fv[:, 0].double(); dur = (fv[:, 1] >> 32).double(); dur2 = (fv[:, 1] & 0xffffffff).double()
+        print(label, 'first tile of each CTA: n=%d  tables_fill ns mean %.0f max %.0f | stage_lane_init ns mean %.0f max %.0f | end-time spread %.1f us' % (len(fv), dur.mean(), dur.max(), dur2.mean(), dur2.max(), (end_ns.max() - end_ns.min()) / 1e3))
         entry = fv[:, 2].double(); tile0 = fv[:, 3].double()
         k0 = entry.min()
         print('   ns from first CTA entry: entry mean %.0f max %.0f | prologue (entry->tile start) mean %.0f max %.0f | tile end mean %.0f max %.0f'
