@@ -13,8 +13,8 @@
 //
 // Real FFT of 320 samples = complex FFT of the 160 packed samples z[j] = x[2j] + i x[2j+1],
 // computed with the Good-Thomas prime-factor map 160 = 5 x 32 (no inter-stage twiddles):
-//   stage  : windowed samples -> private columns, permuted into PFA input order
-//   pass 1 : five 32-point FFTs in registers (generated codelet), in place in the scratch
+//   stage  : raw samples -> private columns, permuted into PFA input order (asynchronous copies)
+//   pass 1 : window, then five 32-point FFTs in registers (generated codelet), in place
 //   pass 2 : for each index pair (k2, 32-k2): two 5-point DFTs + the real-split butterfly give
 //            ten bins; the mask(s) for those ten bins (prefetched one step ahead into
 //            registers, lanes along T) are applied at once.  Forward: the masked power replaces
@@ -189,189 +189,105 @@ static inline void sts_if_noalias(float* p, float v, bool pred) { if (pred) *p =
 #endif
 
 // ---------------------------------------------------------------------------------------
-// Staging: copy the (32+1)*160 samples a tile needs into the 32 frame columns, windowed and
-// permuted into PFA input order.  Lanes run along the packed-sample index, so global reads are
-// coalesced 256-byte runs and the scratch writes are conflict-free.  The 33 hop-rows are split
-// between the W warps; each warp loads its rows in one or two batches (<= 27 independent 8-byte
-// loads in flight per lane).
+// Staging: the (32+1)*160 samples a tile needs go STRAIGHT from global memory into the 32 frame
+// columns with 8-byte asynchronous copies (cp.async / LDGSTS): no register round trip, every
+// copy of the tile in flight at once, one exposed memory round trip per tile instead of one per
+// load batch.  The samples land RAW and in PFA input order; the window is applied by pass 1 when
+// it loads them (the window table lives in the pad column of the scratch, window_fill()).
+// Lanes run along the packed-sample index of a hop-row, so the global side is a coalesced
+// 256-byte run and the shared side is conflict-free (slot pitch 33).  Hop-row r feeds frame r
+// (first half, r < 32) and frame r-1 (second half, r >= 1): two copies of the same 8 bytes, the
+// second of which hits L1.
 // ---------------------------------------------------------------------------------------
-struct StageLane {                      // per-lane constants of the staging map
-    int   slot_a[3], slot_b[3];
-    float wa0[3], wa1[3], wb0[3], wb1[3];
+#ifdef __CUDACC__
+__device__ __forceinline__ void cp_async8(float2* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
+                 :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+#else
+static inline void cp_async8(float2* dst, const float* src) { dst->x = src[0]; dst->y = src[1]; }
+static inline void cp_async_wait_all() {}
+#endif
+
+struct StageLane {                      // per-lane constants of the staging map (float2 index of slot * pitch)
+    int slot_a[3], slot_b[3];
 };
 
-LMFB_HD void stage_lane_init(int lane, const float* __restrict__ window, StageLane& sl) {
+LMFB_HD void stage_lane_init(int lane, StageLane& sl) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         const int c = lane + 32 * q;                       // packed index inside a hop-row, < 80 valid
         const int cc = c < 80 ? c : 0;
         sl.slot_a[q] = slot_of_packed(cc) * kPitch;
         sl.slot_b[q] = slot_of_packed(cc + 80) * kPitch;
-        sl.wa0[q] = LMFB_LDG(window + 2 * cc);
-        sl.wa1[q] = LMFB_LDG(window + 2 * cc + 1);
-        sl.wb0[q] = LMFB_LDG(window + 2 * cc + kHop);
-        sl.wb1[q] = LMFB_LDG(window + 2 * cc + kHop + 1);
     }
 }
 
-// rows [row_lo, row_hi) of the unpadded signal lie fully inside [0, len) and can be read as float2
-LMFB_HD bool rows_interior(int row_lo, int row_hi, int len, bool vec_ok) {
-    return vec_ok && row_lo >= 0 && (long long)row_hi * kHop <= (long long)len;
+// window table: pad column (index 32) of slot s holds the window pair of the packed sample that
+// lives in slot s.  Written once per persistent CTA; staging and the passes never touch column 32.
+LMFB_HD void window_fill(float2* __restrict__ S, const float* __restrict__ window, int idx, int cnt) {
+    for (int j = idx; j < kSlots; j += cnt)
+        S[slot_of_packed(j) * kPitch + kTile] = make_float2(LMFB_LDG(window + 2 * j), LMFB_LDG(window + 2 * j + 1));
+}
+
+// hop-row q of the unpadded signal lies fully inside [0, len) and can be copied as 8-byte pieces
+LMFB_HD bool row_interior(int q, int len, bool vec_ok) {
+    return vec_ok && q >= 0 && (long long)(q + 1) * kHop <= (long long)len;
 }
 
 LMFB_HD void stage_store(const StageLane& sl, float2* __restrict__ S, int r, int q, float2 v) {
-    if (r < kTile)  S[sl.slot_a[q] + r]     = make_float2(v.x * sl.wa0[q], v.y * sl.wa1[q]);
-    if (r >= 1)     S[sl.slot_b[q] + r - 1] = make_float2(v.x * sl.wb0[q], v.y * sl.wb1[q]);
+    if (r < kTile)  S[sl.slot_a[q] + r]     = v;
+    if (r >= 1)     S[sl.slot_b[q] + r - 1] = v;
 }
 
-// edge rows (reflect padding at either end of the utterance, or an unaligned wave): one
-// element at a time, rolled -- only boundary tiles ever come here
-LMFB_HD void stage_rows_slow(int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
-                             int t0, float2* __restrict__ S, int r_lo, int r_hi) {
-#pragma unroll 1
-    for (int r = r_lo; r < r_hi; ++r) {
-        const int base = (t0 + r - 1) * kHop;
-        float2 v[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {                      // all six loads in flight before the stores
-            const int c = lane + 32 * q;
-            v[q] = make_float2(0.0f, 0.0f);
-            if (c < 80) {
-                v[q].x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
-                v[q].y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
-            }
-        }
-        stage_store(sl, S, r, 0, v[0]);
-        stage_store(sl, S, r, 1, v[1]);
-        if (lane < 16) stage_store(sl, S, r, 2, v[2]);
-    }
-}
-
-// zero-fill of hop-rows that feed no valid frame (beyond the utterance's last frame): no loads
-LMFB_HD void stage_rows_zero(int lane, const StageLane& sl, float2* __restrict__ S, int r_lo, int r_hi) {
-    const float2 z = make_float2(0.0f, 0.0f);
-#pragma unroll 1
-    for (int r = r_lo; r < r_hi; ++r) {
-        stage_store(sl, S, r, 0, z);
-        stage_store(sl, S, r, 1, z);
-        if (lane < 16) stage_store(sl, S, r, 2, z);
-    }
-}
-
-// hop-row r feeds frame r (first half, r < 32) and frame r-1 (second half, r >= 1).  Only rows
-// 0 .. n_rows-1 feed a frame that exists (n_rows = valid frames of the tile + 1); the others are
-// zero-filled without touching global memory -- in the last tile of an utterance that is most of
-// them, and they would otherwise all take the per-sample reflect path.  The 31 rows 1..31 feed two
-// frames each and are dealt to the warps in equal shares, loaded in batches without any per-row
-// predicate; rows 0 and 32 (one frame each) go to warps 0 and W-1.
+// Only hop-rows 0 .. n_rows-1 feed a frame that exists (n_rows = valid frames of the tile + 1);
+// the others are zero-filled without touching global memory.  Rows that need the reflect padding
+// (either end of the utterance) or an unaligned wave take a per-sample path with plain loads.
+// The 33 rows are dealt to the W warps in contiguous shares; every branch is warp-uniform.
 template <int W>
 LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
                         int t0, int n_rows, float2* __restrict__ S, bool vec_ok) {
-    constexpr int kShare = (kTile - 1 + W - 1) / W;               // rows per warp (last warp may have fewer)
-    constexpr int kBatch = kShare <= 8 ? kShare : 8;
-    const int r_lo = 1 + w * kShare;
-    const int r_end = r_lo + kShare < kTile ? r_lo + kShare : kTile;
-    const int r_hi = r_end < n_rows ? r_end : n_rows;             // rows that need real samples
-    if (r_hi < r_end) stage_rows_zero(lane, sl, S, r_hi > r_lo ? r_hi : r_lo, r_end);
-#pragma unroll 1
-    for (int r0 = r_lo; r0 < r_hi; r0 += kBatch) {
-        const int r1 = r0 + kBatch < r_hi ? r0 + kBatch : r_hi;
-        if (!rows_interior(t0 + r0 - 1, t0 + r1 - 1, len, vec_ok)) {
-            stage_rows_slow(lane, sl, wave_row, len, t0, S, r0, r1);
-            continue;
-        }
-        const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r0 - 1) * kHop) + lane;
-        float2* da0 = S + sl.slot_a[0] + r0; float2* db0 = S + sl.slot_b[0] + r0 - 1;
-        float2* da1 = S + sl.slot_a[1] + r0; float2* db1 = S + sl.slot_b[1] + r0 - 1;
-        float2* da2 = S + sl.slot_a[2] + r0; float2* db2 = S + sl.slot_b[2] + r0 - 1;
-        float2 v[kBatch][3];
-        if (r1 - r0 == kBatch) {                                  // full batch: no predicates at all
-#pragma unroll
-            for (int i = 0; i < kBatch; ++i) {
-                v[i][0] = LMFB_LDG(src + i * 80);
-                v[i][1] = LMFB_LDG(src + i * 80 + 32);
-                if (lane < 16) v[i][2] = LMFB_LDG(src + i * 80 + 64);
-            }
-#pragma unroll
-            for (int i = 0; i < kBatch; ++i) {
-                da0[i] = make_float2(v[i][0].x * sl.wa0[0], v[i][0].y * sl.wa1[0]);
-                db0[i] = make_float2(v[i][0].x * sl.wb0[0], v[i][0].y * sl.wb1[0]);
-                da1[i] = make_float2(v[i][1].x * sl.wa0[1], v[i][1].y * sl.wa1[1]);
-                db1[i] = make_float2(v[i][1].x * sl.wb0[1], v[i][1].y * sl.wb1[1]);
-                if (lane < 16) {
-                    da2[i] = make_float2(v[i][2].x * sl.wa0[2], v[i][2].y * sl.wa1[2]);
-                    db2[i] = make_float2(v[i][2].x * sl.wb0[2], v[i][2].y * sl.wb1[2]);
-                }
-            }
-        } else {
-#pragma unroll 1
-            for (int r = r0; r < r1; ++r) {
-                const float2* s2 = src + (r - r0) * 80;
-                stage_store(sl, S, r, 0, LMFB_LDG(s2));
-                stage_store(sl, S, r, 1, LMFB_LDG(s2 + 32));
-                if (lane < 16) stage_store(sl, S, r, 2, LMFB_LDG(s2 + 64));
-            }
-        }
-    }
-    // the two half rows
-    const int r_edge = w == 0 ? 0 : (w == W - 1 ? kTile : -1);
-    if (W == 1 || r_edge >= 0) {
-#pragma unroll 1
-        for (int r = (W == 1 ? 0 : r_edge); r <= (W == 1 ? kTile : r_edge); r += kTile) {
-            if (r >= n_rows) {
-                stage_rows_zero(lane, sl, S, r, r + 1);
-            } else if (!rows_interior(t0 + r - 1, t0 + r, len, vec_ok)) {
-                stage_rows_slow(lane, sl, wave_row, len, t0, S, r, r + 1);
-            } else {
-                const float2* s2 = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r - 1) * kHop) + lane;
-                stage_store(sl, S, r, 0, LMFB_LDG(s2));
-                stage_store(sl, S, r, 1, LMFB_LDG(s2 + 32));
-                if (lane < 16) stage_store(sl, S, r, 2, LMFB_LDG(s2 + 64));
-            }
-        }
-    }
-}
-
-// Variant used where registers allow (one-wave launches: 4 warps at 128 registers, 2 warps at
-// 168): all 33 rows are dealt in contiguous shares and a warp issues every load of its share (or
-// half of it) before the first store, so that staging costs one or two memory round trips instead
-// of one per leftover row.  Matters most when a launch is a single wave and nothing else hides
-// the DRAM latency.
-template <int W>
-LMFB_HD void stage_tile_batched(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row,
-                                int len, int t0, int n_rows, float2* __restrict__ S, bool vec_ok) {
-    constexpr int kShare = (kTile + 1 + W - 1) / W;               // rows per warp
-    constexpr int kBatch = kShare <= 9 ? kShare : (kShare + 1) / 2;
+    constexpr int kShare = (kTile + 1 + W - 1) / W;               // rows per warp (the last warp may have fewer)
     const int r_lo = w * kShare;
     const int r_hi = r_lo + kShare < kTile + 1 ? r_lo + kShare : kTile + 1;
 #pragma unroll 1
-    for (int r0 = r_lo; r0 < r_hi; r0 += kBatch) {
-        const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)(t0 + r0 - 1) * kHop) + lane;
-        float2 v[kBatch][3];
-        // per row (all warp-uniform): 0 = not mine, 1 = zero-fill, 2 = vector loads, 3 = reflect path
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            const int r = r0 + i;
-            const bool fast = r < r_hi && r < n_rows && rows_interior(t0 + r - 1, t0 + r, len, vec_ok);
-            if (fast) {
-                v[i][0] = LMFB_LDG(src + i * 80);
-                v[i][1] = LMFB_LDG(src + i * 80 + 32);
-                if (lane < 16) v[i][2] = LMFB_LDG(src + i * 80 + 64);
+    for (int r = r_lo; r < r_hi; ++r) {
+        const int q = t0 + r - 1;                                 // hop-row of the signal
+        if (r >= n_rows) {
+            const float2 z = make_float2(0.0f, 0.0f);
+            stage_store(sl, S, r, 0, z);
+            stage_store(sl, S, r, 1, z);
+            if (lane < 16) stage_store(sl, S, r, 2, z);
+        } else if (row_interior(q, len, vec_ok)) {
+            const float* src = wave_row + (long long)q * kHop + 2 * lane;
+            if (r < kTile) {
+                cp_async8(S + sl.slot_a[0] + r, src);
+                cp_async8(S + sl.slot_a[1] + r, src + 64);
+                if (lane < 16) cp_async8(S + sl.slot_a[2] + r, src + 128);
             }
-        }
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            const int r = r0 + i;
-            if (r >= r_hi) continue;
-            if (r >= n_rows) {
-                stage_rows_zero(lane, sl, S, r, r + 1);
-            } else if (rows_interior(t0 + r - 1, t0 + r, len, vec_ok)) {
-                stage_store(sl, S, r, 0, v[i][0]);
-                stage_store(sl, S, r, 1, v[i][1]);
-                if (lane < 16) stage_store(sl, S, r, 2, v[i][2]);
-            } else {
-                stage_rows_slow(lane, sl, wave_row, len, t0, S, r, r + 1);
+            if (r >= 1) {
+                cp_async8(S + sl.slot_b[0] + r - 1, src);
+                cp_async8(S + sl.slot_b[1] + r - 1, src + 64);
+                if (lane < 16) cp_async8(S + sl.slot_b[2] + r - 1, src + 128);
             }
+        } else {
+            const int base = q * kHop;
+            float2 v[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                         // all six loads in flight before the stores
+                const int c = lane + 32 * k;
+                v[k] = make_float2(0.0f, 0.0f);
+                if (c < 80) {
+                    v[k].x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
+                    v[k].y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
+                }
+            }
+            stage_store(sl, S, r, 0, v[0]);
+            stage_store(sl, S, r, 1, v[1]);
+            if (lane < 16) stage_store(sl, S, r, 2, v[2]);
         }
     }
 }
@@ -380,13 +296,17 @@ LMFB_HD void stage_tile_batched(int w, int lane, const StageLane& sl, const floa
 // pass 1: the five in-register 32-point FFTs of a column, dealt round-robin to the W warps
 // ---------------------------------------------------------------------------------------
 template <int W>
-LMFB_HD void fft_pass1(int w, float2* __restrict__ col) {
+LMFB_HD void fft_pass1(int w, float2* __restrict__ col, const float2* __restrict__ win) {
 #pragma unroll 1
     for (int n1 = w; n1 < 5; n1 += W) {
         float2* p = col + n1 * 32 * kPitch;
+        const float2* wn = win + n1 * 32 * kPitch;                // same address for every lane: broadcast
         float xr[32], xi[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { const float2 v = p[i * kPitch]; xr[i] = v.x; xi[i] = v.y; }
+        for (int i = 0; i < 32; ++i) {
+            const float2 v = p[i * kPitch], g = wn[i * kPitch];
+            xr[i] = v.x * g.x; xi[i] = v.y * g.y;
+        }
         fft32(xr, xi);
 #pragma unroll
         for (int i = 0; i < 32; ++i) p[i * kPitch] = make_float2(xr[i], xi[i]);

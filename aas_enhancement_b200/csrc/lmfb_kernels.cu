@@ -47,7 +47,7 @@ struct K1Args {
 
 constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
 
-template <int MASK, bool BWD, int W, int CTAS, bool DSMEM, bool BATCH>
+template <int MASK, bool BWD, int W, int CTAS, bool DSMEM>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     extern __shared__ __align__(16) float2 S[];
@@ -66,9 +66,10 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_p1));
 #endif
     StageLane sl;
-    stage_lane_init(lane, a.window, sl);
+    stage_lane_init(lane, sl);
+    window_fill(S, a.window, threadIdx.x, kTile * W);          // pad column of the scratch <- window table
 #ifdef LMFB_TIMELINE
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_p2) : "f"(sl.wb1[2]));
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_p2) : "r"(sl.slot_b[2]));
 #endif
     float2* col = S + lane;
 
@@ -160,12 +161,12 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
             for (int m = w; m < n_mels; m += W) dEs[m * kTile + lane] = LMFB_LDG(src + (unsigned)m * som);
         }
         const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;          // hop-rows that feed a valid frame
-        if (BATCH) stage_tile_batched<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
-        else       stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
+        stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
         LMFB_TICK(1);
+        cp_async_wait_all();
         __syncthreads();
         LMFB_TICK(2);
-        fft_pass1<W>(w, col);
+        fft_pass1<W>(w, col, S + kTile);
         const float* mr = a.mask_r + moff + clamp;
         const float* mi = a.mask_i + moff + clamp;
         const float* de = (BWD && DSMEM) ? dEs + lane : a.dE + row_nm + clamp;
@@ -444,20 +445,18 @@ typedef void (*k1_fn)(const K1Args, const MelBand);
 
 struct K1Variant { int warps, ctas, dsmem; k1_fn fwd[3], bwd[3]; };   // indexed by mask mode
 
-#define LMFB_VARIANT(W, C, D, B)                                                                       \
-    { W, C, D,                                                                                         \
-      { (k1_fn)lmfb_k1<kMaskNone, false, W, C, D, B>, (k1_fn)lmfb_k1<kMaskReim, false, W, C, D, B>,    \
-        (k1_fn)lmfb_k1<kMaskPower, false, W, C, D, B> },                                               \
-      { nullptr, (k1_fn)lmfb_k1<kMaskReim, true, W, C, D, B>, (k1_fn)lmfb_k1<kMaskPower, true, W, C, D, B> } }
+#define LMFB_VARIANT(W, C, D)                                                                    \
+    { W, C, D,                                                                                   \
+      { (k1_fn)lmfb_k1<kMaskNone, false, W, C, D>, (k1_fn)lmfb_k1<kMaskReim, false, W, C, D>,    \
+        (k1_fn)lmfb_k1<kMaskPower, false, W, C, D> },                                            \
+      { nullptr, (k1_fn)lmfb_k1<kMaskReim, true, W, C, D>, (k1_fn)lmfb_k1<kMaskPower, true, W, C, D> } }
 
 // (warps per tile, resident CTAs per SM the register budget is sized for, dE tile staged in smem)
 static const K1Variant kVariants[] = {
-    LMFB_VARIANT(4, 5, false, false), LMFB_VARIANT(2, 5, false, false), LMFB_VARIANT(3, 5, false, false),
-    LMFB_VARIANT(5, 4, false, false), LMFB_VARIANT(1, 5, false, false), LMFB_VARIANT(4, 4, true, false),
-    LMFB_VARIANT(4, 4, false, false),
-    LMFB_VARIANT(4, 4, false, true),  LMFB_VARIANT(2, 5, false, true),          // batched staging
+    LMFB_VARIANT(4, 5, false), LMFB_VARIANT(2, 5, false), LMFB_VARIANT(3, 5, false),
+    LMFB_VARIANT(5, 4, false), LMFB_VARIANT(1, 5, false), LMFB_VARIANT(4, 4, true),
+    LMFB_VARIANT(4, 4, false),
 };
-constexpr int kVariant44Batched = 7, kVariant2Batched = 8;
 constexpr int kVariantDsmem = 5;
 constexpr int kVariant44 = 6;
 // Defaults measured on B200 (profiles/): in the throughput regime (more tiles than resident CTAs)
@@ -473,8 +472,6 @@ static int pick_variant(const char* env, int dflt) {
         const int wanted = atoi(v);
         if (wanted == 44) return kVariantDsmem;
         if (wanted == 40) return kVariant44;           // 4 warps, register budget for 4 CTAs/SM
-        if (wanted == 41) return kVariant44Batched;    // ... with batched staging
-        if (wanted == 21) return kVariant2Batched;     // 2 warps with batched staging
         for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
             if (kVariants[i].warps == wanted && kVariants[i].ctas == (wanted == 5 ? 4 : 5) && !kVariants[i].dsmem) return (int)i;   // first match: unbatched
     }

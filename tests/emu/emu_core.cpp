@@ -18,16 +18,16 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
               std::vector<float2>& S) {
     Tables tb;
     tables_fill(&tb, mb, mb.ent[1].moff, 0, 1);            // ent[1].moff == bytes per mask row
+    window_fill(S.data(), window, 0, 1);
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
             StageLane sl;
-            stage_lane_init(lane, window, sl);
+            stage_lane_init(lane, sl);
             const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;
-            if (W == 2 || W == 4) stage_tile_batched<W>(w, lane, sl, wave_row, len, t0, n_rows, S.data(), vec_ok);
-            else                  stage_tile<W>(w, lane, sl, wave_row, len, t0, n_rows, S.data(), vec_ok);
+            stage_tile<W>(w, lane, sl, wave_row, len, t0, n_rows, S.data(), vec_ok);
         }
     for (int w = 0; w < W; ++w)
-        for (int lane = 0; lane < 32; ++lane) fft_pass1<W>(w, S.data() + lane);
+        for (int lane = 0; lane < 32; ++lane) fft_pass1<W>(w, S.data() + lane, S.data() + kTile);
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
             const int t = t0 + lane;
