@@ -3,13 +3,13 @@
 // Execution model ("lane = frame"): a CTA of W warps owns a tile of 32 consecutive frames of
 // one utterance.  Lane t of EVERY warp works on frame t0+t, whose 320-point real FFT lives in
 // column t of a shared-memory scratch; the W warps split the independent pieces of that FFT
-// between them (sub-transforms in pass 1, column pairs in pass 2, filter ranges in phase 3) and
+// between them (sub-transforms in pass 1, column pairs in pass 2, bin ranges in phase 3) and
 // meet at block barriers between the passes.  Consequences:
 //   * every twiddle is a literal (the FFT code is identical for all lanes),
 //   * every global access of a (N, F, T)/(N, M, T) tensor has the lanes along T, i.e. is a
 //     128-byte coalesced row segment -- no transposition is ever needed,
 //   * W times more warps are resident per SM for the same shared memory (the scratch, 42 KB per
-//     32 frames, is what limits residency), which is what hides the load and FFT latencies.
+//     32 frames, is what limits residency).
 //
 // Real FFT of 320 samples = complex FFT of the 160 packed samples z[j] = x[2j] + i x[2j+1],
 // computed with the Good-Thomas prime-factor map 160 = 5 x 32 (no inter-stage twiddles):
@@ -17,12 +17,18 @@
 //   pass 1 : window, then five 32-point FFTs in registers (generated codelet), in place
 //   pass 2 : for each index pair (k2, 32-k2): two 5-point DFTs + the real-split butterfly give
 //            ten bins; the mask(s) for those ten bins (prefetched one step ahead into
-//            registers, lanes along T) are applied at once.  Forward: the masked power replaces
-//            the spectrum in place (bin f lives in slot (f mod 5)*32 + (f mod 32); bins 0 and
-//            160, both real, share slot 0).  Backward: dP of the ten bins is formed from dE and
-//            the mask gradients are stored straight from here -- there is no phase 3.
-//   phase 3: (forward only) banded mel accumulation over ascending bins out of the scratch,
-//            then log1p.
+//            registers, lanes along T) are applied at once.  Forward: the masked power P[f] is
+//            written back over the step's own slots as a compact float row.  Backward: dP of the
+//            ten bins is formed from dE and the mask gradients are stored straight from here.
+//   phase 3: (forward only) banded mel accumulation over ascending bins, then log1p.
+// The code is rolled (one copy of a pass-2 step and of an 8-bin phase-3 group serves every warp
+// and stays in the 32 KB instruction cache); what differs between steps / bins comes from small
+// tables in shared memory, laid out so that a step fetches them with a few 128-bit broadcast
+// loads, and every global row address is ONE IMAD.WIDE (row * stride + base).  Measured
+// alternatives: per-element tables with 32-bit offsets (16.9 k / 17.4 k warp instructions per
+// tile forward / backward, 60 % of them address arithmetic and table loads) and fully unrolled
+// passes with compile-time bins (fewest instructions, but 145 KB of code per kernel: 15 warps
+// streaming different code thrash the instruction cache, twice slower).
 // The spectrum is kept as X' = 2 X (the 1/2 of the split is folded into the mel weights as
 // 1/4, exact in binary floating point).
 //
@@ -38,12 +44,13 @@
 #ifdef __CUDACC__
 #  define LMFB_LDG(p) __ldg(p)
 #  define LMFB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
-// make a pointer opaque to the optimiser: it is then kept as one 64-bit register pair and
-// "pointer + 32-bit byte offset" costs one or two instructions instead of a re-derived 64-bit
-// element-offset chain (shift + add + add).
+// make a value opaque to the optimiser: it is then kept in its register(s) instead of being
+// re-derived (rematerialised) at every use
 #  define LMFB_OPAQUE(p) asm volatile("" : "+l"(p))
+#  define LMFB_OPAQUE32(v) asm volatile("" : "+r"(v))
 #else
 #  define LMFB_OPAQUE(p) ((void)0)
+#  define LMFB_OPAQUE32(v) ((void)0)
 #  define LMFB_LDG(p) (*(p))
 #  define LMFB_PREFETCH_L2(p) ((void)(p))
 struct float2 { float x, y; };
@@ -57,6 +64,7 @@ constexpr int kHop   = 160;
 constexpr int kBins  = 161;
 constexpr int kTile  = 32;             // frames per tile
 constexpr int kPitch = 33;             // float2 per scratch slot (32 lanes + 1 pad: conflict-free staging)
+constexpr int kRow   = 2 * kPitch;     // floats per scratch slot row
 constexpr int kSlots = 160;
 constexpr int kMaxMels = 128;
 constexpr int kScratchBytes = kSlots * kPitch * 8;     // 42,240 B per tile
@@ -68,86 +76,70 @@ enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2 };
 #define LMFB_NEEDS_MASK_R(MASK, BWD) ((BWD) ? (MASK) == kMaskReim : (MASK) != kMaskNone)
 #define LMFB_NEEDS_MASK_I(MASK, BWD) ((MASK) == kMaskReim)
 
-// Banded-2 description of the mel basis, passed by value as a kernel parameter (constant
-// bank).  Bin f feeds filters ml(f) (weight wl) and ml(f)+1 (weight wh) with ml non-decreasing,
-// so the bins whose lower filter is m form the contiguous range [fend[m-1], fend[m]).
-// Weights already carry the 1/4 that undoes X' = 2X.
-struct BinEnt {
-    float    wl, wh;   // forward: weights into filters ml, ml+1.  backward: weights of dE rows dlo, dlo+1
-    uint32_t off;      // forward: float offset of the bin's masked power inside a scratch column
-                       // backward: dlo * (BYTES per dE row), dlo+1 always being a valid row
-    uint32_t moff;     // f * (BYTES per mask row)
-};
-struct MelBand {
-    BinEnt  ent[kBins];
-    uint8_t fend[kMaxMels];
-    uint8_t mbeg[kMaxW + 1];   // forward phase 3: warp w owns filters [mbeg[w], mbeg[w+1])
-    uint8_t pad_[3];
+// compile-time loop: f(IC<B>{}), f(IC<B+1>{}), ... f(IC<E-1>{})
+template <int I> struct IC { static constexpr int value = I; };
+template <int B, int E, class F>
+LMFB_HD void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(IC<B>{});
+        static_for<B + 1, E>(static_cast<F&&>(f));
+    }
+}
+// run f(IC<w>{}) for the (warp-uniform) run-time w in [0, W)
+template <int W, class F>
+LMFB_HD void dispatch_warp(int w, F&& f) {
+    static_for<0, W>([&](auto wc) { if (w == decltype(wc)::value) f(wc); });
+}
+
+// ---- tables -------------------------------------------------------------------------------
+// Banded-2 form of the mel basis (built on the host, mel_band.hpp): bin f feeds filters ml(f)
+// (weight wl) and ml(f)+1 (weight wh) with ml non-decreasing.  Weights already carry the 1/4 that
+// undoes X' = 2X.  The tables travel as a kernel parameter and are copied once per persistent
+// CTA into shared memory behind the scratch.
+constexpr int kGroups = kSlots / 8;            // phase 3 walks bins 0..159 in groups of 8; bin 160 is peeled
+
+struct FwdTab {                                // forward kernel parameter
+    float2  w[kBins];                          // (wl, wh) of bin f
+    uint8_t hmask[kGroups + 4];                // bit i of byte g: the band moves on before bin 8g+i (adv != 0)
+    uint8_t adv[kBins + 3];                    // ml(f) - ml(f-1): filters completed before bin f (0 for f = 0)
+    uint8_t lo[kMaxW];                         // phase 3: warp w produces partial sums of filters lo[w] .. hi[w]
+    uint8_t hi[kMaxW];                         //          (hi may exceed n_mels - 1; lo > hi: warp has no bins)
     int     n_mels;
+    int     multi;                             // some bin completes more than one filter (adv > 1)
 };
-
-// Shared-memory copy of every table the tile loop indexes at run time.  Indexed constant-bank
-// loads (LDC with a register index) miss the small indexed-constant cache about one time in
-// five on this kernel and each miss stalls the warp for hundreds of cycles (ncu:
-// idc__request_hit_rate 79 %); shared memory has a fixed ~30-cycle latency and broadcasts.
-// Filled once per (persistent) CTA by tables_fill().
-struct Tables {
-    float    wl[kBins + 3], wh[kBins + 3];
-    uint32_t off[kBins + 3];      // forward: float offset of the bin's masked power in a scratch column
-                                  // backward: byte offset of dE row dlo (dlo+1 always valid)
-    float    ssin[88], scos[88];  // real-split twiddles [k2*5 + k1]
-    uint8_t  binof[88];           // bin produced by pass-2 step k2, output k1 [k2*5 + k1]
-    uint8_t  fend[kMaxMels];
-    uint8_t  mbeg[kMaxW + 1];
-    uint8_t  pad_[3];
+struct BwdTab {                                // backward kernel parameter, per pass-2 step k2 and output k1
+    float    w[17][5][4];                      // wl_f, wh_f, wl_fp, wh_fp: weights of the dE rows (d, d+1)
+    uint32_t d[17][5][2];                      // dE row d of bin f and of bin fp = 160 - f (d+1 is always valid)
     int      n_mels;
-    uint32_t msf_bytes;           // bytes per mask row
-    uint32_t pad2_[2];
+    int      pad_;
 };
-constexpr int kTablesBytes = (int)((sizeof(Tables) + 15) / 16 * 16);
-constexpr int kSmemBytes = kScratchBytes + kTablesBytes;
+// shared-memory image: the per-step constants of the algorithm, then the parameter above
+struct alignas(16) StepEnt { uint32_t f[5]; float sn[5]; float cs[5]; uint32_t pad_; };     // 64 B
+struct alignas(16) FwdSmem { StepEnt step[17]; float2 w[kBins]; uint8_t hmask[kGroups + 4]; uint8_t adv[kBins + 3]; };
+struct alignas(16) BwdSmem { StepEnt step[17]; float w[17][5][4]; uint32_t d[17][5][2]; };
+constexpr int kTabBytesFwd = (int)((sizeof(FwdSmem) + 15) / 16 * 16);
+constexpr int kTabBytesBwd = (int)((sizeof(BwdSmem) + 15) / 16 * 16);
+template <bool BWD> struct TabOf;
+template <> struct TabOf<false> { typedef FwdTab Param; typedef FwdSmem Smem; };
+template <> struct TabOf<true>  { typedef BwdTab Param; typedef BwdSmem Smem; };
+constexpr int smem_bytes(bool bwd) { return kScratchBytes + (bwd ? kTabBytesBwd : kTabBytesFwd); }
 
-// Cooperative copy, once per persistent CTA.  The source lives in constant banks (kernel
-// parameters and __constant__ tables), which only serve a warp quickly when all lanes read the
-// SAME address: every warp therefore walks a contiguous share of the entries with a warp-uniform
-// index and all lanes store the same value (a benign broadcast store).  A lane-indexed copy costs
-// ~5 us per CTA (32-way serialised constant reads); this one well under 1 us.
-LMFB_HD void tables_fill(Tables* tb, const MelBand& mb, uint32_t msf_bytes, int warp, int nwarps) {
-    const int per = (kBins + nwarps - 1) / nwarps;
-    const int f0 = warp * per, f1 = f0 + per < kBins ? f0 + per : kBins;
-#pragma unroll 4
-    for (int f = f0; f < f1; ++f) {
-        tb->wl[f] = mb.ent[f].wl;
-        tb->wh[f] = mb.ent[f].wh;
-        tb->off[f] = mb.ent[f].off;
-    }
-    const int per2 = (85 + nwarps - 1) / nwarps;
-    const int i0 = warp * per2, i1 = i0 + per2 < 85 ? i0 + per2 : 85;
-    int k2 = i0 / 5, k1 = i0 - 5 * k2;
-#pragma unroll 4
-    for (int i = i0; i < i1; ++i) {
-        tb->ssin[i] = kSplitSin[k2][k1];
-        tb->scos[i] = kSplitCos[k2][k1];
-        tb->binof[i] = kBinOf[k2][k1];
-        if (++k1 == 5) { k1 = 0; ++k2; }
-    }
-    const int per3 = (kMaxMels + nwarps - 1) / nwarps;
-    const int m0 = warp * per3, m1 = m0 + per3 < kMaxMels ? m0 + per3 : kMaxMels;
-#pragma unroll 4
-    for (int m = m0; m < m1; ++m) tb->fend[m] = mb.fend[m];
-    if (warp == 0) {
-#pragma unroll
-        for (int i = 0; i <= kMaxW; ++i) tb->mbeg[i] = mb.mbeg[i];
-        tb->n_mels = mb.n_mels;
-        tb->msf_bytes = msf_bytes;
-    }
-}
+// phase 3: warp w of W walks the 8-bin groups [p3_g0, p3_g1); the last warp also takes bin 160
+LMFB_CX int p3_per(int W) { return (kGroups + W - 1) / W; }
+LMFB_CX int p3_g0(int W, int w) { return w * p3_per(W) < kGroups ? w * p3_per(W) : kGroups; }
+LMFB_CX int p3_g1(int W, int w) { return (w + 1) * p3_per(W) < kGroups ? (w + 1) * p3_per(W) : kGroups; }
 
-LMFB_HD int slot_of_packed(int j) {            // j in [0,160): packed-sample index -> PFA input slot
-    const int n1 = (3 * (j % 5)) % 5;
-    const int n2 = (13 * (j & 31)) & 31;
-    return n1 * 32 + n2;
+LMFB_CX int slot_of_packed(int j) {            // j in [0,160): packed-sample index -> PFA input slot
+    return ((3 * (j % 5)) % 5) * 32 + ((13 * (j & 31)) & 31);
 }
+// bin produced by pass-2 step k2, output k1 (CRT of k1 mod 5, k2 mod 32); its partner is 160 - f
+LMFB_CX int bin_of(int k2, int k1) { return (96 * k1 + 65 * k2) % 160; }
+// float offset (inside the scratch, before adding the lane) of the masked power of bin f after
+// pass 2: the first 32 floats of slot row f (row f = columns f mod 32 of sub-transform f / 32 is
+// one of the rows the producing step has just consumed); bin 160 takes the second 32 floats of row 0
+LMFB_CX int p_off(int f) { return f == kBins - 1 ? kTile : f * kRow; }
+// float offset of partial-sum row r of phase 3: second 32 floats of slot row 1 + r
+LMFB_CX int e_off(int r) { return (1 + r) * kRow + kTile; }
 
 // 'reflect' padding index (numpy semantics, any offset, length >= 1)
 LMFB_HD int reflect_index(int i, int len) {
@@ -158,27 +150,25 @@ LMFB_HD int reflect_index(int i, int len) {
     return j >= len ? period - j : j;
 }
 
-// pointer + byte offset (offsets come from the per-launch tables, in bytes, and fit 32 bits)
-LMFB_HD const float* at_bytes(const float* p, uint32_t bytes) {
-    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p) + bytes);
+// row `row` of a tensor whose rows are `stride_bytes` apart: one IMAD.WIDE when `row` is a constant
+LMFB_HD const float* at_row(const float* p, uint32_t row, uint32_t stride_bytes) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p) +
+                                          (unsigned long long)row * (unsigned long long)stride_bytes);
 }
-LMFB_HD float* at_bytes(float* p, uint32_t bytes) {
-    return reinterpret_cast<float*>(reinterpret_cast<char*>(p) + bytes);
+LMFB_HD float* at_row(float* p, uint32_t row, uint32_t stride_bytes) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(p) +
+                                    (unsigned long long)row * (unsigned long long)stride_bytes);
 }
 
 #ifdef __CUDACC__
 // predicated 4-byte global store (keeps the store a single predicated instruction)
 __device__ __forceinline__ void st_if(float* p, float v, bool pred) {
-#ifdef LMFB_DBG_NOSTORE
-    if (v == 1.2345e-30f) *p = v;      // experiment: keep the value live, never store
-    return;
-#endif
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}"
                  :: "l"(p), "f"(v), "r"((int)pred));
 }
 // predicated shared-memory store that the optimiser does not see as a memory access: used for
-// the E[m] slots of phase 3, which can never alias the P[f] words the same loop reads, so that
-// those reads may be hoisted and overlapped freely.
+// the partial-sum rows of phase 3, which can never alias the P[f] words the same code reads, so
+// that those reads may be hoisted and overlapped freely
 __device__ __forceinline__ void sts_if_noalias(float* p, float v, bool pred) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}"
                  :: "r"((unsigned)__cvta_generic_to_shared(p)), "f"(v), "r"((int)pred));
@@ -191,39 +181,47 @@ static inline void sts_if_noalias(float* p, float v, bool pred) { if (pred) *p =
 // ---------------------------------------------------------------------------------------
 // Staging: the (32+1)*160 samples a tile needs go STRAIGHT from global memory into the 32 frame
 // columns with 8-byte asynchronous copies (cp.async / LDGSTS): no register round trip, every
-// copy of the tile in flight at once, one exposed memory round trip per tile instead of one per
-// load batch.  The samples land RAW and in PFA input order; the window is applied by pass 1 when
-// it loads them (the window table lives in the pad column of the scratch, window_fill()).
-// Lanes run along the packed-sample index of a hop-row, so the global side is a coalesced
-// 256-byte run and the shared side is conflict-free (slot pitch 33).  Hop-row r feeds frame r
-// (first half, r < 32) and frame r-1 (second half, r >= 1): two copies of the same 8 bytes, the
-// second of which hits L1.
+// copy of the tile in flight at once, one exposed memory round trip per tile.  The samples land
+// RAW and in PFA input order; the window is applied by pass 1 when it loads them (the window
+// table lives in the pad column of the scratch, window_fill()).  Lanes run along the
+// packed-sample index of a hop-row, so the global side is a coalesced 256-byte run and the
+// shared side is conflict-free (slot pitch 33).  Hop-row r feeds frame r (first half, r < 32)
+// and frame r-1 (second half, r >= 1).
 // ---------------------------------------------------------------------------------------
 #ifdef __CUDACC__
-__device__ __forceinline__ void cp_async8(float2* dst, const float* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
-                 :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8(unsigned dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 #else
-static inline void cp_async8(float2* dst, const float* src) { dst->x = src[0]; dst->y = src[1]; }
 static inline void cp_async_wait_all() {}
 #endif
 
-struct StageLane {                      // per-lane constants of the staging map (float2 index of slot * pitch)
-    int slot_a[3], slot_b[3];
+struct StageLane {                      // per-lane constants of the staging map
+    int      slot_a[3], slot_b[3];      // float2 index of (slot * pitch) for packed samples c, c + 80
+    unsigned sa[3], sb[3];              // the same as shared-space byte addresses of column 0 (device only)
 };
 
-LMFB_HD void stage_lane_init(int lane, StageLane& sl) {
+LMFB_HD void stage_lane_init(int lane, float2* S, StageLane& sl) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         const int c = lane + 32 * q;                       // packed index inside a hop-row, < 80 valid
         const int cc = c < 80 ? c : 0;
         sl.slot_a[q] = slot_of_packed(cc) * kPitch;
         sl.slot_b[q] = slot_of_packed(cc + 80) * kPitch;
+        LMFB_OPAQUE32(sl.slot_a[q]); LMFB_OPAQUE32(sl.slot_b[q]);
+#ifdef __CUDACC__
+        sl.sa[q] = smem_u32(S + sl.slot_a[q]);
+        sl.sb[q] = smem_u32(S + sl.slot_b[q]);
+        LMFB_OPAQUE32(sl.sa[q]); LMFB_OPAQUE32(sl.sb[q]);
+#else
+        sl.sa[q] = sl.sb[q] = 0;
+#endif
     }
+    (void)S;
 }
 
 // window table: pad column (index 32) of slot s holds the window pair of the packed sample that
@@ -243,53 +241,74 @@ LMFB_HD void stage_store(const StageLane& sl, float2* __restrict__ S, int r, int
     if (r >= 1)     S[sl.slot_b[q] + r - 1] = v;
 }
 
-// Only hop-rows 0 .. n_rows-1 feed a frame that exists (n_rows = valid frames of the tile + 1);
-// the others are zero-filled without touching global memory.  Rows that need the reflect padding
-// (either end of the utterance) or an unaligned wave take a per-sample path with plain loads.
-// The 33 rows are dealt to the W warps in contiguous shares; every branch is warp-uniform.
+// one hop-row, any case (warp-uniform branches): rows >= n_rows feed no frame that exists and are
+// zero-filled; rows that need the reflect padding (either end of the utterance) or an unaligned
+// wave take a per-sample path with plain loads
+LMFB_HD void stage_row_any(int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
+                           int t0, int r, int n_rows, float2* __restrict__ S, bool vec_ok) {
+    const int q = t0 + r - 1;                                 // hop-row of the signal
+    float2 v[3];
+    v[0] = v[1] = v[2] = make_float2(0.0f, 0.0f);
+    if (r >= n_rows) {
+        // zero-fill
+    } else if (row_interior(q, len, vec_ok)) {
+        const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)q * kHop) + lane;
+        v[0] = LMFB_LDG(src);
+        v[1] = LMFB_LDG(src + 32);
+        if (lane < 16) v[2] = LMFB_LDG(src + 64);
+    } else {
+        const int base = q * kHop;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {                         // all six loads in flight before the stores
+            const int c = lane + 32 * k;
+            if (c < 80) {
+                v[k].x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
+                v[k].y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
+            }
+        }
+    }
+    stage_store(sl, S, r, 0, v[0]);
+    stage_store(sl, S, r, 1, v[1]);
+    if (lane < 16) stage_store(sl, S, r, 2, v[2]);
+}
+
+// The 33 rows are dealt to the W warps in contiguous shares.  Fast path (every row of the share
+// valid and interior -- all tiles but the first and last of an utterance): straight-line
+// asynchronous copies, every address a register plus an immediate.
 template <int W>
 LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
                         int t0, int n_rows, float2* __restrict__ S, bool vec_ok) {
     constexpr int kShare = (kTile + 1 + W - 1) / W;               // rows per warp (the last warp may have fewer)
     const int r_lo = w * kShare;
     const int r_hi = r_lo + kShare < kTile + 1 ? r_lo + kShare : kTile + 1;
-#pragma unroll 1
-    for (int r = r_lo; r < r_hi; ++r) {
-        const int q = t0 + r - 1;                                 // hop-row of the signal
-        if (r >= n_rows) {
-            const float2 z = make_float2(0.0f, 0.0f);
-            stage_store(sl, S, r, 0, z);
-            stage_store(sl, S, r, 1, z);
-            if (lane < 16) stage_store(sl, S, r, 2, z);
-        } else if (row_interior(q, len, vec_ok)) {
-            const float* src = wave_row + (long long)q * kHop + 2 * lane;
-            if (r < kTile) {
-                cp_async8(S + sl.slot_a[0] + r, src);
-                cp_async8(S + sl.slot_a[1] + r, src + 64);
-                if (lane < 16) cp_async8(S + sl.slot_a[2] + r, src + 128);
-            }
-            if (r >= 1) {
-                cp_async8(S + sl.slot_b[0] + r - 1, src);
-                cp_async8(S + sl.slot_b[1] + r - 1, src + 64);
-                if (lane < 16) cp_async8(S + sl.slot_b[2] + r - 1, src + 128);
-            }
-        } else {
-            const int base = q * kHop;
-            float2 v[3];
+#ifdef __CUDACC__
+    if (r_hi <= n_rows && row_interior(t0 + r_lo - 1, len, vec_ok) && row_interior(t0 + r_hi - 2, len, vec_ok)) {
+        const float* src = wave_row + (long long)(t0 + r_lo - 1) * kHop + 2 * lane;
+        LMFB_OPAQUE(src);
+        const unsigned ro = (unsigned)r_lo * 8u;
+        const unsigned a0 = sl.sa[0] + ro, a1 = sl.sa[1] + ro, a2 = sl.sa[2] + ro;
+        const unsigned b0 = sl.sb[0] + ro, b1 = sl.sb[1] + ro, b2 = sl.sb[2] + ro;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {                         // all six loads in flight before the stores
-                const int c = lane + 32 * k;
-                v[k] = make_float2(0.0f, 0.0f);
-                if (c < 80) {
-                    v[k].x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
-                    v[k].y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
+        for (int i = 0; i < kShare; ++i) {
+            const int r = r_lo + i;                               // warp-uniform
+            if (r < r_hi) {
+                if (r < kTile) {
+                    cp_async8(a0 + i * 8, src + i * kHop);
+                    cp_async8(a1 + i * 8, src + i * kHop + 64);
+                    if (lane < 16) cp_async8(a2 + i * 8, src + i * kHop + 128);
+                }
+                if (r >= 1) {
+                    cp_async8(b0 + i * 8 - 8, src + i * kHop);
+                    cp_async8(b1 + i * 8 - 8, src + i * kHop + 64);
+                    if (lane < 16) cp_async8(b2 + i * 8 - 8, src + i * kHop + 128);
                 }
             }
-            stage_store(sl, S, r, 0, v[0]);
-            stage_store(sl, S, r, 1, v[1]);
-            if (lane < 16) stage_store(sl, S, r, 2, v[2]);
         }
+        return;
     }
+#endif
+#pragma unroll 1
+    for (int r = r_lo; r < r_hi; ++r) stage_row_any(lane, sl, wave_row, len, t0, r, n_rows, S, vec_ok);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -352,183 +371,266 @@ LMFB_HD float masked_power(float2 x, float mr, float mi) {
     return MASK == kMaskPower ? mr * p : p;
 }
 
-// what pass 2 needs from global memory for the ten bins of column pair k2: index k1 -> bin f,
-// index 5+k1 -> bin 160-f.  All pointers are readable for every lane (out-of-row lanes are
-// clamped by the caller), so no load is predicated; offsets come from the per-launch tables.
+// ---------------------------------------------------------------------------------------
+// table fill, once per persistent CTA.  The source lives in constant banks (kernel parameter and
+// __constant__ tables), which only serve a warp quickly when all lanes read the SAME address:
+// every warp walks a contiguous share of the words with a warp-uniform index and lane 0 stores.
+// ---------------------------------------------------------------------------------------
+LMFB_HD void copy_words(uint32_t* dst, const uint32_t* src, int words, int warp, int nwarps, int lane) {
+    const int per = (words + nwarps - 1) / nwarps;
+    const int i0 = warp * per, i1 = i0 + per < words ? i0 + per : words;
+#pragma unroll 8
+    for (int i = i0; i < i1; ++i) { const uint32_t v = src[i]; if (lane == 0) dst[i] = v; }
+}
+LMFB_HD void fill_steps(StepEnt* st, int warp, int nwarps, int lane) {
+    for (int i = warp; i < 17 * 5; i += nwarps) {
+        const int k2 = i / 5, k1 = i - 5 * k2;
+        const uint32_t f = kStepBin[k2][k1];
+        const float sn = kStepSin[k2][k1], cs = kStepCos[k2][k1];
+        if (lane == 0) { st[k2].f[k1] = f; st[k2].sn[k1] = sn; st[k2].cs[k1] = cs; }
+    }
+}
+LMFB_HD void tables_fill(FwdSmem* sm, const FwdTab& tab, int warp, int nwarps, int lane) {
+    fill_steps(sm->step, warp, nwarps, lane);
+    copy_words(reinterpret_cast<uint32_t*>(sm->w), reinterpret_cast<const uint32_t*>(tab.w), 2 * kBins, warp, nwarps, lane);
+    copy_words(reinterpret_cast<uint32_t*>(sm->hmask), reinterpret_cast<const uint32_t*>(tab.hmask),
+               (kGroups + 4 + kBins + 3) / 4, warp, nwarps, lane);            // hmask and adv are adjacent in both structs
+}
+LMFB_HD void tables_fill(BwdSmem* sm, const BwdTab& tab, int warp, int nwarps, int lane) {
+    fill_steps(sm->step, warp, nwarps, lane);
+    copy_words(reinterpret_cast<uint32_t*>(sm->w), reinterpret_cast<const uint32_t*>(tab.w), 17 * 5 * 4 + 17 * 5 * 2, warp, nwarps, lane);
+}
+
+// ---------------------------------------------------------------------------------------
+// pass 2.  Step k2 works on columns k2 and kb = (32-k2) mod 32 of the five sub-transforms: two
+// 5-point DFTs -> real split -> ten bins f = (96 k1 + 65 k2) mod 160 and 160 - f -> mask.  The
+// step is branch-free and identical for all k2 (the self-paired columns k2 = 0, 16, where
+// kb == k2, simply compute each of their bins twice).
+// ---------------------------------------------------------------------------------------
+struct StepK {                                            // the per-step constants, fetched as four 128-bit words
+    uint32_t f[5]; float sn[5], cs[5];
+};
+LMFB_HD void load_step(const StepEnt& se, StepK& k) {
+#ifdef __CUDACC__
+    const uint4* q = reinterpret_cast<const uint4*>(&se);
+    const uint4 a = q[0], b = q[1], c = q[2], d = q[3];
+    k.f[0] = a.x; k.f[1] = a.y; k.f[2] = a.z; k.f[3] = a.w; k.f[4] = b.x;
+    k.sn[0] = __uint_as_float(b.y); k.sn[1] = __uint_as_float(b.z); k.sn[2] = __uint_as_float(b.w);
+    k.sn[3] = __uint_as_float(c.x); k.sn[4] = __uint_as_float(c.y);
+    k.cs[0] = __uint_as_float(c.z); k.cs[1] = __uint_as_float(c.w);
+    k.cs[2] = __uint_as_float(d.x); k.cs[3] = __uint_as_float(d.y); k.cs[4] = __uint_as_float(d.z);
+#else
+    for (int i = 0; i < 5; ++i) { k.f[i] = se.f[i]; k.sn[i] = se.sn[i]; k.cs[i] = se.cs[i]; }
+#endif
+}
+LMFB_HD void load_step_bins(const StepEnt& se, uint32_t (&f)[5]) {
+#ifdef __CUDACC__
+    const uint4* q = reinterpret_cast<const uint4*>(&se);
+    const uint4 a = q[0];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = se.f[4];
+#else
+    for (int i = 0; i < 5; ++i) f[i] = se.f[i];
+#endif
+}
+
+// what a step needs from global memory: index k1 -> bin f, index 5+k1 -> bin 160-f.  All pointers
+// are readable for every lane (out-of-row lanes are clamped by the caller): no load is predicated.
 struct StepMasks { float vr[10], vi[10]; };              // mask values (prefetched one step ahead)
 struct StepD     { float d0[10], d1[10]; };              // backward: the two dE rows of each bin
 
 template <int MASK, bool BWD>
-LMFB_HD void load_masks(int k2, const Tables& tb, const float* __restrict__ mr, const float* __restrict__ mi,
+LMFB_HD void load_masks(const StepEnt& se, const float* __restrict__ mr, const float* __restrict__ mi, unsigned msf_bytes,
                         StepMasks& in) {
-    const uint32_t msf = tb.msf_bytes;
+    uint32_t f[5];
+    load_step_bins(se, f);
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
-        const unsigned f = tb.binof[k2 * 5 + k1], fp = kBins - 1 - f;
-        const uint32_t of = f * msf, op = fp * msf;
-#ifdef LMFB_DBG_NOMASKLOAD
-        in.vr[k1] = in.vr[5 + k1] = 0.5f + 1e-9f * of; in.vi[k1] = in.vi[5 + k1] = 0.25f + 1e-9f * op;   // experiment
-        continue;
-#endif
-        if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(at_bytes(mr, of)); in.vr[5 + k1] = LMFB_LDG(at_bytes(mr, op)); }
-        if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(at_bytes(mi, of)); in.vi[5 + k1] = LMFB_LDG(at_bytes(mi, op)); }
+        const uint32_t fp = kBins - 1 - f[k1];
+        if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(at_row(mr, f[k1], msf_bytes)); in.vr[5 + k1] = LMFB_LDG(at_row(mr, fp, msf_bytes)); }
+        if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(at_row(mi, f[k1], msf_bytes)); in.vi[5 + k1] = LMFB_LDG(at_row(mi, fp, msf_bytes)); }
     }
 }
 
 // issued at the start of the step that consumes it: the two 5-point DFTs and the split (about
 // 200 instructions that need nothing from global memory) run while these loads are in flight.
-// `dE` is either the global column (row stride sem_bytes) or, in the variants that stage the
-// tile's dE rows in shared memory, that staged column (row stride 128 bytes).
-template <bool DSMEM>
-LMFB_HD void load_d(int k2, const Tables& tb, const float* __restrict__ dE, unsigned sem_bytes, StepD& in) {
+// de1 = dE + one row.
+LMFB_HD void load_d(const uint32_t (*drow)[2], const float* __restrict__ dE, const float* __restrict__ de1,
+                    unsigned sem_bytes, StepD& in) {
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
-        const unsigned f = tb.binof[k2 * 5 + k1], fp = kBins - 1 - f;
-        const uint32_t df = tb.off[f], dp = tb.off[fp];
-        if (DSMEM) {                                           // shared memory: plain loads
-            in.d0[k1]     = *at_bytes(dE, df);
-            in.d1[k1]     = *at_bytes(dE, df + sem_bytes);
-            in.d0[5 + k1] = *at_bytes(dE, dp);
-            in.d1[5 + k1] = *at_bytes(dE, dp + sem_bytes);
-        } else {
-            in.d0[k1]     = LMFB_LDG(at_bytes(dE, df));
-            in.d1[k1]     = LMFB_LDG(at_bytes(dE, df + sem_bytes));
-            in.d0[5 + k1] = LMFB_LDG(at_bytes(dE, dp));
-            in.d1[5 + k1] = LMFB_LDG(at_bytes(dE, dp + sem_bytes));
-        }
+        const uint32_t df = drow[k1][0], dp = drow[k1][1];
+        in.d0[k1]     = LMFB_LDG(at_row(dE, df, sem_bytes));
+        in.d1[k1]     = LMFB_LDG(at_row(de1, df, sem_bytes));
+        in.d0[5 + k1] = LMFB_LDG(at_row(dE, dp, sem_bytes));
+        in.d1[5 + k1] = LMFB_LDG(at_row(de1, dp, sem_bytes));
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// pass 2, one step: columns k2 and kb = (32-k2) mod 32 of the five sub-transforms -> two 5-point
-// DFTs -> real split -> ten bins -> mask.  Branch-free and identical for all k2: the self-paired
-// columns (k2 = 0, 16, where kb == k2) simply compute each of their bins twice.
-//   forward : masked power stored in place (bins 0/160 share slot 0 -> one select)
+//   col : this lane's float2 column (S + lane);  pl : this lane's float column ((float*)S + lane)
+//   forward : masked power of bin f -> pl[p_off(f)], i.e. slot row f, one of the rows this step
+//             has just read and no other step touches
 //   backward: gradients = (2 Mr Re'^2, 2 Mi Im'^2) * dP, or (Re'^2 + Im'^2) * dP for 'power',
-//             stored to gr/gi (+ f*gsf); every lane's pointers are valid, `inrow` gates the store
-// ---------------------------------------------------------------------------------------
-template <int MASK, bool BWD, bool DSMEM>
-LMFB_HD void pass2_step(float2* __restrict__ col, int k2, const Tables& tb, const StepMasks& in,
-                        const float* __restrict__ dE, unsigned sem_bytes,
+//             stored to row f of gr/gi; every lane's pointers are valid, `inrow` gates the store
+template <int MASK, bool BWD, class SM>
+LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl, const SM& sm, const StepMasks& in,
+                        const float* __restrict__ dE, const float* __restrict__ de1, unsigned sem_bytes, unsigned msf_bytes,
                         float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
     StepD d;
-    if (BWD) load_d<DSMEM>(k2, tb, dE, sem_bytes, d);
+    if constexpr (BWD) load_d(sm.d[k2], dE, de1, sem_bytes, d);
     const int kb = (32 - k2) & 31;
-    float2* ca = col + k2 * kPitch;
-    float2* cb = col + kb * kPitch;
+    const float2* ca = col + k2 * kPitch;
+    const float2* cb = col + kb * kPitch;
     float ar[5], ai[5], br[5], bi[5], Ar[5], Ai[5], Br[5], Bi[5];
 #pragma unroll
     for (int n = 0; n < 5; ++n) {
         const float2 v = ca[n * 32 * kPitch]; ar[n] = v.x; ai[n] = v.y;
         const float2 u = cb[n * 32 * kPitch]; br[n] = u.x; bi[n] = u.y;
     }
+    StepK k;
+    load_step(sm.step[k2], k);
     dft5(ar, ai, Ar, Ai);
     dft5(br, bi, Br, Bi);
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
         const int kp = (5 - k1) % 5;
+        const uint32_t f = k.f[k1], fp = kBins - 1 - f;
         float2 xf, xp;
-        split_pair(Ar[k1], Ai[k1], Br[kp], Bi[kp], tb.ssin[k2 * 5 + k1], tb.scos[k2 * 5 + k1], xf, xp);
-        if (!BWD) {
-            float pf = masked_power<MASK>(xf, in.vr[k1], in.vi[k1]);
-            float pp = masked_power<MASK>(xp, in.vr[5 + k1], in.vi[5 + k1]);
-            float2 sf2 = make_float2(pf, 0.0f), sp2 = make_float2(pp, 0.0f);
-            if (k1 == 0) {                                // bins 0 and 160 (real) share slot 0
-                const bool z = k2 == 0;
-                sf2 = make_float2(pf, z ? pp : 0.0f);
-                sp2 = make_float2(z ? pf : pp, z ? pp : 0.0f);
-            }
-            ca[k1 * 32 * kPitch] = sf2;
-            cb[kp * 32 * kPitch] = sp2;
+        split_pair(Ar[k1], Ai[k1], Br[kp], Bi[kp], k.sn[k1], k.cs[k1], xf, xp);
+        if constexpr (!BWD) {
+            pl[f * kRow] = masked_power<MASK>(xf, in.vr[k1], in.vi[k1]);
+            // bin 160 (the partner of bin 0, which only output k1 = 0 can produce) sits beside bin 0
+            const uint32_t po = (k1 == 0 && f == 0) ? (uint32_t)kTile : fp * kRow;
+            pl[po] = masked_power<MASK>(xp, in.vr[5 + k1], in.vi[5 + k1]);
         } else {
-            const unsigned f = tb.binof[k2 * 5 + k1], fp = kBins - 1 - f;
-            const uint32_t of = f * tb.msf_bytes, op = fp * tb.msf_bytes;
-            const float dpf = fmaf(tb.wh[f], d.d1[k1], tb.wl[f] * d.d0[k1]);
-            const float dpp = fmaf(tb.wh[fp], d.d1[5 + k1], tb.wl[fp] * d.d0[5 + k1]);
+#ifdef __CUDACC__
+            const float4 wv = *reinterpret_cast<const float4*>(sm.w[k2][k1]);
+            const float wlf = wv.x, whf = wv.y, wlp = wv.z, whp = wv.w;
+#else
+            const float wlf = sm.w[k2][k1][0], whf = sm.w[k2][k1][1], wlp = sm.w[k2][k1][2], whp = sm.w[k2][k1][3];
+#endif
+            const float dpf = fmaf(whf, d.d1[k1], wlf * d.d0[k1]);
+            const float dpp = fmaf(whp, d.d1[5 + k1], wlp * d.d0[5 + k1]);
             if (MASK == kMaskReim) {
-                st_if(at_bytes(gr, of), 2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
-                st_if(at_bytes(gi, of), 2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
-                st_if(at_bytes(gr, op), 2.0f * in.vr[5 + k1] * xp.x * xp.x * dpp, inrow);
-                st_if(at_bytes(gi, op), 2.0f * in.vi[5 + k1] * xp.y * xp.y * dpp, inrow);
+                st_if(at_row(gr, f, msf_bytes), 2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
+                st_if(at_row(gi, f, msf_bytes), 2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
+                st_if(at_row(gr, fp, msf_bytes), 2.0f * in.vr[5 + k1] * xp.x * xp.x * dpp, inrow);
+                st_if(at_row(gi, fp, msf_bytes), 2.0f * in.vi[5 + k1] * xp.y * xp.y * dpp, inrow);
             } else {
-                st_if(at_bytes(gr, of), fmaf(xf.x, xf.x, xf.y * xf.y) * dpf, inrow);
-                st_if(at_bytes(gr, op), fmaf(xp.x, xp.x, xp.y * xp.y) * dpp, inrow);
+                st_if(at_row(gr, f, msf_bytes), fmaf(xf.x, xf.x, xf.y * xf.y) * dpf, inrow);
+                st_if(at_row(gr, fp, msf_bytes), fmaf(xp.x, xp.x, xp.y * xp.y) * dpp, inrow);
             }
         }
     }
 }
 
-// pass 2 over the 17 column pairs, dealt round-robin to the W warps; the global inputs of a
-// warp's next step are loaded into a second register set while the current step is computed.
-// `a` must already hold the masks of the warp's first step (k2 = w): the caller issues that
-// load before the block barrier that ends pass 1, so its latency hides behind the barrier.
-template <int W, int MASK, bool BWD, bool DSMEM>
-LMFB_HD void fft_pass2(int w, float2* __restrict__ col, const Tables& tb, StepMasks& a,
+// pass 2 over the 17 column pairs, dealt round-robin to the W warps, in pairs: the global inputs
+// of a warp's next step are loaded into a second register set while the current step is computed
+// (ping-pong, no register moves).  `a` must already hold the masks of the warp's first step
+// (k2 = w): the caller issues that load before the block barrier that ends pass 1, so its latency
+// hides behind the barrier.
+template <int W, int MASK, bool BWD, class SM>
+LMFB_HD void fft_pass2(int w, float2* __restrict__ col, float* __restrict__ pl, const SM& sm, StepMasks& a,
                        const float* __restrict__ mr, const float* __restrict__ mi,
-                       const float* __restrict__ dE, unsigned sem_bytes,
+                       const float* __restrict__ dE, unsigned sem_bytes, unsigned msf_bytes,
                        float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
+    const float* de1 = at_row(dE, 1u, sem_bytes);
     StepMasks b;
 #pragma unroll 1
     for (int k2 = w; k2 <= 16; k2 += 2 * W) {
         const bool has_b = k2 + W <= 16;
-        if (has_b) load_masks<MASK, BWD>(k2 + W, tb, mr, mi, b);
-        pass2_step<MASK, BWD, DSMEM>(col, k2, tb, a, dE, sem_bytes, gr, gi, inrow);
+        if (has_b) load_masks<MASK, BWD>(sm.step[k2 + W], mr, mi, msf_bytes, b);
+        pass2_step<MASK, BWD>(k2, col, pl, sm, a, dE, de1, sem_bytes, msf_bytes, gr, gi, inrow);
         if (has_b) {
-            if (k2 + 2 * W <= 16) load_masks<MASK, BWD>(k2 + 2 * W, tb, mr, mi, a);
-            pass2_step<MASK, BWD, DSMEM>(col, k2 + W, tb, b, dE, sem_bytes, gr, gi, inrow);
+            if (k2 + 2 * W <= 16) load_masks<MASK, BWD>(sm.step[k2 + 2 * W], mr, mi, msf_bytes, a);
+            pass2_step<MASK, BWD>(k2 + W, col, pl, sm, b, dE, de1, sem_bytes, msf_bytes, gr, gi, inrow);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 3 (forward): banded mel accumulation filter by filter (E[m] parked in the free .y of
-// slot 1+m), then log1p + store in an unrolled second sweep.  Warp w owns filters
-// [mbeg[w], mbeg[w+1]); to get the upper-weight contributions of its first filter it starts
-// one filter early and discards that filter's (partial) sum.
+// phase 3 (forward).  A: warp w walks its range of bins in ascending order with two running sums
+// (filters ml(f), ml(f)+1); when the band moves on, the finished sum goes to this warp's partial
+// rows.  A warp writes every row lo[w] .. hi[w] of its own set exactly once (row index = filter +
+// 2w, so the sets of neighbouring warps, which share at most two filters, never collide).
+// B (after a block barrier): filter m = sum of the partial rows of the warps whose range covers
+// m, then log1p + store.
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
-LMFB_HD void phase3_fwd(int w, float2* __restrict__ col, const Tables& tb,
-                        float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid
-#ifdef LMFB_TIMELINE
-                        , long long* g_tl_mid = nullptr
-#endif
-                        ) {
-    float* colf = reinterpret_cast<float*>(col);
-    const int m_lo = tb.mbeg[w], m_hi = tb.mbeg[w + 1];
-    if (m_lo >= m_hi) return;
-    const int m_first = m_lo > 0 ? m_lo - 1 : 0;
-    int f = m_first > 0 ? (int)tb.fend[m_first - 1] : 0;
-    float acc0 = 0.0f, acc1 = 0.0f;
-    float* ep = colf + (1 + m_first) * 2 * kPitch + 1;     // E[m] -> .y of slot 1+m
-    int fe = tb.fend[m_first];
+struct Walk { float acc0, acc1; float* cur; };
+
+// one bin; `h`: the band moves on by one filter before this bin
+LMFB_HD void walk_bin(Walk& wk, float p, float2 wgt, bool h) {
+    sts_if_noalias(wk.cur, wk.acc0, h);
+    wk.acc0 = h ? wk.acc1 : wk.acc0;
+    wk.acc1 = h ? 0.0f : wk.acc1;
+    wk.cur += h ? kRow : 0;
+    wk.acc0 = fmaf(wgt.x, p, wk.acc0);
+    wk.acc1 = fmaf(wgt.y, p, wk.acc1);
+}
+// general hand-over of `adv` filters (bases in which several filters end on the same bin)
+LMFB_HD void walk_bin_multi(Walk& wk, float p, float2 wgt, unsigned adv) {
+    if (adv != 0) {
+        sts_if_noalias(wk.cur, wk.acc0, true); wk.cur += kRow;
+        wk.acc0 = wk.acc1; wk.acc1 = 0.0f;
+        if (adv > 1) {
+            sts_if_noalias(wk.cur, wk.acc0, true); wk.cur += kRow;
+            wk.acc0 = 0.0f;
 #pragma unroll 1
-    for (int m = m_first; m < m_hi; ++m) {
-        const int fe_next = m + 1 < m_hi ? (int)tb.fend[m + 1] : fe;     // fetched one filter ahead
-#pragma unroll 4
-        for (; f < fe; ++f) {
-            // slot of bin f computed, not looked up: the P read does not wait for a table read
-            const int off = ((f % 5) * 32 + (f & 31)) * (2 * kPitch) + (f == kBins - 1 ? 1 : 0);
-            const float p = colf[off];
-            acc0 = fmaf(tb.wl[f], p, acc0);
-            acc1 = fmaf(tb.wh[f], p, acc1);
+            for (unsigned i = 2; i < adv; ++i) { sts_if_noalias(wk.cur, 0.0f, true); wk.cur += kRow; }
         }
-        if (m >= m_lo) *ep = acc0;                         // the early filter m_lo-1 belongs to another warp
-        ep += 2 * kPitch;
-        acc0 = acc1;
-        acc1 = 0.0f;
-        fe = fe_next;
     }
-#ifdef LMFB_TIMELINE
-    if (g_tl_mid) *g_tl_mid = clock64();
-#endif
-    const float* eq = colf + (1 + m_lo) * 2 * kPitch + 1;
-    float* op = at_bytes(out, (uint32_t)m_lo * som_bytes);
-#pragma unroll 4
+    wk.acc0 = fmaf(wgt.x, p, wk.acc0);
+    wk.acc1 = fmaf(wgt.y, p, wk.acc1);
+}
+
+template <int W>
+LMFB_HD void phase3_walk(int w, float* __restrict__ pl, const FwdSmem& sm, const FwdTab& tab) {
+    const int g0 = p3_g0(W, w), g1 = p3_g1(W, w);
+    const bool last = w == W - 1;
+    if (g0 >= g1 && !last) return;
+    Walk wk;
+    wk.acc0 = wk.acc1 = 0.0f;
+    wk.cur = pl + e_off(2 * w) + (int)tab.lo[w] * kRow;
+    const float* pp = pl + g0 * 8 * kRow;
+    const float2* wp = sm.w + g0 * 8;
+    if (!tab.multi) {
+#pragma unroll 1
+        for (int g = g0; g < g1; ++g) {
+            float p[8]; float2 wg[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { p[i] = pp[i * kRow]; wg[i] = wp[i]; }
+            unsigned hm = sm.hmask[g];
+            if (g == g0) hm &= ~1u;                        // nothing is complete before the warp's first bin
+#pragma unroll
+            for (int i = 0; i < 8; ++i) walk_bin(wk, p[i], wg[i], (hm >> i) & 1u);
+            pp += 8 * kRow; wp += 8;
+        }
+        if (last) walk_bin(wk, pl[p_off(kBins - 1)], sm.w[kBins - 1], g1 > g0 && (sm.hmask[kGroups] & 1u));
+    } else {
+#pragma unroll 1
+        for (int f = g0 * 8; f < g1 * 8; ++f) walk_bin_multi(wk, pl[f * kRow], sm.w[f], f == g0 * 8 ? 0u : sm.adv[f]);
+        if (last) walk_bin_multi(wk, pl[p_off(kBins - 1)], sm.w[kBins - 1], g1 > g0 ? sm.adv[kBins - 1] : 0u);
+    }
+    sts_if_noalias(wk.cur, wk.acc0, true);
+    sts_if_noalias(wk.cur + kRow, wk.acc1, true);
+}
+
+template <int W>
+LMFB_HD void phase3_finish(int w, const float* __restrict__ pl, const FwdTab& tab,
+                           float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid) {
+    const int n_mels = tab.n_mels;
+    const int per = (n_mels + W - 1) / W;
+    const int m_lo = w * per, m_hi = m_lo + per < n_mels ? m_lo + per : n_mels;
+    float* op = at_row(out, (uint32_t)m_lo, som_bytes);
+#pragma unroll 2
     for (int m = m_lo; m < m_hi; ++m) {
-        const float y = valid ? log1pf(*eq) : 0.0f;
+        float e = 0.0f;
+#pragma unroll
+        for (int wi = 0; wi < W; ++wi)
+            if (m >= (int)tab.lo[wi] && m <= (int)tab.hi[wi]) e += pl[e_off(2 * wi) + m * kRow];
+        const float y = valid ? log1pf(e) : 0.0f;
         st_if(op, y, inrow);
-        eq += 2 * kPitch;
-        op = at_bytes(op, som_bytes);
+        op = at_row(op, 1u, som_bytes);
     }
 }
 

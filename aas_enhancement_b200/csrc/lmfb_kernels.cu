@@ -42,43 +42,32 @@ struct K1Args {
     int            total_tiles;
     int            vec_ok;
     long long*     timeline;   // debug builds (-DLMFB_TIMELINE) only: per-warp phase clocks
-    int            stagger_ns; // delay of the k-th resident CTA of an SM before its first tile
 };
 
 constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
 
-template <int MASK, bool BWD, int W, int CTAS, bool DSMEM>
+template <int MASK, bool BWD, int W, int CTAS>
 __global__ void __launch_bounds__(kTile * W, CTAS)
-lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
+lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf<BWD>::Param tab) {
+    typedef typename TabOf<BWD>::Smem SM;
     extern __shared__ __align__(16) float2 S[];
+    SM& sm = *reinterpret_cast<SM*>(reinterpret_cast<char*>(S) + kScratchBytes);
 #ifdef LMFB_TIMELINE
     unsigned long long gt_entry;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_entry));
 #endif
-    Tables& tb = *reinterpret_cast<Tables*>(reinterpret_cast<char*>(S) + kScratchBytes);
-    float* dEs = reinterpret_cast<float*>(reinterpret_cast<char*>(S) + kSmemBytes);   // DSMEM: [n_mels][32]
     const int lane = threadIdx.x & 31;
     const int w    = threadIdx.x >> 5;
-    const int n_mels = mb.n_mels;
-    tables_fill(&tb, mb, a.msf * 4u, w, W);                    // visible after the first block barrier
-#ifdef LMFB_TIMELINE
-    unsigned long long gt_p1, gt_p2;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_p1));
-#endif
+    const int n_mels = tab.n_mels;
     StageLane sl;
-    stage_lane_init(lane, sl);
+    stage_lane_init(lane, S, sl);
     window_fill(S, a.window, threadIdx.x, kTile * W);          // pad column of the scratch <- window table
-#ifdef LMFB_TIMELINE
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_p2) : "r"(sl.slot_b[2]));
-#endif
+    tables_fill(&sm, tab, w, W, lane);                         // visible after the first block barrier
     float2* col = S + lane;
+    float*  pl  = reinterpret_cast<float*>(S) + lane;
+    const unsigned msf_bytes = a.msf * 4u;
+    const unsigned som = (unsigned)a.tmax, som_bytes = som * 4u;
 
-    // CTAs that start together would run their phases in lockstep (all staging, then all FFT, ...)
-    // and leave the load/store and math pipes idle in turn; de-phase the co-resident CTAs once.
-    if (a.stagger_ns > 0) {
-        const unsigned k = blockIdx.x / 148u;
-        if (k > 0) __nanosleep(k * (unsigned)a.stagger_ns);
-    }
     // persistent CTA: tiles are dealt round-robin, neighbouring tiles run at the same time
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int n   = tile / a.tiles_per_utt;
@@ -89,7 +78,6 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         T = T < a.tmax ? T : a.tmax;
         const bool inrow = t < a.tmax;
         const bool valid = t < T;
-        const unsigned som = (unsigned)a.tmax;
         const long long row_nm = (long long)n * n_mels * som + t;
         const long long moff = (long long)n * a.msn + t;
 
@@ -110,24 +98,11 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         }
 
 #ifndef LMFB_DBG_NOPREFETCH
-#ifdef LMFB_DBG_PREFETCH_NEXT
-        {   // experiment: prefetch the NEXT tile's rows (a whole tile ahead)
-            const int nt = tile + gridDim.x;
-            if (nt < a.total_tiles) {
-                const int nn = nt / a.tiles_per_utt;
-                const int nt0 = (nt - nn * a.tiles_per_utt) * kTile;
-                if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)nn * a.msn, a.msf, kBins, nt0, a.tmax);
-                if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)nn * a.msn, a.msf, kBins, nt0, a.tmax);
-                if (BWD && !DSMEM) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)nn * n_mels * som, som, n_mels, nt0, a.tmax);
-                prefetch_wave_l2(threadIdx.x, kTile * W, a.wave + (long long)nn * a.wave_stride, a.lengths[nn], nt0);
-            }
-        }
-#else
         // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs ...
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
-        if (BWD && !DSMEM) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
-        // ... and the next tile's samples, so that its staging loads hit L2
+        if (BWD) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
+        // ... and the next tile's samples, so that its staging copies hit L2
         {
             const int nt = tile + gridDim.x;
             if (nt < a.total_tiles) {
@@ -136,7 +111,6 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
                                  (nt - nn * a.tiles_per_utt) * kTile);
             }
         }
-#endif
 #endif
 
 #ifdef LMFB_TIMELINE
@@ -149,17 +123,8 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
 #define LMFB_TICK(i) ((void)0)
 #endif
         LMFB_TICK(0);
-#ifdef LMFB_TIMELINE
-        unsigned long long gt_tile0 = 0;
-        if (tile == (int)blockIdx.x) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_tile0));
-#endif
         // loads of out-of-row lanes are redirected to the last column of the row (always readable)
         const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
-        if (BWD && DSMEM) {                         // this tile's dE rows -> shared memory, lanes along T
-            const float* src = a.dE + row_nm + clamp;
-#pragma unroll 4
-            for (int m = w; m < n_mels; m += W) dEs[m * kTile + lane] = LMFB_LDG(src + (unsigned)m * som);
-        }
         const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;          // hop-rows that feed a valid frame
         stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
         LMFB_TICK(1);
@@ -169,29 +134,25 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
         fft_pass1<W>(w, col, S + kTile);
         const float* mr = a.mask_r + moff + clamp;
         const float* mi = a.mask_i + moff + clamp;
-        const float* de = (BWD && DSMEM) ? dEs + lane : a.dE + row_nm + clamp;
-        const unsigned de_stride = (BWD && DSMEM) ? (unsigned)(kTile * 4) : som * 4u;
+        const float* de = a.dE + row_nm + clamp;
         float* gr = a.gr + moff;
         float* gi = a.gi + moff;
         float* po = a.out + row_nm;
         LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
         StepMasks first;                            // issued before the barrier: its latency hides behind it
-        load_masks<MASK, BWD>(w, tb, mr, mi, first);
+        load_masks<MASK, BWD>(sm.step[w], mr, mi, msf_bytes, first);
         LMFB_TICK(3);
         __syncthreads();
         LMFB_TICK(4);
-        fft_pass2<W, MASK, BWD, DSMEM>(w, col, tb, first, mr, mi, de, de_stride, gr, gi, inrow);
+        fft_pass2<W, MASK, BWD>(w, col, pl, sm, first, mr, mi, de, som_bytes, msf_bytes, gr, gi, inrow);
         LMFB_TICK(5);
-        if (!BWD) {
+        if constexpr (!BWD) {
             __syncthreads();
             LMFB_TICK(6);
-#ifdef LMFB_TIMELINE
-            long long mid = 0;
-            phase3_fwd(w, col, tb, po, som * 4u, inrow, valid, &mid);
-            tl[5] = mid;                        // (overwrites the pass-2 end stamp: phase 3 split A | B)
-#else
-            phase3_fwd(w, col, tb, po, som * 4u, inrow, valid);
-#endif
+            phase3_walk<W>(w, pl, sm, tab);
+            __syncthreads();
+            LMFB_TICK(5);                       // (overwrites the pass-2 end stamp: phase 3 split A | B)
+            phase3_finish<W>(w, pl, tab, po, som_bytes, inrow, valid);
         }
 #ifdef LMFB_TIMELINE
         else tl[6] = tl[5];
@@ -209,9 +170,9 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ MelBand mb) {
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
             long long* dst = a.timeline + 8 * 64 * 8 * 8 + (long long)blockIdx.x * 4;
             dst[0] = (long long)gt;                 // end of the tile (ns)
-            dst[1] = ((long long)(gt_p1 - gt_entry) << 32) | (long long)(gt_p2 - gt_p1);   // prologue split (ns)
+            dst[1] = 0;
             dst[2] = (long long)gt_entry;           // kernel entry of this CTA (ns)
-            dst[3] = (long long)gt_tile0;           // start of its first tile, after the prologue (ns)
+            dst[3] = 0;
         }
 #endif
     }
@@ -441,49 +402,45 @@ cmvn_bwd_rows(const float* __restrict__ z, const float* __restrict__ stats,
 // ======================================================================================
 using namespace aas_lmfb;
 
-typedef void (*k1_fn)(const K1Args, const MelBand);
+typedef void (*k1_fwd_fn)(const K1Args, const FwdTab);
+typedef void (*k1_bwd_fn)(const K1Args, const BwdTab);
 
-struct K1Variant { int warps, ctas, dsmem; k1_fn fwd[3], bwd[3]; };   // indexed by mask mode
+struct K1Variant { int warps, ctas; k1_fwd_fn fwd[3]; k1_bwd_fn bwd[3]; };   // indexed by mask mode
 
-#define LMFB_VARIANT(W, C, D)                                                                    \
-    { W, C, D,                                                                                   \
-      { (k1_fn)lmfb_k1<kMaskNone, false, W, C, D>, (k1_fn)lmfb_k1<kMaskReim, false, W, C, D>,    \
-        (k1_fn)lmfb_k1<kMaskPower, false, W, C, D> },                                            \
-      { nullptr, (k1_fn)lmfb_k1<kMaskReim, true, W, C, D>, (k1_fn)lmfb_k1<kMaskPower, true, W, C, D> } }
+#define LMFB_VARIANT(W, C)                                                                 \
+    { W, C,                                                                                \
+      { lmfb_k1<kMaskNone, false, W, C>, lmfb_k1<kMaskReim, false, W, C>,                  \
+        lmfb_k1<kMaskPower, false, W, C> },                                                \
+      { nullptr, lmfb_k1<kMaskReim, true, W, C>, lmfb_k1<kMaskPower, true, W, C> } }
 
-// (warps per tile, resident CTAs per SM the register budget is sized for, dE tile staged in smem)
+// (warps per tile, resident CTAs per SM the register budget is sized for)
 static const K1Variant kVariants[] = {
-    LMFB_VARIANT(4, 5, false), LMFB_VARIANT(2, 5, false), LMFB_VARIANT(3, 5, false),
-    LMFB_VARIANT(5, 4, false), LMFB_VARIANT(1, 5, false), LMFB_VARIANT(4, 4, true),
-    LMFB_VARIANT(4, 4, false),
+#ifdef LMFB_ONLY_W3
+    LMFB_VARIANT(3, 5),
+#else
+    LMFB_VARIANT(3, 5), LMFB_VARIANT(2, 5), LMFB_VARIANT(4, 4),
+#endif
 };
-constexpr int kVariantDsmem = 5;
-constexpr int kVariant44 = 6;
-// Defaults measured on B200 (profiles/): in the throughput regime (more tiles than resident CTAs)
-// 3 warps per tile win for both directions (128 registers, no spills); in the latency regime (a
-// launch that does not fill the resident slots, e.g. 30 x 6 s) the backward prefers 2 warps (168
-// registers, nothing spilled, shortest per-tile critical path); the forward stays at 3.
-constexpr int kFwdVariantBig = 2, kFwdVariantSmall = 2;
-constexpr int kBwdVariantBig = 2, kBwdVariantSmall = 1;
+// Defaults measured on B200 (profiles/): 3 warps per tile (128 registers, 15 warps per SM).
+constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 0;
+constexpr int kBwdVariantBig = 0, kBwdVariantSmall = 0;
 
 static int pick_variant(const char* env, int dflt) {
-    const char* v = getenv(env);            // tuning knob: warps per tile; 44 = 4 warps, 4 CTAs/SM, dE in smem
+    const char* v = getenv(env);            // tuning knob: warps per tile
     if (v) {
         const int wanted = atoi(v);
-        if (wanted == 44) return kVariantDsmem;
-        if (wanted == 40) return kVariant44;           // 4 warps, register budget for 4 CTAs/SM
         for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
-            if (kVariants[i].warps == wanted && kVariants[i].ctas == (wanted == 5 ? 4 : 5) && !kVariants[i].dsmem) return (int)i;   // first match: unbatched
+            if (kVariants[i].warps == wanted) return (int)i;
     }
     return dflt;
 }
 
 struct aas_lmfb_plan {
-    MelBand fwd, bwd;
-    uint8_t dlo[kBins];
+    FwdTab  fwd;
+    BwdTab  bwd;
+    int     ml[kBins];
     int     n_mels;
     int     vfwd, vbwd;
-    int     stagger_ns;
 };
 
 extern "C" int aas_lmfb_abi_version(void) { return AAS_LMFB_ABI_VERSION; }
@@ -515,10 +472,8 @@ extern "C" aas_lmfb_plan* aas_lmfb_plan_create(const float* mel, int n_mels, int
         p->n_mels = n_mels;
         p->vfwd = pick_variant("AAS_LMFB_WARPS_FWD", -1);       // -1: choose by problem size at launch
         p->vbwd = pick_variant("AAS_LMFB_WARPS_BWD", -1);
-        { const char* e = getenv("AAS_LMFB_STAGGER_NS"); p->stagger_ns = e ? atoi(e) : 0; }
-        int ml[kBins];
-        if (build_mel_band(mel, n_mels, 1, &p->fwd, ml) != 0) { st = AAS_LMFB_E_MEL; break; }
-        make_bwd_band(p->fwd, ml, &p->bwd, p->dlo);
+        if (build_fwd_tab(mel, n_mels, &p->fwd, p->ml) != 0) { st = AAS_LMFB_E_MEL; break; }
+        build_bwd_tab(p->fwd, p->ml, &p->bwd);
     } while (0);
     if (st != AAS_LMFB_OK && p) { delete p; p = nullptr; }
     if (status) *status = st;
@@ -536,26 +491,28 @@ namespace {
 
 // cudaFuncSetAttribute is per (function, device); do it once each so that launches inside
 // a CUDA-graph capture are pure stream work.
-int ensure_attrs(k1_fn fn) {
+int ensure_attrs(const void* fn, int smem) {
     static std::mutex mu;
     static std::set<std::pair<const void*, int> > done;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     std::lock_guard<std::mutex> lock(mu);
-    const std::pair<const void*, int> key((const void*)fn, dev);
+    const std::pair<const void*, int> key(fn, dev);
     if (done.count(key)) return 0;
-    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + kMaxMels * kTile * 4);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return (int)e;
     done.insert(key);
     return 0;
 }
 
-int launch_k1(const K1Variant& v, k1_fn fn, K1Args& a, const MelBand& mb, int n, cudaStream_t stream) {
+template <class Fn, class Tab>
+int launch_k1(const K1Variant& v, Fn fn, K1Args& a, const Tab& tab, bool bwd, int n, cudaStream_t stream) {
     if (!fn) return AAS_LMFB_E_FLAGS;
-    const int rc = ensure_attrs(fn);
+    const int smem = smem_bytes(bwd);
+    const int rc = ensure_attrs((const void*)fn, smem);
     if (rc) return rc;
     const long long total = (long long)n * a.tiles_per_utt;
     if (total <= 0) return AAS_LMFB_OK;
@@ -565,13 +522,12 @@ int launch_k1(const K1Variant& v, k1_fn fn, K1Args& a, const MelBand& mb, int n,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    const int smem = kSmemBytes + (v.dsmem ? mb.n_mels * kTile * 4 : 0);
     int per_sm = 233472 / (smem + 1024);                           // shared memory per SM / per-CTA footprint
     if (per_sm > v.ctas) per_sm = v.ctas;
     if (per_sm < 1) per_sm = 1;
     const long long resident = (long long)sms * per_sm;           // one persistent CTA per scratch slot
     const unsigned blocks = (unsigned)(total < resident ? total : resident);
-    fn<<<blocks, kTile * v.warps, smem, stream>>>(a, mb);
+    fn<<<blocks, kTile * v.warps, smem, stream>>>(a, tab);
     return (int)cudaPeekAtLastError();
 }
 
@@ -621,15 +577,13 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
 #ifdef LMFB_TIMELINE
     { const char* e = getenv(false ? "AAS_LMFB_TIMELINE_BWD" : "AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
 #endif
-    a.stagger_ns = plan->stagger_ns;
 
     const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
     const K1Variant& v = kVariants[plan->vfwd >= 0 ? plan->vfwd : (small ? kFwdVariantSmall : kFwdVariantBig)];
-    MelBand band = plan->fwd;
-    patch_strides(&band, a.msf, nullptr, 0);
-    split_filters(&band, v.warps);
+    FwdTab band = plan->fwd;
+    set_warp_ranges(&band, plan->ml, v.warps);
     rec(prof, 0, stream);
-    rc = launch_k1(v, v.fwd[mask], a, band, n, stream);
+    rc = launch_k1(v, v.fwd[mask], a, band, false, n, stream);
     rec(prof, 1, stream);
     if (rc) return rc;
     rec(prof, 2, stream);
@@ -701,14 +655,11 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
 #ifdef LMFB_TIMELINE
     { const char* e = getenv(true ? "AAS_LMFB_TIMELINE_BWD" : "AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
 #endif
-    a.stagger_ns = plan->stagger_ns;
 
     const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
     const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
-    MelBand band = plan->bwd;
-    patch_strides(&band, a.msf, plan->dlo, v.dsmem ? (unsigned)kTile : (unsigned)tmax);
     rec(prof, 0, stream);
-    rc = launch_k1(v, v.bwd[mask], a, band, n, stream);
+    rc = launch_k1(v, v.bwd[mask], a, plan->bwd, true, n, stream);
     rec(prof, 1, stream);
     return rc;
 }

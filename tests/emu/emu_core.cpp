@@ -13,21 +13,26 @@ namespace {
 
 template <int W, int MASK, bool BWD>
 void emu_tile(const float* wave_row, int len, int t0, const float* window, bool vec_ok,
-              const MelBand& mb, const float* mr, const float* mi, unsigned /*sf*/,
+              const typename TabOf<BWD>::Param& tab, const float* mr, const float* mi, unsigned msf,
               const float* dE, float* out, unsigned som, float* gr, float* gi, int tmax, int T,
               std::vector<float2>& S) {
-    Tables tb;
-    tables_fill(&tb, mb, mb.ent[1].moff, 0, 1);            // ent[1].moff == bytes per mask row
+    typename TabOf<BWD>::Smem sm;
+    for (int w = 0; w < W; ++w) tables_fill(&sm, tab, w, W, 0);
     window_fill(S.data(), window, 0, 1);
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
             StageLane sl;
-            stage_lane_init(lane, sl);
+            stage_lane_init(lane, S.data(), sl);
             const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;
             stage_tile<W>(w, lane, sl, wave_row, len, t0, n_rows, S.data(), vec_ok);
         }
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) fft_pass1<W>(w, S.data() + lane, S.data() + kTile);
+    // pass 2: a real warp runs its lanes in lockstep (all loads of a step before its stores); the
+    // emulation runs lane after lane, which is equivalent only if no lane's store can hit a word
+    // another lane of the same step still has to read.  The compact P rows overlap the float2
+    // words of OTHER lanes (same slot), so emulate the lockstep by double-buffering the scratch.
+    std::vector<float2> Sin(S);
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
             const int t = t0 + lane;
@@ -37,25 +42,30 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
             const float* mip = mi ? mi + t + clamp : nullptr;
             const float* dep = dE ? dE + t + clamp : nullptr;
             StepMasks first;
-            load_masks<MASK, BWD>(w, tb, mrp, mip, first);
-            fft_pass2<W, MASK, BWD, false>(w, S.data() + lane, tb, first, mrp, mip, dep, som * 4u,
+            load_masks<MASK, BWD>(sm.step[w], mrp, mip, msf * 4u, first);
+            fft_pass2<W, MASK, BWD>(w, Sin.data() + lane, reinterpret_cast<float*>(S.data()) + lane, sm, first,
+                                    mrp, mip, dep, som * 4u, msf * 4u,
                                     gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
         }
-    if (!BWD)
+    if constexpr (!BWD) {
+        for (int w = 0; w < W; ++w)
+            for (int lane = 0; lane < 32; ++lane)
+                phase3_walk<W>(w, reinterpret_cast<float*>(S.data()) + lane, sm, tab);
         for (int w = 0; w < W; ++w)
             for (int lane = 0; lane < 32; ++lane) {
                 const int t = t0 + lane;
-                phase3_fwd(w, S.data() + lane, tb, out + t, som * 4u, t < tmax, t < T);
+                phase3_finish<W>(w, reinterpret_cast<float*>(S.data()) + lane, tab, out + t, som * 4u, t < tmax, t < T);
             }
+    }
 }
 
 template <int W, int MASK>
 void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_utt, long long wave_stride,
                  const float* mask_r, const float* mask_i, long long msn, long long msf,
-                 const float* window, const MelBand& mb, float* out, const float* dE,
+                 const float* window, const FwdTab& ft, const BwdTab& bt, float* out, const float* dE,
                  float* gr, float* gi, int tmax, int vec_ok) {
     const int tiles = (tmax + kTile - 1) / kTile;
-    const int n_mels = mb.n_mels;
+    const int n_mels = ft.n_mels;
     std::vector<float2> S(kSlots * kPitch);
     for (int n = 0; n < n_utt; ++n)
         for (int tile = 0; tile < tiles; ++tile) {
@@ -81,10 +91,10 @@ void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_utt, long
             const float* mr = mask_r ? mask_r + (long long)n * msn : nullptr;
             const float* mi = mask_i ? mask_i + (long long)n * msn : nullptr;
             if (!bwd)
-                emu_tile<W, MASK, false>(wr, len, t0, window, vec_ok != 0, mb, mr, mi, (unsigned)msf, nullptr,
+                emu_tile<W, MASK, false>(wr, len, t0, window, vec_ok != 0, ft, mr, mi, (unsigned)msf, nullptr,
                                          out + nb, som, nullptr, nullptr, tmax, T, S);
             else
-                emu_tile<W, MASK, true>(wr, len, t0, window, vec_ok != 0, mb, mr, mi, (unsigned)msf, dE + nb,
+                emu_tile<W, MASK, true>(wr, len, t0, window, vec_ok != 0, bt, mr, mi, (unsigned)msf, dE + nb,
                                         nullptr, som, gr + (long long)n * msn, gi ? gi + (long long)n * msn : nullptr,
                                         tmax, T, S);
         }
@@ -95,22 +105,16 @@ int emu_k1_w(int bwd, int mask_mode, const float* wave, const int* lengths, int 
              long long wave_stride, const float* mask_r, const float* mask_i,
              long long msn, long long msf, const float* window, const float* mel, int n_mels,
              float* out, const float* dE, float* gr, float* gi, int tmax, int vec_ok) {
-    MelBand mb, mbb;
-    memset(&mb, 0, sizeof(mb));
+    FwdTab ft;
+    BwdTab bt;
     int ml[kBins];
-    uint8_t dlo[kBins];
-    if (build_mel_band(mel, n_mels, W, &mb, ml) != 0) return -5;
-    if (bwd) {
-        make_bwd_band(mb, ml, &mbb, dlo);
-        mb = mbb;
-        patch_strides(&mb, (unsigned)msf, dlo, (unsigned)tmax);
-    } else {
-        patch_strides(&mb, (unsigned)msf, nullptr, 0);
-    }
+    if (build_fwd_tab(mel, n_mels, &ft, ml) != 0) return -5;
+    build_bwd_tab(ft, ml, &bt);
+    set_warp_ranges(&ft, ml, W);
     switch (mask_mode) {
-        case kMaskNone:  emu_k1_impl<W, kMaskNone>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
-        case kMaskReim:  emu_k1_impl<W, kMaskReim>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
-        case kMaskPower: emu_k1_impl<W, kMaskPower>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mb, out, dE, gr, gi, tmax, vec_ok); break;
+        case kMaskNone:  emu_k1_impl<W, kMaskNone>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, ft, bt, out, dE, gr, gi, tmax, vec_ok); break;
+        case kMaskReim:  emu_k1_impl<W, kMaskReim>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, ft, bt, out, dE, gr, gi, tmax, vec_ok); break;
+        case kMaskPower: emu_k1_impl<W, kMaskPower>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, ft, bt, out, dE, gr, gi, tmax, vec_ok); break;
         default: return -4;
     }
     return 0;
@@ -118,7 +122,7 @@ int emu_k1_w(int bwd, int mask_mode, const float* wave, const int* lengths, int 
 
 }  // namespace
 
-// whole K1 (forward / backward), tile by tile, same control flow as lmfb_k1<>, for `warps` in {1,2,4,5}
+// whole K1 (forward / backward), tile by tile, same control flow as lmfb_k1<>, for `warps` in {1,2,3,4,5}
 extern "C" int emu_k1(int warps, int bwd, int mask_mode, const float* wave, const int* lengths, int n_utt,
                       long long wave_stride, const float* mask_r, const float* mask_i,
                       long long msn, long long msf, const float* window, const float* mel, int n_mels,
@@ -127,6 +131,7 @@ extern "C" int emu_k1(int warps, int bwd, int mask_mode, const float* wave, cons
     switch (warps) {
         case 1: CALL(1);
         case 2: CALL(2);
+        case 3: CALL(3);
         case 4: CALL(4);
         case 5: CALL(5);
     }
@@ -134,19 +139,18 @@ extern "C" int emu_k1(int warps, int bwd, int mask_mode, const float* wave, cons
     return -3;
 }
 
-extern "C" int emu_mel_band(const float* mel, int n_mels, int warps, float* wl, float* wh, int* ml, int* mbeg) {
-    MelBand mb;
-    memset(&mb, 0, sizeof(mb));
-    const int rc = build_mel_band(mel, n_mels, warps, &mb, ml);
-    for (int f = 0; f < kBins; ++f) { wl[f] = mb.ent[f].wl; wh[f] = mb.ent[f].wh; }
-    for (int w = 0; w <= kMaxW; ++w) mbeg[w] = mb.mbeg[w];
-    if (rc == 0) {                      // the filter ranges must tile the bins in order
-        int f = 0;
-        for (int m = 0; m < n_mels; ++m)
-            for (; f < mb.fend[m]; ++f) if (ml[f] != m) return -100 - m;
-        for (; f < kBins; ++f) if (ml[f] != n_mels) return -300;
-        for (int w = 0; w < warps; ++w) if (mb.mbeg[w] > mb.mbeg[w + 1]) return -400;
-        if (mb.mbeg[0] != 0 || mb.mbeg[warps] != n_mels) return -401;
+extern "C" int emu_mel_band(const float* mel, int n_mels, int warps, float* wl, float* wh, int* ml, int* lohi) {
+    FwdTab ft;
+    const int rc = build_fwd_tab(mel, n_mels, &ft, ml);
+    if (rc != 0) return rc;
+    set_warp_ranges(&ft, ml, warps);
+    for (int f = 0; f < kBins; ++f) { wl[f] = ft.w[f].x; wh[f] = ft.w[f].y; }
+    for (int w = 0; w < kMaxW; ++w) { lohi[2 * w] = ft.lo[w]; lohi[2 * w + 1] = ft.hi[w]; }
+    int m = ml[0];                      // the advance counts must reproduce ml
+    for (int f = 1; f < kBins; ++f) {
+        m += (int)ft.adv[f];
+        if (m != ml[f]) return -100 - f;
+        if (((ft.hmask[f >> 3] >> (f & 7)) & 1) != (ft.adv[f] != 0)) return -300 - f;
     }
-    return rc;
+    return 0;
 }

@@ -75,7 +75,7 @@ def test_emulated_stft_matches_oracle(emu, length, sym):
             assert np.abs(got - ref).max() / scale < 3e-6, (lo, which)
 
 
-@pytest.mark.parametrize("warps", [1, 2, 4, 5])
+@pytest.mark.parametrize("warps", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("mode", ["reim", "power", "none"])
 def test_emulated_k1_forward_and_backward(emu, mode, warps):
     b = _synth.make_batch(3, 5000, seed=17, ragged=True, tonal=(mode == "power"))
@@ -111,9 +111,9 @@ def test_mel_band_tables(emu):
         for warps in (1, 2, 4, 5):
             mel = np.ascontiguousarray(orc.mel_filterbank(n_mels=n_mels), dtype=np.float32)
             wl = np.zeros(161, np.float32); wh = np.zeros(161, np.float32)
-            ml = np.zeros(161, np.int32); mbeg = np.zeros(9, np.int32)
+            ml = np.zeros(161, np.int32); lohi = np.zeros(16, np.int32)
             assert emu.emu_mel_band(mel.ctypes.data, n_mels, warps, wl.ctypes.data, wh.ctypes.data,
-                                    ml.ctypes.data, mbeg.ctypes.data) == 0
+                                    ml.ctypes.data, lohi.ctypes.data) == 0
             rebuilt = np.zeros_like(mel)
             for f in range(161):
                 if ml[f] < n_mels:
@@ -124,6 +124,6 @@ def test_mel_band_tables(emu):
             assert np.all(np.diff(ml) >= 0)
     dense = np.ones((40, 161), dtype=np.float32)
     wl = np.zeros(161, np.float32); wh = np.zeros(161, np.float32)
-    ml = np.zeros(161, np.int32); mbeg = np.zeros(9, np.int32)
+    ml = np.zeros(161, np.int32); lohi = np.zeros(16, np.int32)
     assert emu.emu_mel_band(dense.ctypes.data, 40, 4, wl.ctypes.data, wh.ctypes.data, ml.ctypes.data,
-                            mbeg.ctypes.data) == -1
+                            lohi.ctypes.data) == -1

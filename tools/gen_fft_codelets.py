@@ -215,11 +215,11 @@ def main():
     parts.append("#    define LMFB_HD inline __attribute__((always_inline))")
     parts.append("#  endif")
     parts.append("#endif")
-    parts.append("#ifndef LMFB_CONST")
+    parts.append("#ifndef LMFB_CX")
     parts.append("#  ifdef __CUDACC__")
-    parts.append("#    define LMFB_CONST __constant__ const")
+    parts.append("#    define LMFB_CX __host__ __device__ constexpr")
     parts.append("#  else")
-    parts.append("#    define LMFB_CONST static const")
+    parts.append("#    define LMFB_CX constexpr")
     parts.append("#  endif")
     parts.append("#endif")
     parts.append("#include <math.h>")
@@ -228,32 +228,26 @@ def main():
         code, flops = gen_codelet(n)
         parts.append(f"// fft{n}: {flops} floating-point operations (fma counted once)")
         parts.append(code)
-    # split twiddles for the real-FFT post-pass: theta = 2*pi*f/320, f = (96*k1 + 65*k2) mod 160
-    sin_rows, cos_rows = [], []
+    # split twiddles for the real-FFT post-pass, as compile-time functions of the bin: every use
+    # has a constant bin index (pass 2 is fully unrolled), so the values become immediates
+    sins = ", ".join(lit(math.sin(2.0 * math.pi * f / 320.0)) for f in range(161))
+    coss = ", ".join(lit(math.cos(2.0 * math.pi * f / 320.0)) for f in range(161))
+    parts.append("// real-split twiddles sin/cos(2*pi*f/320) of bin f, usable in constant expressions")
+    parts.append("LMFB_CX float split_sin(int f) {\n    constexpr float t[161] = {" + sins + "};\n    return t[f];\n}")
+    parts.append("LMFB_CX float split_cos(int f) {\n    constexpr float t[161] = {" + coss + "};\n    return t[f];\n}")
+    # the same per pass-2 step (k2) and output (k1), for code that is rolled over k2: constant-bank
+    # tables read with a warp-uniform index
+    parts.append("#ifdef __CUDACC__\n#  define LMFB_CONST __constant__ const\n#else\n#  define LMFB_CONST static const\n#endif")
+    rows_s, rows_c, rows_f = [], [], []
     for k2 in range(17):
         fs = [(96 * k1 + 65 * k2) % 160 for k1 in range(5)]
-        sin_rows.append(", ".join(lit(math.sin(2.0 * math.pi * f / 320.0)) for f in fs))
-        cos_rows.append(", ".join(lit(math.cos(2.0 * math.pi * f / 320.0)) for f in fs))
-    parts.append("// real-split twiddles (sin, cos of 2*pi*f/320) for bin f = (96*k1 + 65*k2) mod 160, [k2][k1]")
-    parts.append("LMFB_CONST float kSplitSin[17][5] = {\n  {" + "},\n  {".join(sin_rows) + "}};")
-    parts.append("LMFB_CONST float kSplitCos[17][5] = {\n  {" + "},\n  {".join(cos_rows) + "}};")
-    # bin handled by (k2, k1) in pass 2, and the float offset of bin f inside a scratch column
-    rows = []
-    for k2 in range(17):
-        rows.append(", ".join(str((96 * k1 + 65 * k2) % 160) for k1 in range(5)))
-    parts.append("// bin f = (96*k1 + 65*k2) mod 160 produced by pass-2 step k2, output k1")
-    parts.append("LMFB_CONST unsigned char kBinOf[17][5] = {\n  {" + "},\n  {".join(rows) + "}};")
-    pitch = 33
-    offs = []
-    for f in range(161):
-        if f == 0:
-            offs.append(0)
-        elif f == 160:
-            offs.append(1)
-        else:
-            offs.append(((f % 5) * 32 + (f % 32)) * pitch * 2)
-    parts.append("// float offset of bin f in a finished scratch column (slot*kPitch*2; bin 160 is slot 0 .y)")
-    parts.append("LMFB_CONST unsigned short kBinOff[161] = {" + ", ".join(str(o) for o in offs) + "};")
+        rows_s.append(", ".join(lit(math.sin(2.0 * math.pi * f / 320.0)) for f in fs) + ", 0.0f, 0.0f, 0.0f")
+        rows_c.append(", ".join(lit(math.cos(2.0 * math.pi * f / 320.0)) for f in fs) + ", 0.0f, 0.0f, 0.0f")
+        rows_f.append(", ".join(str(f) for f in fs) + ", 0, 0, 0")
+    parts.append("// [k2][k1] (rows padded to 8 words): split twiddles and bin f = (96*k1 + 65*k2) mod 160")
+    parts.append("LMFB_CONST float kStepSin[17][8] = {\n  {" + "},\n  {".join(rows_s) + "}};")
+    parts.append("LMFB_CONST float kStepCos[17][8] = {\n  {" + "},\n  {".join(rows_c) + "}};")
+    parts.append("LMFB_CONST unsigned kStepBin[17][8] = {\n  {" + "},\n  {".join(rows_f) + "}};")
     parts.append("}  // namespace aas_lmfb")
     with open(OUT, "w") as f:
         f.write("\n".join(parts) + "\n")

@@ -4,17 +4,21 @@ Run on the GPU box:  python tools/timeline.py [workload]"""
 import os, subprocess, sys, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import torch
 from aas_enhancement_b200 import build as B
-lib_dbg = os.path.join(ROOT, "gpurun_out", "libaas_lmfb_timeline.so")
-os.makedirs(os.path.dirname(lib_dbg), exist_ok=True)
-extra = [a for a in sys.argv[2:] if a.startswith("-D")]
-subprocess.check_call([B.find_nvcc()] + B.NVCC_FLAGS + ["-DLMFB_TIMELINE"] + extra + [B.SRC, "-o", lib_dbg])
-print("debug build flags:", extra)
+# built in-tree (git-ignored *.so) so that a copy made on the CPU container travels to the GPU box:
+#   python tools/timeline.py --build-only [-D...]
+lib_dbg = os.path.join(ROOT, "aas_enhancement_b200", "libaas_lmfb_timeline%s.so" % os.environ.get("TL_TAG", ""))
+extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+if "--build-only" in sys.argv or not os.path.exists(lib_dbg):
+    subprocess.check_call([B.find_nvcc()] + B.NVCC_FLAGS + ["-DLMFB_TIMELINE"] + extra + [B.SRC, "-o", lib_dbg])
+    print("debug build flags:", extra)
+    if "--build-only" in sys.argv:
+        sys.exit(0)
+import torch
 from aas_enhancement_b200 import _lib
 _lib.LIB_PATH = lib_dbg
 from aas_enhancement_b200 import LMFBFrontEnd
-wl = sys.argv[1] if len(sys.argv) > 1 else "sweep"
+wl = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "sweep"
 n, samples = (256, 160000) if wl == "sweep" else (30, 96000)
 tmax = 1 + samples // 160
 dev = torch.device("cuda", 0)
