@@ -9,7 +9,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libaas_lmfb.so")
+LIB_PATH = os.environ.get("AAS_LMFB_LIB") or os.path.join(HERE, "libaas_lmfb.so")   # env: development A/B only
 
 ABI_VERSION = 1
 N_FFT, HOP, N_BINS = 320, 160, 161

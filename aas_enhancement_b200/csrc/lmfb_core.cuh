@@ -326,7 +326,9 @@ LMFB_HD void fft_pass1(int w, float2* __restrict__ col, const float2* __restrict
             const float2 v = p[i * kPitch], g = wn[i * kPitch];
             xr[i] = v.x * g.x; xi[i] = v.y * g.y;
         }
+#ifndef LMFB_DBG_NOFFT
         fft32(xr, xi);
+#endif
 #pragma unroll
         for (int i = 0; i < 32; ++i) p[i * kPitch] = make_float2(xr[i], xi[i]);
     }
@@ -488,8 +490,13 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
     }
     StepK k;
     load_step(sm.step[k2], k);
+#ifndef LMFB_DBG_NOFFT
     dft5(ar, ai, Ar, Ai);
     dft5(br, bi, Br, Bi);
+#else
+#pragma unroll
+    for (int n = 0; n < 5; ++n) { Ar[n] = ar[n]; Ai[n] = ai[n]; Br[n] = br[n]; Bi[n] = bi[n]; }
+#endif
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
         const int kp = (5 - k1) % 5;
@@ -634,18 +641,9 @@ LMFB_HD void phase3_finish(int w, const float* __restrict__ pl, const FwdTab& ta
     }
 }
 
-// L2 prefetch of the (32+1)*160 samples of a tile (165 lines of 128 B), `idx`/`cnt` = this
-// thread's index / the number of threads sharing the job
-LMFB_HD void prefetch_wave_l2(int idx, int cnt, const float* __restrict__ wave_row, int len, int t0) {
-    long long lo = (long long)(t0 - 1) * kHop, hi = (long long)(t0 + kTile) * kHop;
-    if (lo < 0) lo = 0;
-    if (hi > len) hi = len;
-#pragma unroll 1
-    for (long long i = lo + idx * 32; i < hi; i += (long long)cnt * 32) LMFB_PREFETCH_L2(wave_row + i);
-}
-
 // L2 prefetch of the row segments a tile will read: threads take rows idx, idx+cnt, ...; a
-// 128-byte segment may straddle two lines, so both ends are touched.
+// 128-byte segment may straddle two lines, so both ends are touched.  (Touching all five sectors
+// of a row was measured: slower, the extra prefetches cost more load/store-unit time than they save.)
 LMFB_HD void prefetch_rows_l2(int idx, int cnt, const float* __restrict__ base, unsigned sf, int rows, int t0, int tmax) {
     if (t0 >= tmax) return;
     const int last = (t0 + kTile <= tmax ? t0 + kTile : tmax) - 1;

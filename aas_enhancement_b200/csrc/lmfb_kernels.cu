@@ -102,15 +102,8 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (BWD) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
-        // ... and the next tile's samples, so that its staging copies hit L2
-        {
-            const int nt = tile + gridDim.x;
-            if (nt < a.total_tiles) {
-                const int nn = nt / a.tiles_per_utt;
-                prefetch_wave_l2(threadIdx.x, kTile * W, a.wave + (long long)nn * a.wave_stride, a.lengths[nn],
-                                 (nt - nn * a.tiles_per_utt) * kTile);
-            }
-        }
+        // (prefetching the NEXT tile's samples was measured and dropped: in the backward kernel the
+        // lines are evicted before use and the wave is read from DRAM twice, 707 -> 578 MB per launch)
 #endif
 
 #ifdef LMFB_TIMELINE
@@ -418,7 +411,7 @@ static const K1Variant kVariants[] = {
 #ifdef LMFB_ONLY_W3
     LMFB_VARIANT(3, 5),
 #else
-    LMFB_VARIANT(3, 5), LMFB_VARIANT(2, 5), LMFB_VARIANT(4, 4),
+    LMFB_VARIANT(3, 5), LMFB_VARIANT(2, 5), LMFB_VARIANT(4, 4), LMFB_VARIANT(5, 3),
 #endif
 };
 // Defaults measured on B200 (profiles/): 3 warps per tile (128 registers, 15 warps per SM).

@@ -265,7 +265,10 @@ def run_ours(args):
     k_avg = {k: sum(v) / len(v) for k, v in k_ms.items()}
 
     # ---- e2e: public autograd API, pinned host buffers, copies inside the timed region
-    e2e = measure_e2e(fe, n, samples, tmax, n_mels, audio_s, dev, min(max(args.steps, 20), 200), world)
+    if args.no_e2e:                                          # development A/B runs only: not a bench line
+        e2e = {"value": float("nan"), "unit": "audio-s/s", "skipped": True}
+    else:
+        e2e = measure_e2e(fe, n, samples, tmax, n_mels, audio_s, dev, min(max(args.steps, 20), 200), world)
 
     if rank != 0:
         if world > 1:
@@ -514,6 +517,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="chime4_30x6s", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel A/B runs; not a valid bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 20

@@ -106,6 +106,31 @@ def test_emulated_k1_forward_and_backward(emu, mode, warps):
         assert orc.rel_err(gi, g_ref["grad_mask_i"]) < 2e-5
 
 
+@pytest.mark.parametrize("n_mels,warps", [(80, 3), (64, 5), (2, 4)])
+def test_emulated_forward_other_bases(emu, n_mels, warps):
+    """Bases in which several filters end on the same bin (hand-over of more than one filter per
+    bin, the rolled phase-3 path) and the two-filter minimum."""
+    b = _synth.make_batch(2, 4000, seed=n_mels, ragged=True)
+    mel = orc.mel_filterbank(n_mels=n_mels) if n_mels > 2 else np.stack([np.linspace(1, 0, 161), np.linspace(0, 1, 161)])
+    window = orc.hamming_window()
+    mel32 = mel.astype(np.float32).astype(np.float64)
+    win32 = window.astype(np.float32).astype(np.float64)
+    y_ref, fl = orc.lmfb_forward(b["wave"], b["lengths"], b["mask_r"], b["mask_i"], mel32, win32,
+                                 mask_mode="reim", cmvn_mode="none")
+    y, _, _ = _k1(emu, warps, 0, "reim", b, mel, window)
+    assert not np.isnan(y).any()
+    assert orc.rel_err(y, y_ref) < 2e-5
+    g = np.random.RandomState(3).randn(*y_ref.shape)
+    g_ref = orc.lmfb_grads(b["wave"], b["lengths"], b["mask_r"], b["mask_i"], g, mel32, win32,
+                           mask_mode="reim", cmvn_mode="none")
+    dE = g * np.exp(-y_ref)
+    for i in range(2):
+        dE[i, :, fl[i]:] = 0.0
+    _, gr, gi = _k1(emu, warps, 1, "reim", b, mel, window, dE=dE)
+    assert orc.rel_err(gr, g_ref["grad_mask_r"]) < 2e-5
+    assert orc.rel_err(gi, g_ref["grad_mask_i"]) < 2e-5
+
+
 def test_mel_band_tables(emu):
     for n_mels in (40, 23, 64, 80):
         for warps in (1, 2, 4, 5):
