@@ -374,33 +374,38 @@ LMFB_HD float masked_power(float2 x, float mr, float mi) {
 }
 
 // ---------------------------------------------------------------------------------------
-// table fill, once per persistent CTA.  The source lives in constant banks (kernel parameter and
-// __constant__ tables), which only serve a warp quickly when all lanes read the SAME address:
-// every warp walks a contiguous share of the words with a warp-uniform index and lane 0 stores.
+// table fill, once per persistent CTA: every thread copies its share of the words of the kernel
+// parameter (lane-indexed constant loads: a handful per thread, all independent) and computes its
+// share of the per-step constants (the twiddles are sin/cos(pi f / 160), evaluated with sincospif:
+// no table to read at all).  Together with window_fill() this is the whole prologue, ~1 us;
+// walking the constant bank with warp-uniform indices and storing from lane 0 was measured at
+// 6-8 us per CTA (a quarter of a one-wave launch).
 // ---------------------------------------------------------------------------------------
-LMFB_HD void copy_words(uint32_t* dst, const uint32_t* src, int words, int warp, int nwarps, int lane) {
-    const int per = (words + nwarps - 1) / nwarps;
-    const int i0 = warp * per, i1 = i0 + per < words ? i0 + per : words;
-#pragma unroll 8
-    for (int i = i0; i < i1; ++i) { const uint32_t v = src[i]; if (lane == 0) dst[i] = v; }
+LMFB_HD void copy_words(uint32_t* dst, const uint32_t* src, int words, int tid, int nthreads) {
+    for (int i = tid; i < words; i += nthreads) dst[i] = src[i];
 }
-LMFB_HD void fill_steps(StepEnt* st, int warp, int nwarps, int lane) {
-    for (int i = warp; i < 17 * 5; i += nwarps) {
+LMFB_HD void fill_steps(StepEnt* st, int tid, int nthreads) {
+    for (int i = tid; i < 17 * 5; i += nthreads) {
         const int k2 = i / 5, k1 = i - 5 * k2;
-        const uint32_t f = kStepBin[k2][k1];
-        const float sn = kStepSin[k2][k1], cs = kStepCos[k2][k1];
-        if (lane == 0) { st[k2].f[k1] = f; st[k2].sn[k1] = sn; st[k2].cs[k1] = cs; }
+        const int f = bin_of(k2, k1);
+        float sn, cs;
+#ifdef __CUDACC__
+        sincospif((float)f * (1.0f / 160.0f), &sn, &cs);
+#else
+        sn = (float)sin(3.14159265358979323846 * f / 160.0); cs = (float)cos(3.14159265358979323846 * f / 160.0);
+#endif
+        st[k2].f[k1] = (uint32_t)f; st[k2].sn[k1] = sn; st[k2].cs[k1] = cs;
     }
 }
-LMFB_HD void tables_fill(FwdSmem* sm, const FwdTab& tab, int warp, int nwarps, int lane) {
-    fill_steps(sm->step, warp, nwarps, lane);
-    copy_words(reinterpret_cast<uint32_t*>(sm->w), reinterpret_cast<const uint32_t*>(tab.w), 2 * kBins, warp, nwarps, lane);
+LMFB_HD void tables_fill(FwdSmem* sm, const FwdTab& tab, int tid, int nthreads) {
+    fill_steps(sm->step, tid, nthreads);
+    copy_words(reinterpret_cast<uint32_t*>(sm->w), reinterpret_cast<const uint32_t*>(tab.w), 2 * kBins, tid, nthreads);
     copy_words(reinterpret_cast<uint32_t*>(sm->hmask), reinterpret_cast<const uint32_t*>(tab.hmask),
-               (kGroups + 4 + kBins + 3) / 4, warp, nwarps, lane);            // hmask and adv are adjacent in both structs
+               (kGroups + 4 + kBins + 3) / 4, tid, nthreads);                // hmask and adv are adjacent in both structs
 }
-LMFB_HD void tables_fill(BwdSmem* sm, const BwdTab& tab, int warp, int nwarps, int lane) {
-    fill_steps(sm->step, warp, nwarps, lane);
-    copy_words(reinterpret_cast<uint32_t*>(sm->w), reinterpret_cast<const uint32_t*>(tab.w), 17 * 5 * 4 + 17 * 5 * 2, warp, nwarps, lane);
+LMFB_HD void tables_fill(BwdSmem* sm, const BwdTab& tab, int tid, int nthreads) {
+    fill_steps(sm->step, tid, nthreads);
+    copy_words(reinterpret_cast<uint32_t*>(sm->w), reinterpret_cast<const uint32_t*>(tab.w), 17 * 5 * 4 + 17 * 5 * 2, tid, nthreads);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -530,26 +535,41 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
     }
 }
 
-// pass 2 over the 17 column pairs, dealt round-robin to the W warps, in pairs: the global inputs
-// of a warp's next step are loaded into a second register set while the current step is computed
-// (ping-pong, no register moves).  `a` must already hold the masks of the warp's first step
-// (k2 = w): the caller issues that load before the block barrier that ends pass 1, so its latency
-// hides behind the barrier.
-template <int W, int MASK, bool BWD, class SM>
-LMFB_HD void fft_pass2(int w, float2* __restrict__ col, float* __restrict__ pl, const SM& sm, StepMasks& a,
+// pass 2 over the 17 column pairs, dealt round-robin to the W warps.  The global inputs of a warp's
+// steps are loaded AHEAD register sets in advance (AHEAD = 1: ping-pong; AHEAD = 2: three sets in
+// rotation, the loop body is unrolled over the rotation so that no register ever moves): bytes in
+// flight per warp are what bounds these kernels (throughput = bytes in flight / ~2000 cycles of
+// loaded memory latency), and these are the only registers that can buy any.
+// `m[0 .. AHEAD-1]` must already hold the masks of the warp's first AHEAD steps (k2 = w, w + W, ...):
+// the caller issues those loads before the block barrier that ends pass 1.
+template <int AHEAD>
+struct MaskSets { StepMasks m[AHEAD + 1]; };
+
+template <int W, int MASK, bool BWD, int AHEAD, class SM>
+LMFB_HD void preload_masks(int w, const SM& sm, const float* __restrict__ mr, const float* __restrict__ mi,
+                           unsigned msf_bytes, MaskSets<AHEAD>& ms) {
+#pragma unroll
+    for (int i = 0; i < AHEAD; ++i)
+        if (w + i * W <= 16) load_masks<MASK, BWD>(sm.step[w + i * W], mr, mi, msf_bytes, ms.m[i]);
+}
+
+template <int W, int MASK, bool BWD, int AHEAD, class SM>
+LMFB_HD void fft_pass2(int w, float2* __restrict__ col, float* __restrict__ pl, const SM& sm, MaskSets<AHEAD>& ms,
                        const float* __restrict__ mr, const float* __restrict__ mi,
                        const float* __restrict__ dE, unsigned sem_bytes, unsigned msf_bytes,
                        float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
     const float* de1 = at_row(dE, 1u, sem_bytes);
-    StepMasks b;
+    constexpr int R = AHEAD + 1;                            // register sets in rotation
 #pragma unroll 1
-    for (int k2 = w; k2 <= 16; k2 += 2 * W) {
-        const bool has_b = k2 + W <= 16;
-        if (has_b) load_masks<MASK, BWD>(sm.step[k2 + W], mr, mi, msf_bytes, b);
-        pass2_step<MASK, BWD>(k2, col, pl, sm, a, dE, de1, sem_bytes, msf_bytes, gr, gi, inrow);
-        if (has_b) {
-            if (k2 + 2 * W <= 16) load_masks<MASK, BWD>(sm.step[k2 + 2 * W], mr, mi, msf_bytes, a);
-            pass2_step<MASK, BWD>(k2 + W, col, pl, sm, b, dE, de1, sem_bytes, msf_bytes, gr, gi, inrow);
+    for (int k2 = w; k2 <= 16; k2 += R * W) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int k = k2 + i * W;                       // this step; its masks are in set i
+            if (k <= 16) {
+                const int kn = k + AHEAD * W;               // the step AHEAD later goes to set (i + AHEAD) mod R
+                if (kn <= 16) load_masks<MASK, BWD>(sm.step[kn], mr, mi, msf_bytes, ms.m[(i + AHEAD) % R]);
+                pass2_step<MASK, BWD>(k, col, pl, sm, ms.m[i], dE, de1, sem_bytes, msf_bytes, gr, gi, inrow);
+            }
         }
     }
 }

@@ -42,14 +42,68 @@ struct K1Args {
     int            total_tiles;
     int            vec_ok;
     long long*     timeline;   // debug builds (-DLMFB_TIMELINE) only: per-warp phase clocks
+    int            dynamic;    // tiles handed out by cluster launch control (grid = one CTA per tile)
 };
 
 constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
+
+// ---- dynamic tile scheduling with cluster launch control (sm_100) -------------------------------
+// The grid has one CTA per tile, but only the resident CTAs ever run: a running CTA asks the
+// hardware to CANCEL a CTA that has not been launched yet and, when that succeeds, does that CTA's
+// tile itself (persistent CTAs without a global work counter: nothing to allocate or reset, safe
+// across streams).  Measured with a static round-robin deal of the tiles to 740 persistent CTAs:
+// the CTAs of one launch finish between 163 and 212 us (mean 185): 13 % of the kernel is spent
+// waiting for the slowest SMs.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LMFB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LMFB_DONE;\n\t"
+        "bra LMFB_WAIT;\n\t"
+        "LMFB_DONE:\n\t"
+        "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one thread: request the cancellation of a pending CTA; 16 bytes of answer land in *resp and complete *bar
+__device__ __forceinline__ void clc_request(uint4* resp, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 16;" :: "r"(smem_u32(bar)) : "memory");
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 :: "r"(smem_u32(resp)), "r"(smem_u32(bar)) : "memory");
+}
+// every thread: was a CTA cancelled for us, and which one
+__device__ __forceinline__ bool clc_answer(const uint4* resp, int& ctaid_x) {
+    unsigned ok, x;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p1;\n\t"
+        ".reg .b128 r;\n\t"
+        "mov.u32 %1, 0;\n\t"
+        "ld.shared.b128 r, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+        "selp.u32 %0, 1, 0, p1;\n\t"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %1, r;\n\t"
+        "}" : "=r"(ok), "=r"(x) : "r"(smem_u32(resp)) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // our read before the next asynchronous write
+    ctaid_x = (int)x;
+    return ok != 0;
+}
 
 template <int MASK, bool BWD, int W, int CTAS>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf<BWD>::Param tab) {
     typedef typename TabOf<BWD>::Smem SM;
+#ifndef LMFB_AHEAD_FWD
+#define LMFB_AHEAD_FWD 2
+#endif
+#ifndef LMFB_AHEAD_BWD
+#define LMFB_AHEAD_BWD 1
+#endif
+    constexpr int AHEAD = BWD ? LMFB_AHEAD_BWD : LMFB_AHEAD_FWD;   // mask register sets loaded ahead in pass 2
     extern __shared__ __align__(16) float2 S[];
     SM& sm = *reinterpret_cast<SM*>(reinterpret_cast<char*>(S) + kScratchBytes);
 #ifdef LMFB_TIMELINE
@@ -62,14 +116,31 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
     StageLane sl;
     stage_lane_init(lane, S, sl);
     window_fill(S, a.window, threadIdx.x, kTile * W);          // pad column of the scratch <- window table
-    tables_fill(&sm, tab, w, W, lane);                         // visible after the first block barrier
+    tables_fill(&sm, tab, threadIdx.x, kTile * W);             // visible after the first block barrier
     float2* col = S + lane;
     float*  pl  = reinterpret_cast<float*>(S) + lane;
     const unsigned msf_bytes = a.msf * 4u;
     const unsigned som = (unsigned)a.tmax, som_bytes = som * 4u;
 
-    // persistent CTA: tiles are dealt round-robin, neighbouring tiles run at the same time
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+#ifdef LMFB_TIMELINE
+    unsigned long long gt_loop;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_loop));
+    int n_done = 0;
+#endif
+    // scheduler state behind the tables: the answer of the launch-control unit and its barrier
+    uint4*    clc_resp = reinterpret_cast<uint4*>(reinterpret_cast<char*>(&sm) + sizeof(SM));
+    uint64_t* clc_bar  = reinterpret_cast<uint64_t*>(clc_resp + 1);
+    unsigned  clc_phase = 0;
+    if (a.dynamic) {
+        if (threadIdx.x == 0) mbar_init(clc_bar, 1);
+        __syncthreads();
+    }
+    // persistent CTA.  dynamic: the next tile is whichever pending CTA the hardware cancels for us
+    // (asked for at the start of a tile, read at its end); static: round-robin over the grid.
+    // Either way neighbouring tiles run at the same time, so the sectors they share hit L2.
+    for (int tile = blockIdx.x; tile < a.total_tiles; ) {
+      if (a.dynamic && threadIdx.x == 0) clc_request(clc_resp, clc_bar);
+      do {
         const int n   = tile / a.tiles_per_utt;
         const int t0  = (tile - n * a.tiles_per_utt) * kTile;
         const int t   = t0 + lane;
@@ -94,7 +165,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
                     }
                 }
             }
-            continue;
+            break;
         }
 
 #ifndef LMFB_DBG_NOPREFETCH
@@ -132,12 +203,12 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         float* gi = a.gi + moff;
         float* po = a.out + row_nm;
         LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
-        StepMasks first;                            // issued before the barrier: its latency hides behind it
-        load_masks<MASK, BWD>(sm.step[w], mr, mi, msf_bytes, first);
+        MaskSets<AHEAD> ms;                         // issued before the barrier: the latency hides behind it
+        preload_masks<W, MASK, BWD, AHEAD>(w, sm, mr, mi, msf_bytes, ms);
         LMFB_TICK(3);
         __syncthreads();
         LMFB_TICK(4);
-        fft_pass2<W, MASK, BWD>(w, col, pl, sm, first, mr, mi, de, som_bytes, msf_bytes, gr, gi, inrow);
+        fft_pass2<W, MASK, BWD, AHEAD>(w, col, pl, sm, ms, mr, mi, de, som_bytes, msf_bytes, gr, gi, inrow);
         LMFB_TICK(5);
         if constexpr (!BWD) {
             __syncthreads();
@@ -151,24 +222,39 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         else tl[6] = tl[5];
 #endif
         LMFB_TICK(7);
-        __syncthreads();                            // the scratch is free for the next tile
 #ifdef LMFB_TIMELINE
-        if (a.timeline && lane == 0 && blockIdx.x < 64 && tile < (int)gridDim.x * 8) {
-            long long* dst = a.timeline + ((long long)(tile / gridDim.x) * 64 + blockIdx.x) * (W * 8) + w * 8;
+        if (a.timeline && lane == 0 && blockIdx.x < 64 && n_done < 8) {
+            long long* dst = a.timeline + ((long long)n_done * 64 + blockIdx.x) * (W * 8) + w * 8;
             for (int i = 0; i < 8; ++i) dst[i] = tl[i];
         }
-        // second view: every CTA's first tile, stamped with the global nanosecond timer
-        if (a.timeline && lane == 0 && w == 0 && tile == (int)blockIdx.x && blockIdx.x < 1024) {
-            unsigned long long gt;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-            long long* dst = a.timeline + 8 * 64 * 8 * 8 + (long long)blockIdx.x * 4;
-            dst[0] = (long long)gt;                 // end of the tile (ns)
-            dst[1] = 0;
-            dst[2] = (long long)gt_entry;           // kernel entry of this CTA (ns)
-            dst[3] = 0;
-        }
 #endif
+      } while (false);
+      if (a.dynamic) {
+          mbar_wait(clc_bar, clc_phase);
+          clc_phase ^= 1u;
+          int next;
+          tile = clc_answer(clc_resp, next) ? next : a.total_tiles;
+      } else {
+          tile += gridDim.x;
+      }
+#ifdef LMFB_TIMELINE
+      ++n_done;
+#endif
+      __syncthreads();                              // the scratch (and the scheduler's answer) is free for the next tile
     }
+#ifdef LMFB_TIMELINE
+    // second view: every CTA's life, stamped with the global nanosecond timer
+    if (a.timeline && lane == 0 && w == 0 && blockIdx.x < 1024) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        long long* dst = a.timeline + 8 * 64 * 8 * 8 + (long long)blockIdx.x * 4;
+        dst[0] = (long long)gt;                     // end of the CTA (ns)
+        dst[1] = (long long)gt_loop;                // start of its tile loop, after the prologue (ns)
+        dst[2] = (long long)gt_entry;               // kernel entry of this CTA (ns)
+        unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        dst[3] = (long long)smid | ((long long)n_done << 32);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------ K2
@@ -504,7 +590,7 @@ int ensure_attrs(const void* fn, int smem) {
 template <class Fn, class Tab>
 int launch_k1(const K1Variant& v, Fn fn, K1Args& a, const Tab& tab, bool bwd, int n, cudaStream_t stream) {
     if (!fn) return AAS_LMFB_E_FLAGS;
-    const int smem = smem_bytes(bwd);
+    const int smem = smem_bytes(bwd) + 32;                         // + the scheduler's answer and barrier
     const int rc = ensure_attrs((const void*)fn, smem);
     if (rc) return rc;
     const long long total = (long long)n * a.tiles_per_utt;
@@ -519,7 +605,10 @@ int launch_k1(const K1Variant& v, Fn fn, K1Args& a, const Tab& tab, bool bwd, in
     if (per_sm > v.ctas) per_sm = v.ctas;
     if (per_sm < 1) per_sm = 1;
     const long long resident = (long long)sms * per_sm;           // one persistent CTA per scratch slot
-    const unsigned blocks = (unsigned)(total < resident ? total : resident);
+    // more tiles than resident CTAs: one CTA per tile, the resident ones take over the pending ones
+    static const bool use_clc = []{ const char* e = getenv("AAS_LMFB_SCHED"); return !(e && strcmp(e, "static") == 0); }();
+    a.dynamic = (use_clc && total > resident) ? 1 : 0;
+    const unsigned blocks = (unsigned)(a.dynamic || total < resident ? total : resident);
     fn<<<blocks, kTile * v.warps, smem, stream>>>(a, tab);
     return (int)cudaPeekAtLastError();
 }

@@ -17,7 +17,7 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
               const float* dE, float* out, unsigned som, float* gr, float* gi, int tmax, int T,
               std::vector<float2>& S) {
     typename TabOf<BWD>::Smem sm;
-    for (int w = 0; w < W; ++w) tables_fill(&sm, tab, w, W, 0);
+    tables_fill(&sm, tab, 0, 1);
     window_fill(S.data(), window, 0, 1);
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
@@ -41,9 +41,10 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
             const float* mrp = mr ? mr + t + clamp : nullptr;
             const float* mip = mi ? mi + t + clamp : nullptr;
             const float* dep = dE ? dE + t + clamp : nullptr;
-            StepMasks first;
-            load_masks<MASK, BWD>(sm.step[w], mrp, mip, msf * 4u, first);
-            fft_pass2<W, MASK, BWD>(w, Sin.data() + lane, reinterpret_cast<float*>(S.data()) + lane, sm, first,
+            constexpr int AHEAD = BWD ? 1 : 2;
+            MaskSets<AHEAD> ms;
+            preload_masks<W, MASK, BWD, AHEAD>(w, sm, mrp, mip, msf * 4u, ms);
+            fft_pass2<W, MASK, BWD, AHEAD>(w, Sin.data() + lane, reinterpret_cast<float*>(S.data()) + lane, sm, ms,
                                     mrp, mip, dep, som * 4u, msf * 4u,
                                     gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
         }

@@ -43,12 +43,14 @@ for label, buf in (("fwd", buf_f), ("bwd", buf_b)):
     first = buf.cpu()[8 * 64 * 8 * 8:].view(1024, 4)
     fv = first[first[:, 0] > 0]
     if fv.numel():
-        end_ns = fv[:, 0].double(); dur = (fv[:, 1] >> 32).double(); dur2 = (fv[:, 1] & 0xffffffff).double()
-        print(label, 'first tile of each CTA: n=%d  tables_fill ns mean %.0f max %.0f | stage_lane_init ns mean %.0f max %.0f | end-time spread %.1f us' % (len(fv), dur.mean(), dur.max(), dur2.mean(), dur2.max(), (end_ns.max() - end_ns.min()) / 1e3))
-        entry = fv[:, 2].double(); tile0 = fv[:, 3].double()
+        end = fv[:, 0].double(); loop = fv[:, 1].double(); entry = fv[:, 2].double(); sm = fv[:, 3]
         k0 = entry.min()
-        print('   ns from first CTA entry: entry mean %.0f max %.0f | prologue (entry->tile start) mean %.0f max %.0f | tile end mean %.0f max %.0f'
-              % ((entry - k0).mean(), (entry - k0).max(), (tile0 - entry).mean(), (tile0 - entry).max(), (end_ns - k0).mean(), (end_ns - k0).max()))
+        print(label, 'CTAs: n=%d on %d SMs | entry (us after first) mean %.1f max %.1f | prologue us mean %.2f max %.2f | end us mean %.1f min %.1f max %.1f'
+              % (len(fv), len(set(sm.tolist())), (entry - k0).mean() / 1e3, (entry - k0).max() / 1e3, (loop - entry).mean() / 1e3, (loop - entry).max() / 1e3,
+                 (end - k0).mean() / 1e3, (end - k0).min() / 1e3, (end - k0).max() / 1e3))
+        import collections
+        per_sm = collections.Counter(sm.tolist())
+        print('   CTAs per SM: min %d max %d' % (min(per_sm.values()), max(per_sm.values())))
     t = buf.cpu()[:8 * 64 * 8 * 8].view(8, 64, -1)[:, :, :W * 8].reshape(8, 64, W, 8).double()
     valid = t[..., 7] > 0
     d = t[..., 1:] - t[..., :-1]
