@@ -500,9 +500,15 @@ static const K1Variant kVariants[] = {
     LMFB_VARIANT(3, 5), LMFB_VARIANT(2, 5), LMFB_VARIANT(4, 4), LMFB_VARIANT(5, 3),
 #endif
 };
-// Defaults measured on B200 (profiles/): 3 warps per tile (128 registers, 15 warps per SM).
-constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 0;
-constexpr int kBwdVariantBig = 0, kBwdVariantSmall = 0;
+// Defaults measured on B200 (profiles/): forward 3 warps per tile (5 CTAs, 15 warps per SM), backward
+// 4 warps per tile (4 CTAs, 16 warps per SM: the 45 KB of shared memory it leaves unused become L1,
+// where the tile's dE rows, re-read 8 times, then stay).  Staging those rows in shared memory
+// explicitly was measured and is slower (253 vs 237 us on 256 x 10 s).
+#ifdef LMFB_ONLY_W3
+constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 0, kBwdVariantBig = 0, kBwdVariantSmall = 0;
+#else
+constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 0, kBwdVariantBig = 2, kBwdVariantSmall = 2;
+#endif
 
 static int pick_variant(const char* env, int dflt) {
     const char* v = getenv(env);            // tuning knob: warps per tile
