@@ -375,26 +375,20 @@ LMFB_HD float masked_power(float2 x, float mr, float mi) {
 
 // ---------------------------------------------------------------------------------------
 // table fill, once per persistent CTA: every thread copies its share of the words of the kernel
-// parameter (lane-indexed constant loads: a handful per thread, all independent) and computes its
-// share of the per-step constants (the twiddles are sin/cos(pi f / 160), evaluated with sincospif:
-// no table to read at all).  Together with window_fill() this is the whole prologue, ~1 us;
-// walking the constant bank with warp-uniform indices and storing from lane 0 was measured at
-// 6-8 us per CTA (a quarter of a one-wave launch).
+// parameter and of the per-step constants (lane-indexed constant loads: a handful per thread, all
+// independent).  It runs under the first tile's staging copies.  Walking the constant bank with
+// warp-uniform indices and storing from lane 0 was measured at 6-8 us per CTA, a quarter of a
+// one-wave launch.  (The twiddles stay correctly rounded literals: with sincospif the 1-ulp
+// differences show up in the boundary-length parity test, whose imaginary parts are pure
+// cancellation noise.)
 // ---------------------------------------------------------------------------------------
 LMFB_HD void copy_words(uint32_t* dst, const uint32_t* src, int words, int tid, int nthreads) {
     for (int i = tid; i < words; i += nthreads) dst[i] = src[i];
 }
 LMFB_HD void fill_steps(StepEnt* st, int tid, int nthreads) {
-    for (int i = tid; i < 17 * 5; i += nthreads) {
+    for (int i = tid; i < 17 * 5; i += nthreads) {           // correctly rounded literals (generated tables)
         const int k2 = i / 5, k1 = i - 5 * k2;
-        const int f = bin_of(k2, k1);
-        float sn, cs;
-#ifdef __CUDACC__
-        sincospif((float)f * (1.0f / 160.0f), &sn, &cs);
-#else
-        sn = (float)sin(3.14159265358979323846 * f / 160.0); cs = (float)cos(3.14159265358979323846 * f / 160.0);
-#endif
-        st[k2].f[k1] = (uint32_t)f; st[k2].sn[k1] = sn; st[k2].cs[k1] = cs;
+        st[k2].f[k1] = kStepBin[k2][k1]; st[k2].sn[k1] = kStepSin[k2][k1]; st[k2].cs[k1] = kStepCos[k2][k1];
     }
 }
 LMFB_HD void tables_fill(FwdSmem* sm, const FwdTab& tab, int tid, int nthreads) {

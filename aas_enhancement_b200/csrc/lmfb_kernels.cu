@@ -115,8 +115,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
     const int n_mels = tab.n_mels;
     StageLane sl;
     stage_lane_init(lane, S, sl);
-    window_fill(S, a.window, threadIdx.x, kTile * W);          // pad column of the scratch <- window table
-    tables_fill(&sm, tab, threadIdx.x, kTile * W);             // visible after the first block barrier
+    bool filled = false;                                       // tables: filled under the first tile's staging copies
     float2* col = S + lane;
     float*  pl  = reinterpret_cast<float*>(S) + lane;
     const unsigned msf_bytes = a.msf * 4u;
@@ -191,6 +190,11 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
         const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;          // hop-rows that feed a valid frame
         stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
+        if (!filled) {                              // once per CTA, while the staging copies are in flight
+            window_fill(S, a.window, threadIdx.x, kTile * W);      // pad column of the scratch <- window table
+            tables_fill(&sm, tab, threadIdx.x, kTile * W);         // both visible after the barrier below
+            filled = true;
+        }
         LMFB_TICK(1);
         cp_async_wait_all();
         __syncthreads();

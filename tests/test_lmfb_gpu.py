@@ -367,3 +367,15 @@ def test_l1loss_on_front_end_output_full_size(be):
     assert int(n_element) == want_n
     assert abs(loss.item() - want) < 1e-5 * want
     assert mr.grad is not None and torch.isfinite(mr.grad).all()
+
+
+def test_dynamic_and_static_tile_schedules_agree():
+    """A launch with more tiles than resident CTAs is scheduled with cluster launch control; the
+    result must be bit-identical to the static round-robin schedule (AAS_LMFB_SCHED=static)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_sched.py")],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert "schedules agree" in res.stdout
