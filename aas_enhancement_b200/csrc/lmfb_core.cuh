@@ -42,6 +42,12 @@
 #include "fft_codelets.cuh"
 
 #ifdef __CUDACC__
+#  define LMFB_CX __host__ __device__ constexpr
+#else
+#  define LMFB_CX constexpr
+#endif
+
+#ifdef __CUDACC__
 #  define LMFB_LDG(p) __ldg(p)
 #  define LMFB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 // make a value opaque to the optimiser: it is then kept in its register(s) instead of being

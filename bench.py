@@ -120,16 +120,19 @@ class ClockSampler:
 class Slot:
     """One resident synthetic batch + its output buffers (device)."""
 
-    def __init__(self, n, samples, tmax, n_mels, gen, dev):
+    def __init__(self, n, samples, tmax, n_mels, gen, dev, row_pad=0):
         self.wave = (0.1 * torch.randn(n, samples, generator=gen, device=dev)).clamp_(-1, 1)
         self.lengths = torch.full((n,), samples, dtype=torch.int32, device=dev)
-        self.mr = torch.rand(n, 161, tmax, generator=gen, device=dev)
-        self.mi = torch.rand(n, 161, tmax, generator=gen, device=dev)
+        # row_pad (experiment only, --pad-rows): mask rows padded to a multiple of 32 frames, i.e.
+        # 128-byte aligned row segments; the default is the reference's contiguous (N, 161, T)
+        tp = -(-tmax // row_pad) * row_pad if row_pad else tmax
+        self.mr = torch.rand(n, 161, tp, generator=gen, device=dev)[:, :, :tmax]
+        self.mi = torch.rand(n, 161, tp, generator=gen, device=dev)[:, :, :tmax]
         self.gout = torch.randn(n, n_mels, tmax, generator=gen, device=dev)
         self.out = torch.empty(n, n_mels, tmax, device=dev)
         self.stats = torch.empty(n, n_mels, 2, device=dev)
-        self.gr = torch.empty_like(self.mr)
-        self.gi = torch.empty_like(self.mi)
+        self.gr = torch.empty(n, 161, tp, device=dev)[:, :, :tmax]
+        self.gi = torch.empty(n, 161, tp, device=dev)[:, :, :tmax]
         self.ws = torch.empty(n, n_mels, tmax, device=dev)
 
 
@@ -168,7 +171,7 @@ def run_ours(args):
         ring = max(1, int(60e9 // slot_bytes))
     gen = torch.Generator(device=dev)
     gen.manual_seed(123 + rank)                                      # config.py:62 default seed
-    slots = [Slot(n, samples, tmax, n_mels, gen, dev) for _ in range(ring)]
+    slots = [Slot(n, samples, tmax, n_mels, gen, dev, args.pad_rows) for _ in range(ring)]
 
     def fwd(s, prof=None):
         st = torch.cuda.current_stream().cuda_stream
@@ -517,6 +520,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="chime4_30x6s", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pad-rows", type=int, default=0, help="experiment: pad the mask rows to a multiple of this many frames (not the reference layout; not a valid bench line)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel A/B runs; not a valid bench line)")
     args = ap.parse_args()
     if args.impl == "reference":

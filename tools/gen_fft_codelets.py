@@ -215,28 +215,14 @@ def main():
     parts.append("#    define LMFB_HD inline __attribute__((always_inline))")
     parts.append("#  endif")
     parts.append("#endif")
-    parts.append("#ifndef LMFB_CX")
-    parts.append("#  ifdef __CUDACC__")
-    parts.append("#    define LMFB_CX __host__ __device__ constexpr")
-    parts.append("#  else")
-    parts.append("#    define LMFB_CX constexpr")
-    parts.append("#  endif")
-    parts.append("#endif")
     parts.append("#include <math.h>")
     parts.append("namespace aas_lmfb {")
     for n in (32,):
         code, flops = gen_codelet(n)
         parts.append(f"// fft{n}: {flops} floating-point operations (fma counted once)")
         parts.append(code)
-    # split twiddles for the real-FFT post-pass, as compile-time functions of the bin: every use
-    # has a constant bin index (pass 2 is fully unrolled), so the values become immediates
-    sins = ", ".join(lit(math.sin(2.0 * math.pi * f / 320.0)) for f in range(161))
-    coss = ", ".join(lit(math.cos(2.0 * math.pi * f / 320.0)) for f in range(161))
-    parts.append("// real-split twiddles sin/cos(2*pi*f/320) of bin f, usable in constant expressions")
-    parts.append("LMFB_CX float split_sin(int f) {\n    constexpr float t[161] = {" + sins + "};\n    return t[f];\n}")
-    parts.append("LMFB_CX float split_cos(int f) {\n    constexpr float t[161] = {" + coss + "};\n    return t[f];\n}")
-    # the same per pass-2 step (k2) and output (k1), for code that is rolled over k2: constant-bank
-    # tables read with a warp-uniform index
+    # split twiddles for the real-FFT post-pass (theta = 2*pi*f/320) and the bin of every pass-2
+    # step (k2) and output (k1): copied once per CTA into the shared-memory step table
     parts.append("#ifdef __CUDACC__\n#  define LMFB_CONST __constant__ const\n#else\n#  define LMFB_CONST static const\n#endif")
     rows_s, rows_c, rows_f = [], [], []
     for k2 in range(17):

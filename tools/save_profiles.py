@@ -86,6 +86,11 @@ for wl, rep in (("chime4_30x6s", f"prof_chime_{tag}.ncu-rep"), ("sweep_256x10s",
     st = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_stalls.py"), "15"], input=src,
                         stdout=subprocess.PIPE, text=True).stdout
     open(os.path.join(P, f"{tag}_stalls_{wl}.txt"), "w").write(st)
+    tiles = {"chime4_30x6s": 30 * 19, "sweep_256x10s": 256 * 32}[wl]
+    rg = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), str(tiles)], input=src,
+                        stdout=subprocess.PIPE, text=True).stdout
+    open(os.path.join(P, f"{tag}_regions_{wl}.txt"), "w").write(
+        "# executed warp instructions per tile and stall samples per kernel region (split at BAR.SYNC)\n" + rg)
 json.dump(traffic, open(tpath, "w"), indent=1)
 
 # SASS of the library (opcode histogram per kernel + full listing of the default reim kernels)
@@ -114,8 +119,8 @@ with open(os.path.join(P, f"{tag}_sass_summary.txt"), "w") as f:
                     ops[op.split(".")[0].rstrip(";")] += 1
         f.write(f"{sum(ops.values()):6d}  {k}\n        " + " ".join(f"{o}:{c}" for o, c in ops.most_common(14)) + "\n")
 for k, lines in blocks.items():
-    if "lmfb_k1ILi1ELb1ELi3ELi5" in k or "lmfb_k1ILi1ELb0ELi3ELi5" in k:
-        short = "k1_bwd_reim_w3" if "Lb1" in k else "k1_fwd_reim_w3"
+    if "lmfb_k1ILi1ELb1ELi4ELi4" in k or "lmfb_k1ILi1ELb0ELi3ELi5" in k:      # the default reim kernels
+        short = "k1_bwd_reim_w4" if "Lb1" in k else "k1_fwd_reim_w3"
         with open(os.path.join(P, f"{tag}_sass_{short}.txt"), "w") as f:
             f.write(f"# {k}\n")
             import re as _re
