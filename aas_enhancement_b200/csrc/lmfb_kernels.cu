@@ -478,6 +478,62 @@ cmvn_bwd_rows(const float* __restrict__ z, const float* __restrict__ stats,
     }
 }
 
+// ---- block-per-row backward for rows too long for one warp's registers: the row is read ONCE,
+// K elements per thread in registers (the three-pass kernel above reads g and z twice).
+template <int K>
+__global__ void __launch_bounds__(kRowThreads)
+cmvn_bwd_block(const float* __restrict__ z, const float* __restrict__ stats,
+               const float* __restrict__ grad_out, float* __restrict__ dE,
+               const int32_t* __restrict__ lengths, int n_mels, int tmax, float eps, int mode) {
+    __shared__ double red[kRowThreads / 32];
+    const int row = blockIdx.x;
+    const int n = row / n_mels;
+    const int T = frames_of(lengths, n, tmax);
+    const float* zb = z + (long long)row * tmax;
+    const float* gb = grad_out + (long long)row * tmax;
+    float* eb = dE + (long long)row * tmax;
+    float g[K], zz[K];
+    float sg = 0.0f, sgz = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int t = threadIdx.x + kRowThreads * k;
+        g[k] = t < T ? gb[t] : 0.0f;
+        zz[k] = t < T ? zb[t] : 0.0f;
+        sg += g[k];
+        sgz = fmaf(g[k], zz[k], sgz);
+    }
+    float c1 = 0.0f, kk = 0.0f, mean = 0.0f, rstd = 1.0f;
+    if (mode != 0) {                                   // block-uniform
+        const double sg_d = block_sum((double)sg, red);
+        const double sgz_d = block_sum((double)sgz, red);
+        if (T > 0) {
+            mean = stats[2 * (long long)row];
+            rstd = stats[2 * (long long)row + 1];
+            const double sigma = 1.0 / (double)rstd - (double)eps;
+            c1 = (float)(sg_d / (double)T);
+            kk = (float)(sgz_d / ((double)(T - 1) * sigma));
+        }
+    }
+    const float inv_rstd = 1.0f / rstd;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int t = threadIdx.x + kRowThreads * k;
+        if (t < tmax) {
+            float r = 0.0f;
+            if (t < T) {
+                if (mode != 0) {
+                    const float dy = fmaf(rstd, g[k] - c1, -zz[k] * kk);
+                    const float y = fmaf(zz[k], inv_rstd, mean);
+                    r = dy * expf(-y);
+                } else {
+                    r = g[k] * expf(-zz[k]);
+                }
+            }
+            eb[t] = r;
+        }
+    }
+}
+
 }  // namespace aas_lmfb
 
 // ======================================================================================
@@ -728,6 +784,10 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
             cmvn_bwd_rows<8><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, rows, tmax, eps, (int)cm);
         } else if (cm != 2 && tmax <= 32 * 24) {
             cmvn_bwd_rows<24><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, rows, tmax, eps, (int)cm);
+        } else if (cm != 2 && tmax <= kRowThreads * 8) {
+            cmvn_bwd_block<8><<<(unsigned)rows, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm);
+        } else if (cm != 2 && tmax <= kRowThreads * 24) {
+            cmvn_bwd_block<24><<<(unsigned)rows, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm);
         } else {
             dim3 grid(cm == 2 ? 1 : plan->n_mels, n);
             cmvn_bwd<<<grid, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm);

@@ -159,6 +159,13 @@ def test_long_utterance_30s(be):
 
 
 # ------------------------------------------------------------------ properties
+@pytest.mark.parametrize("seconds", [10, 17])
+def test_cmvn_backward_long_rows(be, seconds):
+    """Rows of 1001 / 1701 frames: the block-per-row CMVN backward variants (K = 8 / 24)."""
+    b = _synth.make_batch(2, 16000 * seconds, seed=40 + seconds, ragged=True)
+    _check(be, b, "reim", "per_bin")
+
+
 def test_unit_masks_equal_unmasked(be):
     b = _synth.make_batch(4, 20000, seed=3, ragged=True)
     b["mask_r"][:] = 1.0
