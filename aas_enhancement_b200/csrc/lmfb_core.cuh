@@ -76,7 +76,8 @@ constexpr int kMaxMels = 128;
 constexpr int kScratchBytes = kSlots * kPitch * 8;     // 42,240 B per tile
 constexpr int kMaxW = 8;               // most warps that may share a tile
 
-enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2 };
+enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2,
+                kStftOut = 3 };   // "backward" skeleton that stores the spectrum itself (Re rows to gr, Im rows to gi)
 
 // which mask tensors a kernel variant reads
 #define LMFB_NEEDS_MASK_R(MASK, BWD) ((BWD) ? (MASK) == kMaskReim : (MASK) != kMaskNone)
@@ -483,7 +484,7 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
                         const float* __restrict__ dE, const float* __restrict__ de1, unsigned sem_bytes, unsigned msf_bytes,
                         float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
     StepD d;
-    if constexpr (BWD) load_d(sm.d[k2], dE, de1, sem_bytes, d);
+    if constexpr (BWD && MASK != kStftOut) load_d(sm.d[k2], dE, de1, sem_bytes, d);
     const int kb = (32 - k2) & 31;
     const float2* ca = col + k2 * kPitch;
     const float2* cb = col + kb * kPitch;
@@ -513,6 +514,14 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
             // bin 160 (the partner of bin 0, which only output k1 = 0 can produce) sits beside bin 0
             const uint32_t po = (k1 == 0 && f == 0) ? (uint32_t)kTile : fp * kRow;
             pl[po] = masked_power<MASK>(xp, in.vr[5 + k1], in.vi[5 + k1]);
+        } else if constexpr (MASK == kStftOut) {
+            // the spectrum is carried as X' = 2X; `dE` doubles as nothing here, the scale (0.5 for
+            // frames that exist, 0 beyond) arrives in the first mask slot
+            const float sc = in.vr[0];
+            st_if(at_row(gr, f, msf_bytes), sc * xf.x, inrow);
+            st_if(at_row(gi, f, msf_bytes), sc * xf.y, inrow);
+            st_if(at_row(gr, fp, msf_bytes), sc * xp.x, inrow);
+            st_if(at_row(gi, fp, msf_bytes), sc * xp.y, inrow);
         } else {
 #ifdef __CUDACC__
             const float4 wv = *reinterpret_cast<const float4*>(sm.w[k2][k1]);

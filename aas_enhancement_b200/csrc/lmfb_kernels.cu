@@ -160,7 +160,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
 #pragma unroll 4
                     for (int f = w; f < kBins; f += W) {
                         a.gr[moff + (unsigned)f * a.msf] = 0.0f;
-                        if (MASK == kMaskReim) a.gi[moff + (unsigned)f * a.msf] = 0.0f;
+                        if (MASK == kMaskReim || MASK == kStftOut) a.gi[moff + (unsigned)f * a.msf] = 0.0f;
                     }
                 }
             }
@@ -171,7 +171,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs ...
         if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
-        if (BWD) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
+        if (BWD && MASK != kStftOut) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
         // (prefetching the NEXT tile's samples was measured and dropped: in the backward kernel the
         // lines are evicted before use and the wave is read from DRAM twice, 707 -> 578 MB per launch)
 #endif
@@ -209,6 +209,10 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
         MaskSets<AHEAD> ms;                         // issued before the barrier: the latency hides behind it
         preload_masks<W, MASK, BWD, AHEAD>(w, sm, mr, mi, msf_bytes, ms);
+        if constexpr (MASK == kStftOut) {           // no masks: the slot carries the output scale
+#pragma unroll
+            for (int i = 0; i <= AHEAD; ++i) ms.m[i].vr[0] = valid ? 0.5f : 0.0f;
+        }
         LMFB_TICK(3);
         __syncthreads();
         LMFB_TICK(4);
@@ -544,13 +548,14 @@ using namespace aas_lmfb;
 typedef void (*k1_fwd_fn)(const K1Args, const FwdTab);
 typedef void (*k1_bwd_fn)(const K1Args, const BwdTab);
 
-struct K1Variant { int warps, ctas; k1_fwd_fn fwd[3]; k1_bwd_fn bwd[3]; };   // indexed by mask mode
+struct K1Variant { int warps, ctas; k1_fwd_fn fwd[3]; k1_bwd_fn bwd[4]; };   // indexed by mask mode (bwd[3]: STFT output)
 
 #define LMFB_VARIANT(W, C)                                                                 \
     { W, C,                                                                                \
       { lmfb_k1<kMaskNone, false, W, C>, lmfb_k1<kMaskReim, false, W, C>,                  \
         lmfb_k1<kMaskPower, false, W, C> },                                                \
-      { nullptr, lmfb_k1<kMaskReim, true, W, C>, lmfb_k1<kMaskPower, true, W, C> } }
+      { nullptr, lmfb_k1<kMaskReim, true, W, C>, lmfb_k1<kMaskPower, true, W, C>,          \
+        lmfb_k1<kStftOut, true, W, C> } }
 
 // (warps per tile, resident CTAs per SM the register budget is sized for)
 static const K1Variant kVariants[] = {
@@ -814,6 +819,32 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
     rc = launch_k1(v, v.bwd[mask], a, plan->bwd, true, n, stream);
     rec(prof, 1, stream);
     return rc;
+}
+
+// STFT as an output: what BRNNmultiCH.forward takes as its input, (N, 2*F, T) with the real rows first
+// and the imaginary rows second (model.py:170, :186-188).  Same staging + FFT as the other kernels;
+// the spectrum rows are stored straight from pass 2.
+extern "C" int aas_lmfb_stft(const aas_lmfb_plan* plan,
+                             const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                             const float* window, float* out, int64_t out_stride_n, int tmax,
+                             void* cuda_stream) {
+    int rc = check_common(plan, wave, lengths, n, nullptr, nullptr, window, tmax, AAS_LMFB_MASK_NONE);
+    if (rc) return rc;
+    if (n == 0) return AAS_LMFB_OK;
+    if (!out) return AAS_LMFB_E_NULL;
+    if ((uintptr_t)out & 3u) return AAS_LMFB_E_ALIGN;
+    if (out_stride_n < 2LL * kBins * tmax) return AAS_LMFB_E_SHAPE;
+    K1Args a;
+    memset(&a, 0, sizeof(a));
+    a.wave = wave; a.lengths = lengths; a.wave_stride = wave_stride;
+    a.mask_r = a.mask_i = out;                                    // never read (clamped pointer arithmetic only)
+    a.msn = out_stride_n; a.msf = (unsigned)tmax;
+    a.window = window; a.dE = out; a.gr = out; a.gi = out + (long long)kBins * tmax; a.tmax = tmax;
+    a.tiles_per_utt = (tmax + kTile - 1) / kTile;
+    a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
+    const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
+    const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
+    return launch_k1(v, v.bwd[3], a, plan->bwd, true, n, (cudaStream_t)cuda_stream);
 }
 
 // ======================================================================================

@@ -237,3 +237,29 @@ class LMFBFrontEnd(torch.nn.Module):
     def forward(self, wave, lengths, mask_r=None, mask_i=None, tmax=None):
         return LMFB.apply(wave, lengths, mask_r, mask_i, self.plan, self.window,
                           self.mask_mode, self.cmvn_mode, self.eps, tmax)
+
+    @torch.no_grad()
+    def stft(self, wave, lengths, tmax=None):
+        """The enhancer's input: ``(N, 2*161, Tmax)`` with the 161 real rows first and the 161
+        imaginary rows second -- the layout ``BRNNmultiCH.forward`` views as ``(N, 2, F, T)``
+        (model.py:170, :186-188) -- and ``frame_lens``.  Same framing, window and FFT as
+        :meth:`forward`; frames ``t >= T_i`` are exact zeros.  Not differentiable (it is data)."""
+        if not wave.is_cuda:
+            raise RuntimeError("LMFB is CUDA-only (sm_100a); there is no CPU fallback")
+        dev = wave.device
+        _check_f32_cuda("wave", wave, dev)
+        if wave.dim() != 2 or wave.stride(1) != 1:
+            raise ValueError("wave must be (N, Lmax) with unit sample stride")
+        lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
+        n = wave.shape[0]
+        tmax = int(1 + wave.shape[1] // HOP if tmax is None else tmax)
+        out = torch.empty((n, 2 * N_BINS, tmax), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.aas_lmfb_stft(self.plan.handle, wave.data_ptr(), lengths.data_ptr(), n, wave.stride(0),
+                                   self.window.data_ptr(), out.data_ptr(), out.stride(0), tmax, stream)
+        _lib.check(rc)
+        frame_lens = torch.clamp(1 + torch.div(lengths, HOP, rounding_mode="floor"), max=tmax)
+        frame_lens = torch.where(lengths >= 1, frame_lens, torch.zeros_like(frame_lens)).to(torch.int32)
+        return out, frame_lens

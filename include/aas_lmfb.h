@@ -99,6 +99,17 @@ int aas_lmfb_backward(const aas_lmfb_plan* plan,
                       void* workspace, int tmax,
                       uint32_t flags, float eps, void* cuda_stream, void* const* prof);
 
+/* STFT as an output (first half): the input BRNNmultiCH.forward takes,
+ * `(N, nCH*F*2, T)` with the F real rows first and the F imaginary rows second
+ * (Speech_enhancement_by_AAS/model.py:170, :186-188), computed from the waveform with the same
+ * framing / window / 320-point FFT as aas_lmfb_forward (AM_training/train.py:39-42, :190-199).
+ *   out  (N, 2, 161, Tmax) fp32, element (n, c, f, t) at n*out_stride_n + (c*161 + f)*tmax + t;
+ *        frames t >= T_n are written as exact zeros.  No mel basis is involved (any plan will do). */
+int aas_lmfb_stft(const aas_lmfb_plan* plan,
+                  const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                  const float* window, float* out, int64_t out_stride_n, int tmax,
+                  void* cuda_stream);
+
 /* ---- L1Loss_mask: the loss applied to the features right after this front-end --------------
  * Replaces Speech_enhancement_by_AAS/model.py:19-31 (called at trainer_AAS.py:146-161, :176-181,
  * trainer_DCE.py, trainer_FSEGAN.py): sum |a - b| over (N, C, Tmax), deterministic two-stage sum.

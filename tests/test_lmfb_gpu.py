@@ -158,6 +158,34 @@ def test_long_utterance_30s(be):
     _check(be, b, "reim", "per_bin")
 
 
+# ------------------------------------------------------------------ STFT as an output
+@pytest.mark.parametrize("n,length", [(3, 9000), (2, 161), (40, 48000)])
+def test_stft_output_matches_oracle_and_feeds_the_reference_glue(be, n, length):
+    """aas_lmfb_stft: (N, 2*161, T) with the real rows first (the layout BRNNmultiCH.forward views
+    as (N, 2, F, T), model.py:186-188) against the float64 oracle; pushing it through the literal
+    ops of model.py:191-198 reproduces the fused forward."""
+    b = _synth.make_batch(n, length, seed=length + n, ragged=True)
+    fe = be.LMFBFrontEnd(mask_mode="reim", cmvn_mode="none").cuda()
+    wave, lengths, mr, mi = _dev(b, "reim")
+    spec, fl = fe.stft(wave, lengths)
+    spec_np = spec.cpu().numpy()
+    win = fe.window.cpu().numpy().astype(np.float64)
+    tmax = spec.shape[2]
+    ref = np.zeros((n, 2 * 161, tmax))
+    for i in range(n):
+        s = orc.stft_frames(b["wave"][i], int(b["lengths"][i]), win)
+        ref[i, :161, :s.shape[1]] = s.real
+        ref[i, 161:, :s.shape[1]] = s.imag
+        assert int(fl[i]) == s.shape[1]
+        assert np.all(spec_np[i, :, s.shape[1]:] == 0.0)
+    assert orc.rel_err(spec_np, ref) < TOL
+    st = spec.view(n, 2, 161, tmax).double().cpu()                    # model.py:186-188 (float64: cuDNN would use TF32)
+    power = (st[:, 0] * mr.detach().double().cpu()) ** 2 + (st[:, 1] * mi.detach().double().cpu()) ** 2   # :191-194
+    glue = torch.log1p(torch.nn.functional.conv1d(power, fe.mel_basis.double().cpu().unsqueeze(-1)))      # :196-198
+    z, _ = fe(wave, lengths, mr, mi)
+    assert orc.rel_err(z.detach().cpu().numpy(), glue.numpy()) < TOL
+
+
 # ------------------------------------------------------------------ properties
 @pytest.mark.parametrize("seconds", [10, 17])
 def test_cmvn_backward_long_rows(be, seconds):
