@@ -82,3 +82,29 @@ class L1Loss_mask(torch.nn.Module):
         err_sum = _L1AbsSum.apply(input, target, mask if self.fix_masking else None)
         loss = err_sum / n_element
         return loss, n_element
+
+
+class CTCLoss(torch.nn.Module):
+    """Stand-in for ``warpctc_pytorch.CTCLoss`` (un-vendored; imported at trainer_AAS.py:12 and
+    called at :168 as ``self.CTCLoss(prob, targets, sizes, target_sizes) / N``) -- SURVEY 8(f)
+    rank 4.  Same call signature and semantics: ``acts`` are UNNORMALISED activations
+    ``(T, N, C)`` (warp-ctc applies the softmax itself), ``labels`` the flat int32 concatenation
+    of the targets (blank = 0), ``act_lens`` / ``label_lens`` int32 on the host; the result is the
+    cost SUMMED over the batch as a 1-element tensor (the trainer divides by N).  Library code
+    (``torch.nn.functional.ctc_loss``) -- it is the boundary after the front-end, not part of the
+    hand-written path."""
+
+    def __init__(self, size_average: bool = False, length_average: bool = False):
+        super().__init__()
+        self.size_average, self.length_average = size_average, length_average
+
+    def forward(self, acts, labels, act_lens, label_lens):
+        log_probs = torch.nn.functional.log_softmax(acts.float(), dim=2)
+        cost = torch.nn.functional.ctc_loss(log_probs, labels.to(torch.long), act_lens.to(torch.long),
+                                            label_lens.to(torch.long), blank=0, reduction="sum",
+                                            zero_infinity=False)
+        if self.length_average:
+            cost = cost / act_lens.sum().to(cost.dtype)
+        elif self.size_average:
+            cost = cost / acts.size(1)
+        return cost.reshape(1)

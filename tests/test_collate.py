@@ -112,3 +112,32 @@ def test_two_rank_sharding_over_gloo():
     total = sum(frames0)
     assert max(frames0) - min(frames0) <= 53  # at most one utterance of imbalance
     assert total == sum(frame_count(l) for l in _wave_batch(seed=3)[0])
+
+
+def test_ctc_boundary_matches_a_brute_force_sum():
+    """CTCLoss (stand-in for warp-ctc at trainer_AAS.py:168): softmax inside, blank 0, cost summed
+    over the batch, lengths from ctc_sizes.  Checked against an explicit sum over alignments."""
+    import itertools
+    from aas_enhancement_b200 import CTCLoss
+    torch.manual_seed(2)
+    t_len, n, c = 5, 2, 4
+    acts = torch.randn(t_len, n, c, requires_grad=True)
+    targets = [[1, 2], [3]]
+    pct = torch.tensor([1.0, 0.8], dtype=torch.float32)
+    sizes = ctc_sizes(pct, t_len)
+    assert sizes.tolist() == [5, 4]
+    loss = CTCLoss()(acts, torch.IntTensor([1, 2, 3]), sizes, torch.IntTensor([2, 1]))
+    assert loss.shape == (1,)
+    logp = torch.log_softmax(acts.detach().double(), dim=2)
+    total = 0.0
+    for b in range(n):
+        tb = int(sizes[b])
+        p = 0.0
+        for path in itertools.product(range(c), repeat=tb):
+            col = [k for k, g in itertools.groupby(path)]
+            if [k for k in col if k != 0] == targets[b]:
+                p += float(torch.exp(sum(logp[t, b, path[t]] for t in range(tb))))
+        total += -np.log(p)
+    assert abs(float(loss) - total) < 1e-4 * abs(total)
+    loss.backward()
+    assert torch.isfinite(acts.grad).all() and float(acts.grad[4, 1].abs().sum()) == 0.0   # beyond act_lens
