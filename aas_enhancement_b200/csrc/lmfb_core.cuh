@@ -54,7 +54,9 @@
 // re-derived (rematerialised) at every use
 #  define LMFB_OPAQUE(p) asm volatile("" : "+l"(p))
 #  define LMFB_OPAQUE32(v) asm volatile("" : "+r"(v))
+#  define LMFB_SYNCWARP() __syncwarp()
 #else
+#  define LMFB_SYNCWARP() ((void)0)
 #  define LMFB_OPAQUE(p) ((void)0)
 #  define LMFB_OPAQUE32(v) ((void)0)
 #  define LMFB_LDG(p) (*(p))
@@ -502,6 +504,9 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
         const float2 v = ca[n * 32 * kPitch]; ar[n] = v.x; ai[n] = v.y;
         const float2 u = cb[n * 32 * kPitch]; br[n] = u.x; bi[n] = u.y;
     }
+    // forward: the compact power rows written below overlap the float2 words OTHER lanes of this warp
+    // have just read (same slot rows); order the warp's reads before its writes
+    if constexpr (!BWD) LMFB_SYNCWARP();
     StepK k;
     load_step(sm.step[k2], k);
 #ifndef LMFB_DBG_NOFFT

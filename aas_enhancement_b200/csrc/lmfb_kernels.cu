@@ -1,11 +1,14 @@
 // B200 (sm_100a) kernels and C ABI of the LMFB front-end.  See include/aas_lmfb.h for the
 // contract and lmfb_core.cuh for the per-thread algorithm.
 //
-//   K1  lmfb_k1<MASK, BWD>   one warp per tile of 32 frames: stage wave -> 320-pt real FFT
-//                            (lane = frame) -> mask -> banded mel -> log1p   (forward)
-//                            or -> d mask from dE                            (backward)
-//   K2  cmvn_fwd / cmvn_bwd  per-utterance mean/variance normalisation of the (M, T) rows
+//   K1  lmfb_k1<MASK, BWD, W, CTAS>   W warps per tile of 32 frames (lane = frame): stage wave ->
+//                            320-pt real FFT -> mask -> banded mel -> log1p      (forward)
+//                            or -> d mask from dE                                 (backward)
+//                            or -> the spectrum itself, (N, 2*161, T)             (aas_lmfb_stft);
+//                            tiles handed out by cluster launch control.
+//   K2  cmvn_fwd* / cmvn_bwd*  per-utterance mean/variance normalisation of the (M, T) rows
 //                            and its gradient folded with d log1p.
+//   K3  l1_abs_*             L1Loss_mask: deterministic sum |a - b| and its gradient.
 //
 // No cuFFT, no library calls, no CPU fallback.
 #include <cuda_runtime.h>
