@@ -19,7 +19,7 @@ CMVN_MODES = {"none": 0 << 2, "per_bin": 1 << 2, "global": 2 << 2}
 
 EXPORTS = ("aas_lmfb_abi_version", "aas_lmfb_strerror", "aas_lmfb_plan_create",
            "aas_lmfb_plan_destroy", "aas_lmfb_workspace_bytes", "aas_lmfb_forward",
-           "aas_lmfb_backward", "aas_lmfb_stft", "aas_l1_partial_count", "aas_l1_abs_sum", "aas_l1_abs_grad")
+           "aas_lmfb_backward", "aas_lmfb_backward_wave", "aas_lmfb_stft", "aas_l1_partial_count", "aas_l1_abs_sum", "aas_l1_abs_grad")
 
 _lock = threading.Lock()
 _lib = None
@@ -55,6 +55,9 @@ def load() -> ctypes.CDLL:
         lib.aas_lmfb_backward.restype = _i32
         lib.aas_lmfb_backward.argtypes = [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _i64, _vp,
                                           _vp, _vp, _vp, _vp, _vp, _vp, _i32, _u32, _f32, _vp, _vp]
+        lib.aas_lmfb_backward_wave.restype = _i32
+        lib.aas_lmfb_backward_wave.argtypes = [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _i64, _vp,
+                                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _u32, _f32, _vp]
         lib.aas_lmfb_stft.restype = _i32
         lib.aas_lmfb_stft.argtypes = [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _i32, _vp]
         lib.aas_l1_partial_count.restype = _i32

@@ -82,8 +82,9 @@ enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2,
                 kStftOut = 3 };   // "backward" skeleton that stores the spectrum itself (Re rows to gr, Im rows to gi)
 
 // which mask tensors a kernel variant reads
-#define LMFB_NEEDS_MASK_R(MASK, BWD) ((BWD) ? (MASK) == kMaskReim : (MASK) != kMaskNone)
-#define LMFB_NEEDS_MASK_I(MASK, BWD) ((MASK) == kMaskReim)
+// (the backward needs the 'power' mask only for the gradient into the waveform, GW)
+#define LMFB_NEEDS_MASK_R(MASK, BWD, GW) ((BWD) ? ((MASK) == kMaskReim || ((GW) && (MASK) == kMaskPower)) : ((MASK) != kMaskNone && (MASK) != kStftOut))
+#define LMFB_NEEDS_MASK_I(MASK, BWD, GW) ((MASK) == kMaskReim)
 
 // compile-time loop: f(IC<B>{}), f(IC<B+1>{}), ... f(IC<E-1>{})
 template <int I> struct IC { static constexpr int value = I; };
@@ -382,6 +383,27 @@ LMFB_HD void split_pair(float Ar, float Ai, float Bzr, float Bzi, float sn, floa
     xp = make_float2(sr + Dr, -(si + Di));
 }
 
+// adjoint of split_pair: gradients w.r.t. (xf, xp) -> gradients w.r.t. A = Z[f] and Bz = Z[160-f]
+LMFB_HD void split_pair_adj(float2 gxf, float2 gxp, float sn, float cs, float2& gA, float2& gBz) {
+    const float g_sr = gxf.x + gxp.x, g_si = gxf.y - gxp.y;
+    const float g_Dr = gxp.x - gxf.x, g_Di = -(gxf.y + gxp.y);
+    const float g_dr = fmaf(sn, g_Dr, cs * g_Di), g_di = fmaf(sn, g_Di, -cs * g_Dr);
+    gA  = make_float2(g_sr + g_dr, g_si + g_di);
+    gBz = make_float2(g_sr - g_dr, g_di - g_si);
+}
+// adjoint of a DFT (conjugate transform) = the same codelet with real and imaginary parts swapped
+// on the way in and on the way out
+LMFB_HD void dft5_adj(const float (&gr_)[5], const float (&gi_)[5], float (&ar)[5], float (&ai)[5]) {
+    dft5(gi_, gr_, ai, ar);
+}
+// gradient of the masked power w.r.t. the spectrum value x (X' scale), times dP
+template <int MASK>
+LMFB_HD float2 masked_power_grad(float2 x, float mr, float mi, float dp) {
+    if (MASK == kMaskReim) return make_float2(2.0f * mr * mr * x.x * dp, 2.0f * mi * mi * x.y * dp);
+    const float m2 = MASK == kMaskPower ? 2.0f * mr * dp : 2.0f * dp;
+    return make_float2(m2 * x.x, m2 * x.y);
+}
+
 // forward: masked power P' of one bin
 template <int MASK>
 LMFB_HD float masked_power(float2 x, float mr, float mi) {
@@ -456,7 +478,7 @@ LMFB_HD void load_step_bins(const StepEnt& se, uint32_t (&f)[5]) {
 struct StepMasks { float vr[10], vi[10]; };              // mask values (prefetched one step ahead)
 struct StepD     { float d0[10], d1[10]; };              // backward: the two dE rows of each bin
 
-template <int MASK, bool BWD>
+template <int MASK, bool BWD, bool GW>
 LMFB_HD void load_masks(const StepEnt& se, const float* __restrict__ mr, const float* __restrict__ mi, unsigned msf_bytes,
                         StepMasks& in) {
     uint32_t f[5];
@@ -464,8 +486,8 @@ LMFB_HD void load_masks(const StepEnt& se, const float* __restrict__ mr, const f
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
         const uint32_t fp = kBins - 1 - f[k1];
-        if (LMFB_NEEDS_MASK_R(MASK, BWD)) { in.vr[k1] = LMFB_LDG(at_row(mr, f[k1], msf_bytes)); in.vr[5 + k1] = LMFB_LDG(at_row(mr, fp, msf_bytes)); }
-        if (LMFB_NEEDS_MASK_I(MASK, BWD)) { in.vi[k1] = LMFB_LDG(at_row(mi, f[k1], msf_bytes)); in.vi[5 + k1] = LMFB_LDG(at_row(mi, fp, msf_bytes)); }
+        if (LMFB_NEEDS_MASK_R(MASK, BWD, GW)) { in.vr[k1] = LMFB_LDG(at_row(mr, f[k1], msf_bytes)); in.vr[5 + k1] = LMFB_LDG(at_row(mr, fp, msf_bytes)); }
+        if (LMFB_NEEDS_MASK_I(MASK, BWD, GW)) { in.vi[k1] = LMFB_LDG(at_row(mi, f[k1], msf_bytes)); in.vi[5 + k1] = LMFB_LDG(at_row(mi, fp, msf_bytes)); }
     }
 }
 
@@ -489,7 +511,7 @@ LMFB_HD void load_d(const uint32_t (*drow)[2], const float* __restrict__ dE, con
 //             has just read and no other step touches
 //   backward: gradients = (2 Mr Re'^2, 2 Mi Im'^2) * dP, or (Re'^2 + Im'^2) * dP for 'power',
 //             stored to row f of gr/gi; every lane's pointers are valid, `inrow` gates the store
-template <int MASK, bool BWD, class SM>
+template <int MASK, bool BWD, bool GW, class SM>
 LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl, const SM& sm, const StepMasks& in,
                         const float* __restrict__ dE, const float* __restrict__ de1, unsigned sem_bytes, unsigned msf_bytes,
                         float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
@@ -516,6 +538,9 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
 #pragma unroll
     for (int n = 0; n < 5; ++n) { Ar[n] = ar[n]; Ai[n] = ai[n]; Br[n] = br[n]; Bi[n] = bi[n]; }
 #endif
+    // GW (gradient into the waveform): the gradients w.r.t. the two columns' DFT5 outputs
+    float gAr[5], gAi[5], gBr[5], gBi[5];
+    const bool self = kb == k2;                              // columns 0 and 16 pair with themselves
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
         const int kp = (5 - k1) % 5;
@@ -544,7 +569,20 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
 #endif
             const float dpf = fmaf(whf, d.d1[k1], wlf * d.d0[k1]);
             const float dpp = fmaf(whp, d.d1[5 + k1], wlp * d.d0[5 + k1]);
-            if (MASK == kMaskReim) {
+            if constexpr (GW) {
+                // in a self-paired column every bin shows up twice (outputs 3, 4 repeat 2, 1) and
+                // bin 80 is its own partner: count each bin once
+                const bool dup = self && k1 >= 3, nopartner = f == fp;
+                // (lanes past the end of the row read a clamped dE column: they are frames that do not exist)
+                float2 gxf = masked_power_grad<MASK>(xf, in.vr[k1], in.vi[k1], (dup || !inrow) ? 0.0f : dpf);
+                float2 gxp = masked_power_grad<MASK>(xp, in.vr[5 + k1], in.vi[5 + k1], (dup || nopartner || !inrow) ? 0.0f : dpp);
+                float2 gA, gBz;
+                split_pair_adj(gxf, gxp, k.sn[k1], k.cs[k1], gA, gBz);
+                gAr[k1] = gA.x; gAi[k1] = gA.y; gBr[kp] = gBz.x; gBi[kp] = gBz.y;
+            }
+            if (MASK == kMaskNone) {
+                // nothing to store: only the waveform takes a gradient
+            } else if (MASK == kMaskReim) {
                 st_if_cs(at_row(gr, f, msf_bytes), 2.0f * in.vr[k1] * xf.x * xf.x * dpf, inrow);
                 st_if_cs(at_row(gi, f, msf_bytes), 2.0f * in.vi[k1] * xf.y * xf.y * dpf, inrow);
                 st_if_cs(at_row(gr, fp, msf_bytes), 2.0f * in.vr[5 + k1] * xp.x * xp.x * dpp, inrow);
@@ -552,6 +590,82 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
             } else {
                 st_if_cs(at_row(gr, f, msf_bytes), fmaf(xf.x, xf.x, xf.y * xf.y) * dpf, inrow);
                 st_if_cs(at_row(gr, fp, msf_bytes), fmaf(xp.x, xp.x, xp.y * xp.y) * dpp, inrow);
+            }
+        }
+    }
+    if constexpr (BWD && GW) {
+        // adjoint 5-point DFTs, in place: the slots of these two columns now hold the gradient w.r.t.
+        // the pass-1 outputs (self-paired column: both halves belong to the same column)
+#pragma unroll
+        for (int n = 0; n < 5; ++n) if (self) { gAr[n] += gBr[n]; gAi[n] += gBi[n]; }
+        float ar2[5], ai2[5];
+        dft5_adj(gAr, gAi, ar2, ai2);
+        float2* wa = col + k2 * kPitch;
+#pragma unroll
+        for (int n = 0; n < 5; ++n) wa[n * 32 * kPitch] = make_float2(ar2[n], ai2[n]);
+        if (!self) {
+            dft5_adj(gBr, gBi, ar2, ai2);
+            float2* wb = col + kb * kPitch;
+#pragma unroll
+            for (int n = 0; n < 5; ++n) wb[n * 32 * kPitch] = make_float2(ar2[n], ai2[n]);
+        }
+    }
+}
+
+// GW, after pass 2 and a block barrier: adjoint of pass 1 -- conjugate 32-point transforms, then
+// the window -- leaves in every column the gradient w.r.t. that frame's 160 packed raw samples
+template <int W>
+LMFB_HD void fft_pass1_adj(int w, float2* __restrict__ col, const float2* __restrict__ win) {
+#pragma unroll 1
+    for (int n1 = w; n1 < 5; n1 += W) {
+        float2* p = col + n1 * 32 * kPitch;
+        const float2* wn = win + n1 * 32 * kPitch;
+        float xr[32], xi[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const float2 v = p[i * kPitch]; xr[i] = v.y; xi[i] = v.x; }   // swapped in
+        fft32(xr, xi);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const float2 g = wn[i * kPitch]; p[i * kPitch] = make_float2(xi[i] * g.x, xr[i] * g.y); }   // swapped out
+    }
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add2(float* p, float2 v) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+#else
+static inline void red_add(float* p, float v) { *p += v; }
+static inline void red_add2(float* p, float2 v) { p[0] += v.x; p[1] += v.y; }
+#endif
+
+// GW, after another barrier: adjoint of the staging (overlap-add).  Hop-row r collects the first
+// half of frame r and the second half of frame r-1 and is ADDED to the (zero-initialised) waveform
+// gradient: neighbouring tiles share their edge rows, and the reflect padding folds the two ends of
+// an utterance back onto its first and last samples.
+template <int W>
+LMFB_HD void unstage_tile(int w, int lane, const StageLane& sl, float* __restrict__ gwave_row, int len,
+                          int t0, int n_rows, const float2* __restrict__ S, bool vec_ok) {
+    constexpr int kShare = (kTile + 1 + W - 1) / W;
+    const int r_lo = w * kShare;
+    const int r_hi = r_lo + kShare < kTile + 1 ? r_lo + kShare : kTile + 1;
+#pragma unroll 1
+    for (int r = r_lo; r < r_hi && r < n_rows; ++r) {
+        const int q = t0 + r - 1;
+        const bool fast = row_interior(q, len, vec_ok);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int c = lane + 32 * k;
+            if (c < 80) {
+                float2 v = make_float2(0.0f, 0.0f);
+                if (r < kTile) { const float2 a = S[sl.slot_a[k] + r]; v.x += a.x; v.y += a.y; }
+                if (r >= 1)    { const float2 b = S[sl.slot_b[k] + r - 1]; v.x += b.x; v.y += b.y; }
+                if (fast) {
+                    red_add2(gwave_row + (long long)q * kHop + 2 * c, v);
+                } else {
+                    red_add(gwave_row + reflect_index(q * kHop + 2 * c, len), v.x);
+                    red_add(gwave_row + reflect_index(q * kHop + 2 * c + 1, len), v.y);
+                }
             }
         }
     }
@@ -567,15 +681,15 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
 template <int AHEAD>
 struct MaskSets { StepMasks m[AHEAD + 1]; };
 
-template <int W, int MASK, bool BWD, int AHEAD, class SM>
+template <int W, int MASK, bool BWD, int AHEAD, bool GW, class SM>
 LMFB_HD void preload_masks(int w, const SM& sm, const float* __restrict__ mr, const float* __restrict__ mi,
                            unsigned msf_bytes, MaskSets<AHEAD>& ms) {
 #pragma unroll
     for (int i = 0; i < AHEAD; ++i)
-        if (w + i * W <= 16) load_masks<MASK, BWD>(sm.step[w + i * W], mr, mi, msf_bytes, ms.m[i]);
+        if (w + i * W <= 16) load_masks<MASK, BWD, GW>(sm.step[w + i * W], mr, mi, msf_bytes, ms.m[i]);
 }
 
-template <int W, int MASK, bool BWD, int AHEAD, class SM>
+template <int W, int MASK, bool BWD, int AHEAD, bool GW, class SM>
 LMFB_HD void fft_pass2(int w, float2* __restrict__ col, float* __restrict__ pl, const SM& sm, MaskSets<AHEAD>& ms,
                        const float* __restrict__ mr, const float* __restrict__ mi,
                        const float* __restrict__ dE, unsigned sem_bytes, unsigned msf_bytes,
@@ -589,8 +703,8 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, float* __restrict__ pl, 
             const int k = k2 + i * W;                       // this step; its masks are in set i
             if (k <= 16) {
                 const int kn = k + AHEAD * W;               // the step AHEAD later goes to set (i + AHEAD) mod R
-                if (kn <= 16) load_masks<MASK, BWD>(sm.step[kn], mr, mi, msf_bytes, ms.m[(i + AHEAD) % R]);
-                pass2_step<MASK, BWD>(k, col, pl, sm, ms.m[i], dE, de1, sem_bytes, msf_bytes, gr, gi, inrow);
+                if (kn <= 16) load_masks<MASK, BWD, GW>(sm.step[kn], mr, mi, msf_bytes, ms.m[(i + AHEAD) % R]);
+                pass2_step<MASK, BWD, GW>(k, col, pl, sm, ms.m[i], dE, de1, sem_bytes, msf_bytes, gr, gi, inrow);
             }
         }
     }

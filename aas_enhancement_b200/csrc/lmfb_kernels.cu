@@ -46,6 +46,7 @@ struct K1Args {
     int            vec_ok;
     long long*     timeline;   // debug builds (-DLMFB_TIMELINE) only: per-warp phase clocks
     int            dynamic;    // tiles handed out by cluster launch control (grid = one CTA per tile)
+    float*         gwave;      // backward with GW: (N, wave_stride) gradient w.r.t. the samples, zeroed by the caller of the kernel
 };
 
 constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
@@ -96,7 +97,7 @@ __device__ __forceinline__ bool clc_answer(const uint4* resp, int& ctaid_x) {
     return ok != 0;
 }
 
-template <int MASK, bool BWD, int W, int CTAS>
+template <int MASK, bool BWD, int W, int CTAS, bool GW = false>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf<BWD>::Param tab) {
     typedef typename TabOf<BWD>::Smem SM;
@@ -172,8 +173,8 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
 
 #ifndef LMFB_DBG_NOPREFETCH
         // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs ...
-        if (LMFB_NEEDS_MASK_R(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
-        if (LMFB_NEEDS_MASK_I(MASK, BWD)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
+        if (LMFB_NEEDS_MASK_R(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
+        if (LMFB_NEEDS_MASK_I(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
         if (BWD && MASK != kStftOut) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
         // (prefetching the NEXT tile's samples was measured and dropped: in the backward kernel the
         // lines are evicted before use and the wave is read from DRAM twice, 707 -> 578 MB per launch)
@@ -211,7 +212,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         float* po = a.out + row_nm;
         LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
         MaskSets<AHEAD> ms;                         // issued before the barrier: the latency hides behind it
-        preload_masks<W, MASK, BWD, AHEAD>(w, sm, mr, mi, msf_bytes, ms);
+        preload_masks<W, MASK, BWD, AHEAD, GW>(w, sm, mr, mi, msf_bytes, ms);
         if constexpr (MASK == kStftOut) {           // no masks: the slot carries the output scale
 #pragma unroll
             for (int i = 0; i <= AHEAD; ++i) ms.m[i].vr[0] = valid ? 0.5f : 0.0f;
@@ -219,7 +220,13 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         LMFB_TICK(3);
         __syncthreads();
         LMFB_TICK(4);
-        fft_pass2<W, MASK, BWD, AHEAD>(w, col, pl, sm, ms, mr, mi, de, som_bytes, msf_bytes, gr, gi, inrow);
+        fft_pass2<W, MASK, BWD, AHEAD, GW>(w, col, pl, sm, ms, mr, mi, de, som_bytes, msf_bytes, gr, gi, inrow);
+        if constexpr (BWD && GW) {                  // gradient into the waveform: adjoint pass 1, overlap-add
+            __syncthreads();
+            fft_pass1_adj<W>(w, col, S + kTile);
+            __syncthreads();
+            unstage_tile<W>(w, lane, sl, a.gwave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
+        }
         LMFB_TICK(5);
         if constexpr (!BWD) {
             __syncthreads();
@@ -551,14 +558,16 @@ using namespace aas_lmfb;
 typedef void (*k1_fwd_fn)(const K1Args, const FwdTab);
 typedef void (*k1_bwd_fn)(const K1Args, const BwdTab);
 
-struct K1Variant { int warps, ctas; k1_fwd_fn fwd[3]; k1_bwd_fn bwd[4]; };   // indexed by mask mode (bwd[3]: STFT output)
+struct K1Variant { int warps, ctas; k1_fwd_fn fwd[3]; k1_bwd_fn bwd[4]; k1_bwd_fn bwd_gw[3]; };   // indexed by mask mode (bwd[3]: STFT output; bwd_gw: with the waveform gradient)
 
 #define LMFB_VARIANT(W, C)                                                                 \
     { W, C,                                                                                \
       { lmfb_k1<kMaskNone, false, W, C>, lmfb_k1<kMaskReim, false, W, C>,                  \
         lmfb_k1<kMaskPower, false, W, C> },                                                \
       { nullptr, lmfb_k1<kMaskReim, true, W, C>, lmfb_k1<kMaskPower, true, W, C>,          \
-        lmfb_k1<kStftOut, true, W, C> } }
+        lmfb_k1<kStftOut, true, W, C> },                                                   \
+      { lmfb_k1<kMaskNone, true, W, C, true>, lmfb_k1<kMaskReim, true, W, C, true>,        \
+        lmfb_k1<kMaskPower, true, W, C, true> } }
 
 // (warps per tile, resident CTAs per SM the register budget is sized for)
 static const K1Variant kVariants[] = {
@@ -762,22 +771,23 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
     return rc;
 }
 
-extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
+static int backward_impl(const aas_lmfb_plan* plan,
                                  const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
                                  const float* mask_r, const float* mask_i,
                                  int64_t mask_stride_n, int64_t mask_stride_f,
                                  const float* window,
                                  const float* out, const float* stats, const float* grad_out,
-                                 float* grad_mask_r, float* grad_mask_i,
+                                 float* grad_mask_r, float* grad_mask_i, float* grad_wave,
                                  void* workspace, int tmax,
                                  uint32_t flags, float eps, void* cuda_stream, void* const* prof) {
     int rc = check_common(plan, wave, lengths, n, mask_r, mask_i, window, tmax, flags);
     if (rc) return rc;
     if (n == 0) return AAS_LMFB_OK;
     const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
-    if (mask == AAS_LMFB_MASK_NONE) return AAS_LMFB_E_FLAGS;        // nothing to differentiate into
-    if (mask_stride_f < tmax || mask_stride_f > (1 << 22)) return AAS_LMFB_E_SHAPE;
-    if (!out || !grad_out || !workspace || !grad_mask_r || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
+    if (mask == AAS_LMFB_MASK_NONE && !grad_wave) return AAS_LMFB_E_FLAGS;        // nothing to differentiate into
+    if (mask != AAS_LMFB_MASK_NONE && (mask_stride_f < tmax || mask_stride_f > (1 << 22))) return AAS_LMFB_E_SHAPE;
+    if (!out || !grad_out || !workspace || (mask != AAS_LMFB_MASK_NONE && !grad_mask_r) || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
+    if ((uintptr_t)grad_wave & 7u) return AAS_LMFB_E_ALIGN;
     if (mask == AAS_LMFB_MASK_REIM && !grad_mask_i) return AAS_LMFB_E_NULL;
     if (((uintptr_t)out | (uintptr_t)grad_out | (uintptr_t)workspace | (uintptr_t)grad_mask_r |
          (uintptr_t)grad_mask_i | (uintptr_t)stats) & 3u) return AAS_LMFB_E_ALIGN;
@@ -818,10 +828,49 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
 
     const bool small = (long long)n * a.tiles_per_utt <= 148LL * kScratchPerSM;
     const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
+    if (mask == AAS_LMFB_MASK_NONE) { a.mask_r = a.mask_i = wave; a.gr = a.gi = nullptr; a.msf = (unsigned)tmax; a.msn = 0; }   // never dereferenced
+    a.gwave = grad_wave;
+    if (grad_wave) {                                             // the kernel ADDS (overlapping frames, reflect padding)
+        const cudaError_t e = cudaMemset2DAsync(grad_wave, (size_t)wave_stride * sizeof(float), 0,
+                                                (size_t)(wave_stride < (int64_t)tmax * kHop ? wave_stride : (int64_t)tmax * kHop) * sizeof(float),
+                                                (size_t)n, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     rec(prof, 0, stream);
-    rc = launch_k1(v, v.bwd[mask], a, plan->bwd, true, n, stream);
+    rc = grad_wave ? launch_k1(v, v.bwd_gw[mask], a, plan->bwd, true, n, stream)
+                   : launch_k1(v, v.bwd[mask], a, plan->bwd, true, n, stream);
     rec(prof, 1, stream);
     return rc;
+}
+
+
+extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
+                                 const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                                 const float* mask_r, const float* mask_i,
+                                 int64_t mask_stride_n, int64_t mask_stride_f,
+                                 const float* window,
+                                 const float* out, const float* stats, const float* grad_out,
+                                 float* grad_mask_r, float* grad_mask_i,
+                                 void* workspace, int tmax,
+                                 uint32_t flags, float eps, void* cuda_stream, void* const* prof) {
+    return backward_impl(plan, wave, lengths, n, wave_stride, mask_r, mask_i, mask_stride_n, mask_stride_f, window,
+                         out, stats, grad_out, grad_mask_r, grad_mask_i, nullptr, workspace, tmax, flags, eps,
+                         cuda_stream, prof);
+}
+
+extern "C" int aas_lmfb_backward_wave(const aas_lmfb_plan* plan,
+                                      const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                                      const float* mask_r, const float* mask_i,
+                                      int64_t mask_stride_n, int64_t mask_stride_f,
+                                      const float* window,
+                                      const float* out, const float* stats, const float* grad_out,
+                                      float* grad_mask_r, float* grad_mask_i, float* grad_wave,
+                                      void* workspace, int tmax,
+                                      uint32_t flags, float eps, void* cuda_stream) {
+    if (!grad_wave) return AAS_LMFB_E_NULL;
+    return backward_impl(plan, wave, lengths, n, wave_stride, mask_r, mask_i, mask_stride_n, mask_stride_f, window,
+                         out, stats, grad_out, grad_mask_r, grad_mask_i, grad_wave, workspace, tmax, flags, eps,
+                         cuda_stream, nullptr);
 }
 
 // STFT as an output: what BRNNmultiCH.forward takes as its input, (N, 2*F, T) with the real rows first

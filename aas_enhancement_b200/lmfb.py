@@ -102,7 +102,8 @@ class LMFB(torch.autograd.Function):
     wave (N, Lmax) f32 cuda zero-padded; lengths (N,) int32 cuda (samples); masks
     (N, 161, Tmax) f32 or None; plan a :class:`MelPlan`; window (320,) f32 cuda.
     Returns Z (N, M, Tmax) f32 with frames ``t >= T_i`` exactly zero, and frame_lens (N,)
-    int32 (``T_i = 1 + L_i // 160``).  Gradients flow to mask_r / mask_i.
+    int32 (``T_i = 1 + L_i // 160``).  Gradients flow to mask_r / mask_i and, when ``wave``
+    requires grad, to the waveform (``aas_lmfb_backward_wave``).
     """
 
     @staticmethod
@@ -173,9 +174,8 @@ class LMFB(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, _grad_lens):
         wave, lengths, mask_r, mask_i, window, out, stats = ctx.saved_tensors
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("gradient w.r.t. the waveform is not implemented")
-        if mask_r is None:
+        want_wave = ctx.needs_input_grad[0]
+        if mask_r is None and not want_wave:
             return (None,) * 10
         lib = _lib.load()
         dev = wave.device
@@ -183,7 +183,8 @@ class LMFB(torch.autograd.Function):
         grad_out = grad_out.contiguous()
         if grad_out.dtype != torch.float32:
             grad_out = grad_out.float()
-        gr = torch.empty_strided(mask_r.shape, mask_r.stride(), dtype=torch.float32, device=dev)
+        gr = torch.empty_strided(mask_r.shape, mask_r.stride(), dtype=torch.float32, device=dev) \
+            if mask_r is not None else None
         gi = torch.empty_strided(mask_i.shape, mask_i.stride(), dtype=torch.float32, device=dev) \
             if mask_i is not None else None
         ws_bytes = lib.aas_lmfb_workspace_bytes(n, plan.n_mels, tmax, ctx.flags)
@@ -191,13 +192,23 @@ class LMFB(torch.autograd.Function):
         msn, msf = ctx.strides
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib.aas_lmfb_backward(plan.handle, wave.data_ptr(), lengths.data_ptr(), n,
-                                       wave.stride(0), _ptr(mask_r), _ptr(mask_i), msn, msf,
-                                       window.data_ptr(), out.data_ptr(), stats.data_ptr(),
-                                       grad_out.data_ptr(), gr.data_ptr(), _ptr(gi), ws.data_ptr(),
-                                       tmax, ctx.flags, ctx.eps, stream, None)
+            if want_wave:
+                # gradient into the samples too (a waveform-domain enhancer in front of this op)
+                gw = torch.zeros_like(wave)
+                rc = lib.aas_lmfb_backward_wave(plan.handle, wave.data_ptr(), lengths.data_ptr(), n,
+                                                wave.stride(0), _ptr(mask_r), _ptr(mask_i), msn, msf,
+                                                window.data_ptr(), out.data_ptr(), stats.data_ptr(),
+                                                grad_out.data_ptr(), _ptr(gr), _ptr(gi), gw.data_ptr(),
+                                                ws.data_ptr(), tmax, ctx.flags, ctx.eps, stream)
+            else:
+                gw = None
+                rc = lib.aas_lmfb_backward(plan.handle, wave.data_ptr(), lengths.data_ptr(), n,
+                                           wave.stride(0), _ptr(mask_r), _ptr(mask_i), msn, msf,
+                                           window.data_ptr(), out.data_ptr(), stats.data_ptr(),
+                                           grad_out.data_ptr(), gr.data_ptr(), _ptr(gi), ws.data_ptr(),
+                                           tmax, ctx.flags, ctx.eps, stream, None)
         _lib.check(rc)
-        return None, None, gr, gi, None, None, None, None, None, None
+        return gw, None, gr, gi, None, None, None, None, None, None
 
 
 class LMFBFrontEnd(torch.nn.Module):

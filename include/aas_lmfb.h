@@ -99,6 +99,25 @@ int aas_lmfb_backward(const aas_lmfb_plan* plan,
                       void* workspace, int tmax,
                       uint32_t flags, float eps, void* cuda_stream, void* const* prof);
 
+/* Backward that ALSO returns the gradient w.r.t. the waveform (second half):
+ * what autograd would give a waveform-domain enhancer feeding this front-end.  Same arguments as
+ * aas_lmfb_backward plus
+ *   grad_wave  (N, wave_stride) fp32, 8-byte aligned, same layout as `wave`; the library zeroes
+ *              the first min(wave_stride, 160*tmax) samples of every row and accumulates into them
+ *              (frames overlap, and the reflect padding folds the ends of an utterance back);
+ *              samples past lengths[n] stay zero.
+ * With MASK_NONE the mask pointers and grad_mask_r/i may be NULL (only the waveform takes a
+ * gradient).  The result is deterministic up to the order of the few additions per sample. */
+int aas_lmfb_backward_wave(const aas_lmfb_plan* plan,
+                           const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                           const float* mask_r, const float* mask_i,
+                           int64_t mask_stride_n, int64_t mask_stride_f,
+                           const float* window,
+                           const float* out, const float* stats, const float* grad_out,
+                           float* grad_mask_r, float* grad_mask_i, float* grad_wave,
+                           void* workspace, int tmax,
+                           uint32_t flags, float eps, void* cuda_stream);
+
 /* STFT as an output (first half): the input BRNNmultiCH.forward takes,
  * `(N, nCH*F*2, T)` with the F real rows first and the F imaginary rows second
  * (Speech_enhancement_by_AAS/model.py:170, :186-188), computed from the waveform with the same

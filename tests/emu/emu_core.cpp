@@ -15,7 +15,7 @@ template <int W, int MASK, bool BWD>
 void emu_tile(const float* wave_row, int len, int t0, const float* window, bool vec_ok,
               const typename TabOf<BWD>::Param& tab, const float* mr, const float* mi, unsigned msf,
               const float* dE, float* out, unsigned som, float* gr, float* gi, int tmax, int T,
-              std::vector<float2>& S) {
+              std::vector<float2>& S, float* gwave_row = nullptr) {
     typename TabOf<BWD>::Smem sm;
     tables_fill(&sm, tab, 0, 1);
     window_fill(S.data(), window, 0, 1);
@@ -43,11 +43,28 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
             const float* dep = dE ? dE + t + clamp : nullptr;
             constexpr int AHEAD = BWD ? 1 : 2;
             MaskSets<AHEAD> ms;
-            preload_masks<W, MASK, BWD, AHEAD>(w, sm, mrp, mip, msf * 4u, ms);
-            fft_pass2<W, MASK, BWD, AHEAD>(w, Sin.data() + lane, reinterpret_cast<float*>(S.data()) + lane, sm, ms,
-                                    mrp, mip, dep, som * 4u, msf * 4u,
-                                    gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
+            if (BWD && gwave_row) preload_masks<W, MASK, BWD, AHEAD, true>(w, sm, mrp, mip, msf * 4u, ms);
+            else                  preload_masks<W, MASK, BWD, AHEAD, false>(w, sm, mrp, mip, msf * 4u, ms);
+            if (BWD && gwave_row)
+                fft_pass2<W, MASK, BWD, AHEAD, true>(w, Sin.data() + lane, reinterpret_cast<float*>(S.data()) + lane, sm, ms,
+                                        mrp, mip, dep, som * 4u, msf * 4u,
+                                        gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
+            else
+                fft_pass2<W, MASK, BWD, AHEAD, false>(w, Sin.data() + lane, reinterpret_cast<float*>(S.data()) + lane, sm, ms,
+                                        mrp, mip, dep, som * 4u, msf * 4u,
+                                        gr ? gr + t : nullptr, gi ? gi + t : nullptr, inrow);
         }
+    if (BWD && gwave_row) {                                // gradient into the waveform (adjoint pass 1, overlap-add)
+        for (int w = 0; w < W; ++w)
+            for (int lane = 0; lane < 32; ++lane) fft_pass1_adj<W>(w, Sin.data() + lane, Sin.data() + kTile);
+        for (int w = 0; w < W; ++w)
+            for (int lane = 0; lane < 32; ++lane) {
+                StageLane sl;
+                stage_lane_init(lane, Sin.data(), sl);
+                const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;
+                unstage_tile<W>(w, lane, sl, gwave_row, len, t0, n_rows, Sin.data(), vec_ok);
+            }
+    }
     if constexpr (!BWD) {
         for (int w = 0; w < W; ++w)
             for (int lane = 0; lane < 32; ++lane)
@@ -64,7 +81,7 @@ template <int W, int MASK>
 void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_utt, long long wave_stride,
                  const float* mask_r, const float* mask_i, long long msn, long long msf,
                  const float* window, const FwdTab& ft, const BwdTab& bt, float* out, const float* dE,
-                 float* gr, float* gi, int tmax, int vec_ok) {
+                 float* gr, float* gi, int tmax, int vec_ok, float* gwave = nullptr) {
     const int tiles = (tmax + kTile - 1) / kTile;
     const int n_mels = ft.n_mels;
     std::vector<float2> S(kSlots * kPitch);
@@ -96,8 +113,8 @@ void emu_k1_impl(int bwd, const float* wave, const int* lengths, int n_utt, long
                                          out + nb, som, nullptr, nullptr, tmax, T, S);
             else
                 emu_tile<W, MASK, true>(wr, len, t0, window, vec_ok != 0, bt, mr, mi, (unsigned)msf, dE + nb,
-                                        nullptr, som, gr + (long long)n * msn, gi ? gi + (long long)n * msn : nullptr,
-                                        tmax, T, S);
+                                        nullptr, som, gr ? gr + (long long)n * msn : nullptr, gi ? gi + (long long)n * msn : nullptr,
+                                        tmax, T, S, gwave ? gwave + (long long)n * wave_stride : nullptr);
         }
 }
 
@@ -105,7 +122,7 @@ template <int W>
 int emu_k1_w(int bwd, int mask_mode, const float* wave, const int* lengths, int n_utt,
              long long wave_stride, const float* mask_r, const float* mask_i,
              long long msn, long long msf, const float* window, const float* mel, int n_mels,
-             float* out, const float* dE, float* gr, float* gi, int tmax, int vec_ok) {
+             float* out, const float* dE, float* gr, float* gi, int tmax, int vec_ok, float* gwave) {
     FwdTab ft;
     BwdTab bt;
     int ml[kBins];
@@ -113,9 +130,9 @@ int emu_k1_w(int bwd, int mask_mode, const float* wave, const int* lengths, int 
     build_bwd_tab(ft, ml, &bt);
     set_warp_ranges(&ft, ml, W);
     switch (mask_mode) {
-        case kMaskNone:  emu_k1_impl<W, kMaskNone>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, ft, bt, out, dE, gr, gi, tmax, vec_ok); break;
-        case kMaskReim:  emu_k1_impl<W, kMaskReim>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, ft, bt, out, dE, gr, gi, tmax, vec_ok); break;
-        case kMaskPower: emu_k1_impl<W, kMaskPower>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, ft, bt, out, dE, gr, gi, tmax, vec_ok); break;
+        case kMaskNone:  emu_k1_impl<W, kMaskNone>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, ft, bt, out, dE, gr, gi, tmax, vec_ok, gwave); break;
+        case kMaskReim:  emu_k1_impl<W, kMaskReim>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, ft, bt, out, dE, gr, gi, tmax, vec_ok, gwave); break;
+        case kMaskPower: emu_k1_impl<W, kMaskPower>(bwd, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, ft, bt, out, dE, gr, gi, tmax, vec_ok, gwave); break;
         default: return -4;
     }
     return 0;
@@ -127,8 +144,8 @@ int emu_k1_w(int bwd, int mask_mode, const float* wave, const int* lengths, int 
 extern "C" int emu_k1(int warps, int bwd, int mask_mode, const float* wave, const int* lengths, int n_utt,
                       long long wave_stride, const float* mask_r, const float* mask_i,
                       long long msn, long long msf, const float* window, const float* mel, int n_mels,
-                      float* out, const float* dE, float* gr, float* gi, int tmax, int vec_ok) {
-#define CALL(W) return emu_k1_w<W>(bwd, mask_mode, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mel, n_mels, out, dE, gr, gi, tmax, vec_ok)
+                      float* out, const float* dE, float* gr, float* gi, int tmax, int vec_ok, float* gwave) {
+#define CALL(W) return emu_k1_w<W>(bwd, mask_mode, wave, lengths, n_utt, wave_stride, mask_r, mask_i, msn, msf, window, mel, n_mels, out, dE, gr, gi, tmax, vec_ok, gwave)
     switch (warps) {
         case 1: CALL(1);
         case 2: CALL(2);

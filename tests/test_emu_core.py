@@ -23,12 +23,12 @@ def emu(tmp_path_factory):
     vp = ctypes.c_void_p
     lib.emu_k1.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_longlong,
                            vp, vp, ctypes.c_longlong, ctypes.c_longlong, vp, vp, ctypes.c_int, vp, vp, vp, vp,
-                           ctypes.c_int, ctypes.c_int]
+                           ctypes.c_int, ctypes.c_int, vp]
     lib.emu_mel_band.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     return lib
 
 
-def _k1(lib, warps, bwd, mode, b, mel, window, dE=None, vec_ok=1):
+def _k1(lib, warps, bwd, mode, b, mel, window, dE=None, vec_ok=1, want_wave_grad=False):
     modes = {"none": 0, "reim": 1, "power": 2}
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     wave, mr, mi = f32(b["wave"]), f32(b["mask_r"]), f32(b["mask_i"])
@@ -39,13 +39,17 @@ def _k1(lib, warps, bwd, mode, b, mel, window, dE=None, vec_ok=1):
     gr = np.full_like(mr, np.nan)
     gi = np.full_like(mi, np.nan)
     dE = f32(dE) if dE is not None else np.zeros_like(out)
+    gw = np.zeros_like(wave) if want_wave_grad else None
     rc = lib.emu_k1(warps, int(bwd), modes[mode], wave.ctypes.data, lens.ctypes.data, n, wave.shape[1],
                     mr.ctypes.data if mode != "none" else None,
                     mi.ctypes.data if mode == "reim" else None,
                     mr.shape[1] * mr.shape[2], mr.shape[2], win.ctypes.data, melf.ctypes.data,
-                    mel.shape[0], out.ctypes.data, dE.ctypes.data, gr.ctypes.data, gi.ctypes.data,
-                    tmax, vec_ok)
+                    mel.shape[0], out.ctypes.data, dE.ctypes.data,
+                    gr.ctypes.data if mode != "none" else None, gi.ctypes.data if mode == "reim" else None,
+                    tmax, vec_ok, gw.ctypes.data if want_wave_grad else None)
     assert rc == 0
+    if want_wave_grad:
+        return out, gr, gi, gw
     return out, gr, gi
 
 
@@ -129,6 +133,36 @@ def test_emulated_forward_other_bases(emu, n_mels, warps):
     _, gr, gi = _k1(emu, warps, 1, "reim", b, mel, window, dE=dE)
     assert orc.rel_err(gr, g_ref["grad_mask_r"]) < 2e-5
     assert orc.rel_err(gi, g_ref["grad_mask_i"]) < 2e-5
+
+
+@pytest.mark.parametrize("mode,warps", [("none", 3), ("reim", 4), ("power", 2), ("reim", 5)])
+@pytest.mark.parametrize("length", [5000, 4999, 161, 700])
+def test_emulated_wave_gradient(emu, mode, warps, length):
+    """Gradient into the waveform (adjoint split / DFT5 / FFT32 / window / overlap-add with the
+    reflect padding folded back) against float64 autograd; the mask gradients must not change."""
+    b = _synth.make_batch(2, length, seed=length + warps, ragged=True)
+    mel, window = orc.mel_filterbank(), orc.hamming_window()
+    mel32 = mel.astype(np.float32).astype(np.float64)
+    win32 = window.astype(np.float32).astype(np.float64)
+    mr = b["mask_r"] if mode != "none" else None
+    mi = b["mask_i"] if mode == "reim" else None
+    y_ref, fl = orc.lmfb_forward(b["wave"], b["lengths"], mr, mi, mel32, win32, mask_mode=mode, cmvn_mode="none")
+    g_ref = orc.lmfb_grads(b["wave"], b["lengths"], mr, mi, b["grad_out"], mel32, win32,
+                           mask_mode=mode, cmvn_mode="none", want_wave_grad=True)
+    dE = b["grad_out"].astype(np.float64) * np.exp(-y_ref)
+    for i in range(2):
+        dE[i, :, fl[i]:] = 0.0
+    _, gr, gi, gw = _k1(emu, warps, 1, mode, b, mel, window, dE=dE, want_wave_grad=True, vec_ok=int(length % 2 == 0))
+    ref = g_ref["grad_wave"]
+    for i in range(2):
+        li = int(b["lengths"][i])
+        assert np.all(gw[i, li:] == 0.0)                       # nothing beyond the utterance
+    assert orc.rel_err(gw, ref) < 5e-5
+    tol = 2e-5 if length > 320 else 2e-4      # two reflect-padded frames: the imaginary parts are cancellation noise
+    if mode != "none":
+        assert orc.rel_err(gr, g_ref["grad_mask_r"]) < tol
+    if mode == "reim":
+        assert orc.rel_err(gi, g_ref["grad_mask_i"]) < tol
 
 
 def test_mel_band_tables(emu):

@@ -186,6 +186,47 @@ def test_stft_output_matches_oracle_and_feeds_the_reference_glue(be, n, length):
     assert orc.rel_err(z.detach().cpu().numpy(), glue.numpy()) < TOL
 
 
+# ------------------------------------------------------------------ gradient into the waveform
+@pytest.mark.parametrize("mask_mode,cmvn_mode", [("none", "per_bin"), ("reim", "per_bin"), ("power", "none"), ("reim", "global")])
+@pytest.mark.parametrize("n,length", [(3, 9000), (2, 161), (48, 80000)])
+def test_wave_gradient_matches_float64_autograd(be, mask_mode, cmvn_mode, n, length):
+    """aas_lmfb_backward_wave through autograd: d/d wave of sum(Z * g) against the float64 oracle
+    (adjoint STFT with the reflect padding folded back, overlap-add across tiles; the largest case
+    is scheduled with cluster launch control), next to unchanged mask gradients."""
+    if n == 48 and (mask_mode, cmvn_mode) != ("reim", "per_bin"):
+        pytest.skip("one large case is enough")
+    if length < 320:
+        cmvn_mode = "none"          # two frames: the CMVN of two samples is +-0.707 whatever the input (no usable gradient)
+    b = _synth.make_batch(n, length, seed=length + n, ragged=True)
+    fe = be.LMFBFrontEnd(mask_mode=mask_mode, cmvn_mode=cmvn_mode).cuda()
+    wave, lengths, mr, mi = _dev(b, mask_mode)
+    wave.requires_grad_(True)
+    z, fl = fe(wave, lengths, mr, mi)
+    g = torch.from_numpy(b["grad_out"]).cuda()
+    z.backward(g)
+    mel = fe.mel_basis.cpu().numpy().astype(np.float64)
+    win = fe.window.cpu().numpy().astype(np.float64)
+    ref = orc.lmfb_grads(b["wave"], b["lengths"], b["mask_r"] if mr is not None else None,
+                         b["mask_i"] if mi is not None else None, b["grad_out"], mel, win,
+                         mask_mode=mask_mode, cmvn_mode=cmvn_mode, want_wave_grad=True)
+    gw = wave.grad.cpu().numpy()
+    for i in range(n):
+        assert np.all(gw[i, int(b["lengths"][i]):] == 0.0)
+    assert np.isfinite(gw).all()
+    assert orc.rel_err(gw, ref["grad_wave"]) < TOL
+    tol = TOL if length > 320 else 3e-4
+    if mr is not None:
+        assert orc.rel_err(mr.grad.cpu().numpy(), ref["grad_mask_r"]) < tol
+    if mi is not None:
+        assert orc.rel_err(mi.grad.cpu().numpy(), ref["grad_mask_i"]) < tol
+    # the call without the waveform gradient gives the same mask gradients, bit for bit
+    if mr is not None:
+        wave2, _, mr2, mi2 = _dev(b, mask_mode)
+        z2, _ = fe(wave2, lengths, mr2, mi2)
+        z2.backward(g)
+        assert torch.equal(mr2.grad, mr.grad)
+
+
 # ------------------------------------------------------------------ properties
 @pytest.mark.parametrize("seconds", [10, 17])
 def test_cmvn_backward_long_rows(be, seconds):
