@@ -345,7 +345,7 @@ def measure_e2e(fe, n, samples, tmax, n_mels, audio_s, dev, steps, world):
     import torch.distributed as dist
     gen = torch.Generator()
     gen.manual_seed(123)
-    nbuf = 2
+    nbuf = int(os.environ.get("AAS_BENCH_E2E_NBUF", "2"))      # buffers in flight (experiment knob)
     host_in = []
     for _ in range(nbuf):
         host_in.append(dict(
