@@ -680,6 +680,7 @@ LMFB_HD void unstage_tile(int w, int lane, const StageLane& sl, float* __restric
 // the caller issues those loads before the block barrier that ends pass 1.
 template <int AHEAD>
 struct MaskSets { StepMasks m[AHEAD + 1]; };
+constexpr int kAheadFwd = 1, kAheadBwd = 1;
 
 template <int W, int MASK, bool BWD, int AHEAD, bool GW, class SM>
 LMFB_HD void preload_masks(int w, const SM& sm, const float* __restrict__ mr, const float* __restrict__ mi,

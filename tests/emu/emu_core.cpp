@@ -41,7 +41,7 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
             const float* mrp = mr ? mr + t + clamp : nullptr;
             const float* mip = mi ? mi + t + clamp : nullptr;
             const float* dep = dE ? dE + t + clamp : nullptr;
-            constexpr int AHEAD = BWD ? 1 : 2;
+            constexpr int AHEAD = BWD ? kAheadBwd : kAheadFwd + 1;   // (the forward emulation keeps exercising the three-set rotation)
             MaskSets<AHEAD> ms;
             if (BWD && gwave_row) preload_masks<W, MASK, BWD, AHEAD, true>(w, sm, mrp, mip, msf * 4u, ms);
             else                  preload_masks<W, MASK, BWD, AHEAD, false>(w, sm, mrp, mip, msf * 4u, ms);
