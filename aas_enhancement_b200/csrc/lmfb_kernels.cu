@@ -49,7 +49,6 @@ struct K1Args {
     float*         gwave;      // backward with GW: (N, wave_stride) gradient w.r.t. the samples, zeroed by the caller of the kernel
 };
 
-constexpr int kScratchPerSM = 5;            // 5 x (42,240 + 1,024) B of shared memory fit one SM
 
 // ---- dynamic tile scheduling with cluster launch control (sm_100) -------------------------------
 // The grid has one CTA per tile, but only the resident CTAs ever run: a running CTA asks the
