@@ -324,6 +324,10 @@ def run_ours(args):
                      "k1_bwd_frac": frames * B_K1_BWD / (k_avg["k1_bwd"] / 1e3) / 1e9 / peak,
                      "step_algorithmic_gbs_per_gpu": step_gbs, "step_frac": step_gbs / peak},
     }
+    if args.no_e2e or args.pad_rows:
+        line["experiment"] = ("not a bench line: " + ", ".join(
+            x for x in ("end-to-end leg skipped" if args.no_e2e else "",
+                        "mask rows padded to %d frames (not the reference layout)" % args.pad_rows if args.pad_rows else "") if x))
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(n, samples, budget_s=12.0)
     print(json.dumps(line))
