@@ -75,7 +75,7 @@ constexpr int kPitch = 33;             // float2 per scratch slot (32 lanes + 1 
 constexpr int kRow   = 2 * kPitch;     // floats per scratch slot row
 constexpr int kSlots = 160;
 constexpr int kMaxMels = 128;
-constexpr int kScratchBytes = kSlots * kPitch * 8;     // 42,240 B per tile
+constexpr int kScratchBytes = kSlots * kPitch * 8 + 128;   // 42,240 B of slots + one 32-float row for the power of bin 160
 constexpr int kMaxW = 8;               // most warps that may share a tile
 
 enum MaskMode { kMaskNone = 0, kMaskReim = 1, kMaskPower = 2,
@@ -102,30 +102,40 @@ LMFB_HD void dispatch_warp(int w, F&& f) {
 }
 
 // ---- tables -------------------------------------------------------------------------------
-// Banded-2 form of the mel basis (built on the host, mel_band.hpp): bin f feeds filters ml(f)
-// (weight wl) and ml(f)+1 (weight wh) with ml non-decreasing.  Weights already carry the 1/4 that
-// undoes X' = 2X.  The tables travel as a kernel parameter and are copied once per persistent
-// CTA into shared memory behind the scratch.
-constexpr int kGroups = kSlots / 8;            // phase 3 walks bins 0..159 in groups of 8; bin 160 is peeled
+// Forward: "walkable" bases (banded-2, see FwdTab) are walked bin by bin with two running sums;
+// any other basis (dense, re-ordered, hand-made) is a GATHER per filter over its row [lo, lo + cnt)
+// with the weights read from the caller's device copy of the (M, 161) matrix.  The spectrum is
+// carried as X' = 2X; the 1/4 is folded into the walk's weights / applied at the end of the gather.
+// Backward: per pass-2 step and output, the two dE rows (d, d+1) a bin's gradient is formed from
+// and their weights ("banded": every bin feeds at most two adjacent filters; other bases go
+// through a precomputed dP = B^T dE, see lmfb_kernels.cu).
+// The tables travel as a kernel parameter and are copied once per persistent CTA into shared
+// memory behind the scratch.
+constexpr int kGroups = kSlots / 8;            // phase 3 (walk) goes over bins 0..159 in groups of 8; bin 160 is peeled
 
 struct FwdTab {                                // forward kernel parameter
-    float2  w[kBins];                          // (wl, wh) of bin f
-    uint8_t hmask[kGroups + 4];                // bit i of byte g: the band moves on before bin 8g+i (adv != 0)
-    uint8_t adv[kBins + 3];                    // ml(f) - ml(f-1): filters completed before bin f (0 for f = 0)
-    uint8_t lo[kMaxW];                         // phase 3: warp w produces partial sums of filters lo[w] .. hi[w]
-    uint8_t hi[kMaxW];                         //          (hi may exceed n_mels - 1; lo > hi: warp has no bins)
-    int     n_mels;
-    int     multi;                             // some bin completes more than one filter (adv > 1)
+    // "walkable" bases (banded-2: bin f feeds filters ml(f) (weight wl) and ml(f)+1 (weight wh) with ml
+    // non-decreasing -- every triangular filterbank); weights carry the 1/4 that undoes X' = 2X
+    float2   w[kBins];                         // (wl, wh) of bin f
+    uint8_t  hmask[kGroups + 4];               // bit i of byte g: the band moves on before bin 8g+i (adv != 0)
+    uint8_t  adv[kBins + 3];                   // ml(f) - ml(f-1): filters completed before bin f (0 for f = 0)
+    uint8_t  lo[kMaxW];                        // phase 3: warp w produces partial sums of filters lo[w] .. hi[w]
+    uint8_t  hi[kMaxW];                        //          (hi may exceed n_mels - 1; lo > hi: warp has no bins)
+    // any other basis: filter m is the row [lo, lo + cnt) of the caller's device matrix
+    uint32_t row[kMaxMels];                    // lo | cnt << 8
+    int      n_mels;
+    int      multi;                            // some bin completes more than one filter (adv > 1)
+    int      walkable;
 };
 struct BwdTab {                                // backward kernel parameter, per pass-2 step k2 and output k1
     float    w[17][5][4];                      // wl_f, wh_f, wl_fp, wh_fp: weights of the dE rows (d, d+1)
     uint32_t d[17][5][2];                      // dE row d of bin f and of bin fp = 160 - f (d+1 is always valid)
-    int      n_mels;
+    int      n_mels;                           // rows of the dE tensor
     int      pad_;
 };
 // shared-memory image: the per-step constants of the algorithm, then the parameter above
 struct alignas(16) StepEnt { uint32_t f[5]; float sn[5]; float cs[5]; uint32_t pad_; };     // 64 B
-struct alignas(16) FwdSmem { StepEnt step[17]; float2 w[kBins]; uint8_t hmask[kGroups + 4]; uint8_t adv[kBins + 3]; };
+struct alignas(16) FwdSmem { StepEnt step[17]; float2 w[kBins]; uint8_t hmask[kGroups + 4]; uint8_t adv[kBins + 3]; uint32_t row[kMaxMels]; };
 struct alignas(16) BwdSmem { StepEnt step[17]; float w[17][5][4]; uint32_t d[17][5][2]; };
 constexpr int kTabBytesFwd = (int)((sizeof(FwdSmem) + 15) / 16 * 16);
 constexpr int kTabBytesBwd = (int)((sizeof(BwdSmem) + 15) / 16 * 16);
@@ -146,9 +156,9 @@ LMFB_CX int slot_of_packed(int j) {            // j in [0,160): packed-sample in
 LMFB_CX int bin_of(int k2, int k1) { return (96 * k1 + 65 * k2) % 160; }
 // float offset (inside the scratch, before adding the lane) of the masked power of bin f after
 // pass 2: the first 32 floats of slot row f (row f = columns f mod 32 of sub-transform f / 32 is
-// one of the rows the producing step has just consumed); bin 160 takes the second 32 floats of row 0
-LMFB_CX int p_off(int f) { return f == kBins - 1 ? kTile : f * kRow; }
-// float offset of partial-sum row r of phase 3: second 32 floats of slot row 1 + r
+// one of the rows the producing step has just consumed); bin 160 has a row of its own behind the slots
+LMFB_CX int p_off(int f) { return f * kRow; }
+// float offset of partial-sum row r of phase 3 (walk): second 32 floats of slot row 1 + r
 LMFB_CX int e_off(int r) { return (1 + r) * kRow + kTile; }
 
 // 'reflect' padding index (numpy semantics, any offset, length >= 1)
@@ -432,9 +442,13 @@ LMFB_HD void fill_steps(StepEnt* st, int tid, int nthreads) {
 }
 LMFB_HD void tables_fill(FwdSmem* sm, const FwdTab& tab, int tid, int nthreads) {
     fill_steps(sm->step, tid, nthreads);
-    copy_words(reinterpret_cast<uint32_t*>(sm->w), reinterpret_cast<const uint32_t*>(tab.w), 2 * kBins, tid, nthreads);
-    copy_words(reinterpret_cast<uint32_t*>(sm->hmask), reinterpret_cast<const uint32_t*>(tab.hmask),
-               (kGroups + 4 + kBins + 3) / 4, tid, nthreads);                // hmask and adv are adjacent in both structs
+    if (tab.walkable) {
+        copy_words(reinterpret_cast<uint32_t*>(sm->w), reinterpret_cast<const uint32_t*>(tab.w), 2 * kBins, tid, nthreads);
+        copy_words(reinterpret_cast<uint32_t*>(sm->hmask), reinterpret_cast<const uint32_t*>(tab.hmask),
+                   (kGroups + 4 + kBins + 3) / 4, tid, nthreads);                // hmask and adv are adjacent in both structs
+    } else {
+        copy_words(sm->row, tab.row, kMaxMels, tid, nthreads);
+    }
 }
 LMFB_HD void tables_fill(BwdSmem* sm, const BwdTab& tab, int tid, int nthreads) {
     fill_steps(sm->step, tid, nthreads);
@@ -549,9 +563,7 @@ LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl
         split_pair(Ar[k1], Ai[k1], Br[kp], Bi[kp], k.sn[k1], k.cs[k1], xf, xp);
         if constexpr (!BWD) {
             pl[f * kRow] = masked_power<MASK>(xf, in.vr[k1], in.vi[k1]);
-            // bin 160 (the partner of bin 0, which only output k1 = 0 can produce) sits beside bin 0
-            const uint32_t po = (k1 == 0 && f == 0) ? (uint32_t)kTile : fp * kRow;
-            pl[po] = masked_power<MASK>(xp, in.vr[5 + k1], in.vi[5 + k1]);
+            pl[fp * kRow] = masked_power<MASK>(xp, in.vr[5 + k1], in.vi[5 + k1]);    // (bin 160: the row behind the slots)
         } else if constexpr (MASK == kStftOut) {
             // the spectrum is carried as X' = 2X; `dE` doubles as nothing here, the scale (0.5 for
             // frames that exist, 0 beyond) arrives in the first mask slot
@@ -781,7 +793,8 @@ LMFB_HD void phase3_walk(int w, float* __restrict__ pl, const FwdSmem& sm, const
 
 template <int W>
 LMFB_HD void phase3_finish(int w, const float* __restrict__ pl, const FwdTab& tab,
-                           float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid) {
+                           float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid,
+                           bool first = true, bool last = true) {
     const int n_mels = tab.n_mels;
     const int per = (n_mels + W - 1) / W;
     const int m_lo = w * per, m_hi = m_lo + per < n_mels ? m_lo + per : n_mels;
@@ -792,9 +805,50 @@ LMFB_HD void phase3_finish(int w, const float* __restrict__ pl, const FwdTab& ta
 #pragma unroll
         for (int wi = 0; wi < W; ++wi)
             if (m >= (int)tab.lo[wi] && m <= (int)tab.hi[wi]) e += pl[e_off(2 * wi) + m * kRow];
-        const float y = valid ? log1pf(e) : 0.0f;
+        if (!first) e += inrow ? *op : 0.0f;                 // multi-channel: partial sums of E travel through `out`
+        const float y = last ? (valid ? log1pf(e) : 0.0f) : e;
         st_if(op, y, inrow);
         op = at_row(op, 1u, som_bytes);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// phase 3 for ANY other basis (the reference applies whatever (M, F) matrix it is given with a k=1
+// conv1d, model.py:167, :196): a gather.  Filters are dealt round-robin to the W warps; a warp
+// forms E[m] = 1/4 sum_f B[m, f] P'[f] over the filter's row [lo, lo + cnt) with the weights read
+// from the caller's device copy of the matrix (same address in every lane: a broadcast load),
+// applies log1p and stores the row segment.  One pass, no partial sums.  Measured on the default
+// basis (weights in shared memory, two bins per load): 7 % slower than walk + finish -- the per-filter
+// chains are latency-bound -- which is why triangular filterbanks keep the walk.
+//   mel : device (M, 161) matrix
+//   first / last : multi-channel input: channel 0 / the last channel; in between the partial sums
+//         of E travel through `out` (the same thread writes and reads them)
+// ---------------------------------------------------------------------------------------
+template <int W>
+LMFB_HD void phase3_gather(int w, const float* __restrict__ pl, const FwdSmem& sm, int n_mels,
+                           const float* __restrict__ mel, float* __restrict__ out, unsigned som_bytes,
+                           bool inrow, bool valid, bool first, bool last) {
+    float* op = at_row(out, (uint32_t)w, som_bytes);
+#pragma unroll 1
+    for (int m = w; m < n_mels; m += W) {
+        const uint32_t d = sm.row[m];
+        const int lo = (int)(d & 255u), c = (int)(d >> 8);
+        const float* pp = pl + lo * kRow;
+        const float* wr = mel + m * kBins + lo;
+        float a0 = 0.0f, a1 = 0.0f;
+        int i = 0;
+#pragma unroll 1
+        for (; i + 2 <= c; i += 2) {
+            a0 = fmaf(LMFB_LDG(wr + i), pp[0], a0);
+            a1 = fmaf(LMFB_LDG(wr + i + 1), pp[kRow], a1);
+            pp += 2 * kRow;
+        }
+        if (i < c) a0 = fmaf(LMFB_LDG(wr + i), pp[0], a0);
+        float e = 0.25f * (a0 + a1);
+        if (!first) e += inrow ? *op : 0.0f;
+        const float y = last ? (valid ? log1pf(e) : 0.0f) : e;
+        st_if(op, y, inrow);
+        op = at_row(op, (uint32_t)W, som_bytes);
     }
 }
 

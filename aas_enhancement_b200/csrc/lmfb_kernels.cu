@@ -47,6 +47,10 @@ struct K1Args {
     long long*     timeline;   // debug builds (-DLMFB_TIMELINE) only: per-warp phase clocks
     int            dynamic;    // tiles handed out by cluster launch control (grid = one CTA per tile)
     float*         gwave;      // backward with GW: (N, wave_stride) gradient w.r.t. the samples, zeroed by the caller of the kernel
+    const float*   mel;        // forward, generic basis only: device copy of the (M, 161) matrix
+    int            n_ch;       // channels per utterance (model.py:167: the basis repeats over channels, i.e. power sums)
+    long long      wave_stride_ch;   // samples between the channels of an utterance
+    long long      wave_len;   // samples of a row that may be read (lengths are clamped to it); 0: trust lengths
 };
 
 
@@ -139,16 +143,22 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
     for (int tile = blockIdx.x; tile < a.total_tiles; ) {
       if (a.dynamic && threadIdx.x == 0) clc_request(clc_resp, clc_bar);
       do {
-        const int n   = tile / a.tiles_per_utt;
-        const int t0  = (tile - n * a.tiles_per_utt) * kTile;
+        // forward: a tile belongs to an utterance and loops over its channels (the power sums);
+        // backward: every (utterance, channel) has tiles of its own (they share only dE)
+        const int nn  = tile / a.tiles_per_utt;
+        const int t0  = (tile - nn * a.tiles_per_utt) * kTile;
+        const int n   = BWD ? nn / a.n_ch : nn;
+        const int ch0 = BWD ? nn - n * a.n_ch : 0;
+        const int nch = BWD ? 1 : a.n_ch;
         const int t   = t0 + lane;
-        const int len = a.lengths[n];
+        int len = a.lengths[n];
+        if (a.wave_len > 0 && (long long)len > a.wave_len) len = (int)a.wave_len;
         int T = len >= 1 ? 1 + len / kHop : 0;
         T = T < a.tmax ? T : a.tmax;
         const bool inrow = t < a.tmax;
         const bool valid = t < T;
         const long long row_nm = (long long)n * n_mels * som + t;
-        const long long moff = (long long)n * a.msn + t;
+        const long long moff0 = (long long)n * a.msn + (long long)ch0 * kBins * a.msf + t;
 
         if (t0 >= T) {                              // tile lies entirely in the zero padding
             if (inrow) {
@@ -158,25 +168,32 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
                 } else if (MASK != kMaskNone) {
 #pragma unroll 4
                     for (int f = w; f < kBins; f += W) {
-                        a.gr[moff + (unsigned)f * a.msf] = 0.0f;
-                        if (MASK == kMaskReim || MASK == kStftOut) a.gi[moff + (unsigned)f * a.msf] = 0.0f;
+                        a.gr[moff0 + (unsigned)f * a.msf] = 0.0f;
+                        if (MASK == kMaskReim || MASK == kStftOut) a.gi[moff0 + (unsigned)f * a.msf] = 0.0f;
                     }
                 }
             }
             break;
         }
 
+#ifdef LMFB_TIMELINE
+      long long tl[8];
+#endif
+      for (int ch = ch0; ch < ch0 + nch; ++ch) {
+        const long long moff = moff0 + (BWD ? 0 : (long long)ch * kBins * a.msf);
+        const float* wave_row = a.wave + (long long)n * a.wave_stride + (long long)ch * a.wave_stride_ch;
+        if (!BWD && ch > ch0) __syncthreads();      // the previous channel's gather has read the scratch
+
 #ifndef LMFB_DBG_NOPREFETCH
         // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs ...
-        if (LMFB_NEEDS_MASK_R(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
-        if (LMFB_NEEDS_MASK_I(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (long long)n * a.msn, a.msf, kBins, t0, a.tmax);
+        if (LMFB_NEEDS_MASK_R(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (moff - t), a.msf, kBins, t0, a.tmax);
+        if (LMFB_NEEDS_MASK_I(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (moff - t), a.msf, kBins, t0, a.tmax);
         if (BWD && MASK != kStftOut) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
         // (prefetching the NEXT tile's samples was measured and dropped: in the backward kernel the
         // lines are evicted before use and the wave is read from DRAM twice, 707 -> 578 MB per launch)
 #endif
 
 #ifdef LMFB_TIMELINE
-        long long tl[8];
 // after a barrier the clock is only meaningful once something protected by the barrier has been
 // touched (BAR.SYNC is deferred-blocking): read a shared word first
 #define LMFB_TICK(i) do { volatile float* vs_ = reinterpret_cast<volatile float*>(S); float x_ = vs_[lane]; \
@@ -188,7 +205,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         // loads of out-of-row lanes are redirected to the last column of the row (always readable)
         const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
         const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;          // hop-rows that feed a valid frame
-        stage_tile<W>(w, lane, sl, a.wave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
+        stage_tile<W>(w, lane, sl, wave_row, len, t0, n_rows, S, a.vec_ok != 0);
         if (!filled) {                              // once per CTA, while the staging copies are in flight
             window_fill(S, a.window, threadIdx.x, kTile * W);      // pad column of the scratch <- window table
             tables_fill(&sm, tab, threadIdx.x, kTile * W);         // both visible after the barrier below
@@ -220,21 +237,26 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
             __syncthreads();
             fft_pass1_adj<W>(w, col, S + kTile);
             __syncthreads();
-            unstage_tile<W>(w, lane, sl, a.gwave + (long long)n * a.wave_stride, len, t0, n_rows, S, a.vec_ok != 0);
+            unstage_tile<W>(w, lane, sl, a.gwave + (wave_row - a.wave), len, t0, n_rows, S, a.vec_ok != 0);
         }
         LMFB_TICK(5);
         if constexpr (!BWD) {
             __syncthreads();
             LMFB_TICK(6);
-            phase3_walk<W>(w, pl, sm, tab);
-            __syncthreads();
-            LMFB_TICK(5);                       // (overwrites the pass-2 end stamp: phase 3 split A | B)
-            phase3_finish<W>(w, pl, tab, po, som_bytes, inrow, valid);
+            if (tab.walkable) {
+                phase3_walk<W>(w, pl, sm, tab);
+                __syncthreads();
+                LMFB_TICK(5);                   // (overwrites the pass-2 end stamp: phase 3 split A | B)
+                phase3_finish<W>(w, pl, tab, po, som_bytes, inrow, valid, ch == ch0, ch + 1 == ch0 + nch);
+            } else {
+                phase3_gather<W>(w, pl, sm, n_mels, a.mel, po, som_bytes, inrow, valid, ch == ch0, ch + 1 == ch0 + nch);
+            }
         }
 #ifdef LMFB_TIMELINE
         else tl[6] = tl[5];
 #endif
         LMFB_TICK(7);
+      }   // channels
 #ifdef LMFB_TIMELINE
         if (a.timeline && lane == 0 && blockIdx.x < 64 && n_done < 8) {
             long long* dst = a.timeline + ((long long)n_done * 64 + blockIdx.x) * (W * 8) + w * 8;
@@ -285,8 +307,9 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
-__device__ __forceinline__ int frames_of(const int32_t* lengths, int n, int tmax) {
-    const int len = lengths[n];
+__device__ __forceinline__ int frames_of(const int32_t* lengths, int n, int tmax, long long wave_len) {
+    int len = lengths[n];
+    if (wave_len > 0 && (long long)len > wave_len) len = (int)wave_len;
     int T = len >= 1 ? 1 + len / kHop : 0;
     return T < tmax ? T : tmax;
 }
@@ -294,10 +317,10 @@ __device__ __forceinline__ int frames_of(const int32_t* lengths, int n, int tmax
 // mode: 1 = per mel bin (grid.x = M rows), 2 = global (grid.x = 1, block walks all M rows)
 __global__ void __launch_bounds__(kRowThreads)
 cmvn_fwd(float* __restrict__ out, float* __restrict__ stats, const int32_t* __restrict__ lengths,
-         int n_mels, int tmax, float eps, int mode) {
+         int n_mels, int tmax, float eps, int mode, long long wave_len) {
     __shared__ double red[kRowThreads / 32];
     const int n = blockIdx.y;
-    const int T = frames_of(lengths, n, tmax);
+    const int T = frames_of(lengths, n, tmax, wave_len);
     const int m0 = mode == 1 ? blockIdx.x : 0;
     const int m1 = mode == 1 ? m0 + 1 : n_mels;
     float* base = out + (long long)n * n_mels * tmax;
@@ -338,10 +361,10 @@ cmvn_fwd(float* __restrict__ out, float* __restrict__ stats, const int32_t* __re
 __global__ void __launch_bounds__(kRowThreads)
 cmvn_bwd(const float* __restrict__ z, const float* __restrict__ stats,
          const float* __restrict__ grad_out, float* __restrict__ dE,
-         const int32_t* __restrict__ lengths, int n_mels, int tmax, float eps, int mode) {
+         const int32_t* __restrict__ lengths, int n_mels, int tmax, float eps, int mode, long long wave_len) {
     __shared__ double red[kRowThreads / 32];
     const int n = blockIdx.y;
-    const int T = frames_of(lengths, n, tmax);
+    const int T = frames_of(lengths, n, tmax, wave_len);
     const int m0 = mode == 2 ? 0 : blockIdx.x;
     const int m1 = mode == 2 ? n_mels : m0 + 1;
     const long long nb = (long long)n * n_mels * tmax;
@@ -399,12 +422,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <int KMAX>
 __global__ void __launch_bounds__(32 * kRowWarps)
 cmvn_fwd_rows(float* __restrict__ out, float* __restrict__ stats, const int32_t* __restrict__ lengths,
-              int n_mels, int rows, int tmax, float eps) {
+              int n_mels, int rows, int tmax, float eps, long long wave_len) {
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const int n = row / n_mels;
-    const int T = frames_of(lengths, n, tmax);
+    const int T = frames_of(lengths, n, tmax, wave_len);
     float* base = out + (long long)row * tmax;
     if (T == 0) {
         if (lane == 0) { stats[2 * (long long)row] = 0.0f; stats[2 * (long long)row + 1] = 1.0f; }
@@ -439,12 +462,12 @@ template <int KMAX>
 __global__ void __launch_bounds__(32 * kRowWarps)
 cmvn_bwd_rows(const float* __restrict__ z, const float* __restrict__ stats,
               const float* __restrict__ grad_out, float* __restrict__ dE,
-              const int32_t* __restrict__ lengths, int n_mels, int rows, int tmax, float eps, int mode) {
+              const int32_t* __restrict__ lengths, int n_mels, int rows, int tmax, float eps, int mode, long long wave_len) {
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const int n = row / n_mels;
-    const int T = frames_of(lengths, n, tmax);
+    const int T = frames_of(lengths, n, tmax, wave_len);
     const float* zb = z + (long long)row * tmax;
     const float* gb = grad_out + (long long)row * tmax;
     float* eb = dE + (long long)row * tmax;
@@ -493,11 +516,11 @@ template <int K>
 __global__ void __launch_bounds__(kRowThreads)
 cmvn_bwd_block(const float* __restrict__ z, const float* __restrict__ stats,
                const float* __restrict__ grad_out, float* __restrict__ dE,
-               const int32_t* __restrict__ lengths, int n_mels, int tmax, float eps, int mode) {
+               const int32_t* __restrict__ lengths, int n_mels, int tmax, float eps, int mode, long long wave_len) {
     __shared__ double red[kRowThreads / 32];
     const int row = blockIdx.x;
     const int n = row / n_mels;
-    const int T = frames_of(lengths, n, tmax);
+    const int T = frames_of(lengths, n, tmax, wave_len);
     const float* zb = z + (long long)row * tmax;
     const float* gb = grad_out + (long long)row * tmax;
     float* eb = dE + (long long)row * tmax;
@@ -550,6 +573,25 @@ cmvn_bwd_block(const float* __restrict__ z, const float* __restrict__ stats,
 // ======================================================================================
 using namespace aas_lmfb;
 
+namespace aas_lmfb {
+// generic bases, backward: dP = 1/4 B^T dE as a tensor of kDpRows rows (row f = dP[f]; row 161 = 0),
+// which K1 then reads through the identity table.  One thread per (f, t); the basis column is a
+// broadcast load, the dE rows are coalesced.  A slow path by design (dense bases are not what the
+// trainers use); the banded path never comes here.
+__global__ void __launch_bounds__(128)
+dp_generic(const float* __restrict__ mel, const float* __restrict__ dE, float* __restrict__ dP, int n_mels, int tmax) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    const int f = blockIdx.y, n = blockIdx.z;
+    if (t >= tmax) return;
+    float acc = 0.0f;
+    if (f < kBins) {
+        const float* de = dE + (long long)n * n_mels * tmax + t;
+        for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(mel + m * kBins + f), de[(long long)m * tmax], acc);
+    }
+    dP[((long long)n * kDpRows + f) * tmax + t] = 0.25f * acc;
+}
+}  // namespace aas_lmfb
+
 typedef void (*k1_fwd_fn)(const K1Args, const FwdTab);
 typedef void (*k1_bwd_fn)(const K1Args, const BwdTab);
 
@@ -582,22 +624,20 @@ constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 0, kBwdVariantBig = 0, kBwd
 constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 2, kBwdVariantBig = 2, kBwdVariantSmall = 2;   // small: one wave of 4-warp CTAs
 #endif
 
-static int pick_variant(const char* env, int dflt) {
-    const char* v = getenv(env);            // tuning knob: warps per tile
-    if (v) {
-        const int wanted = atoi(v);
-        for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
-            if (kVariants[i].warps == wanted) return (int)i;
-    }
-    return dflt;
+static int variant_of_warps(int warps) {
+    for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
+        if (kVariants[i].warps == warps) return (int)i;
+    return -1;
 }
 
 struct aas_lmfb_plan {
     FwdTab  fwd;
-    BwdTab  bwd;
-    int     ml[kBins];
+    BwdTab  bwd;            // banded table, or the identity table over dP when !banded
+    int     ml[kBins];      // lower filter of every bin (walkable bases)
     int     n_mels;
-    int     vfwd, vbwd;
+    int     banded;         // backward fast path
+    int     vfwd, vbwd;     // forced kernel variants (-1: choose by problem size at launch)
+    int     static_sched;   // deal tiles round-robin instead of cluster launch control
 };
 
 extern "C" int aas_lmfb_abi_version(void) { return AAS_LMFB_ABI_VERSION; }
@@ -607,9 +647,9 @@ extern "C" const char* aas_lmfb_strerror(int code) {
         case AAS_LMFB_OK:      return "ok";
         case AAS_LMFB_E_NULL:  return "aas_lmfb: required pointer is NULL";
         case AAS_LMFB_E_ALIGN: return "aas_lmfb: buffer is not sufficiently aligned";
-        case AAS_LMFB_E_SHAPE: return "aas_lmfb: unsupported shape (n_bins must be 161, 2 <= n_mels <= 128, n >= 0, 1 <= tmax and mask row stride <= 2^22)";
+        case AAS_LMFB_E_SHAPE: return "aas_lmfb: unsupported shape (n_bins must be 161, 2 <= n_mels <= 128, n >= 0, n_ch >= 1, 1 <= tmax and mask row stride <= 2^22)";
         case AAS_LMFB_E_FLAGS: return "aas_lmfb: invalid mask/cmvn flags";
-        case AAS_LMFB_E_MEL:   return "aas_lmfb: mel basis is not banded (each bin may feed at most two adjacent, frequency-ordered filters)";
+        case AAS_LMFB_E_MEL:   return "aas_lmfb: this mel basis runs on the generic path, which needs the device copy of the matrix (aas_lmfb_io.mel_dev; use the _ex entry points)";
         case AAS_LMFB_E_NOMEM: return "aas_lmfb: host allocation failed";
         default: break;
     }
@@ -627,21 +667,40 @@ extern "C" aas_lmfb_plan* aas_lmfb_plan_create(const float* mel, int n_mels, int
         if (!p) { st = AAS_LMFB_E_NOMEM; break; }
         memset(p, 0, sizeof(*p));
         p->n_mels = n_mels;
-        p->vfwd = pick_variant("AAS_LMFB_WARPS_FWD", -1);       // -1: choose by problem size at launch
-        p->vbwd = pick_variant("AAS_LMFB_WARPS_BWD", -1);
-        if (build_fwd_tab(mel, n_mels, &p->fwd, p->ml) != 0) { st = AAS_LMFB_E_MEL; break; }
-        build_bwd_tab(p->fwd, p->ml, &p->bwd);
+        p->vfwd = p->vbwd = -1;
+        build_fwd_tab(mel, n_mels, &p->fwd, p->ml);
+        p->banded = build_bwd_tab(mel, n_mels, &p->bwd) == 0 ? 1 : 0;
+        if (!p->banded) build_bwd_tab_identity(&p->bwd);
     } while (0);
-    if (st != AAS_LMFB_OK && p) { delete p; p = nullptr; }
     if (status) *status = st;
     return p;
 }
 
 extern "C" void aas_lmfb_plan_destroy(aas_lmfb_plan* plan) { delete plan; }
 
-extern "C" size_t aas_lmfb_workspace_bytes(int n, int n_mels, int tmax, uint32_t /*flags*/) {
-    if (n <= 0 || n_mels <= 0 || tmax <= 0) return 0;
-    return (size_t)n * (size_t)n_mels * (size_t)tmax * sizeof(float);
+extern "C" int aas_lmfb_plan_info(const aas_lmfb_plan* plan, int* n_mels, int* fwd_compact, int* bwd_banded) {
+    if (!plan) return AAS_LMFB_E_NULL;
+    if (n_mels) *n_mels = plan->n_mels;
+    if (fwd_compact) *fwd_compact = plan->fwd.walkable;
+    if (bwd_banded) *bwd_banded = plan->banded;
+    return AAS_LMFB_OK;
+}
+
+extern "C" int aas_lmfb_plan_set_tuning(aas_lmfb_plan* plan, int warps_fwd, int warps_bwd, int static_schedule) {
+    if (!plan) return AAS_LMFB_E_NULL;
+    const int vf = warps_fwd ? variant_of_warps(warps_fwd) : -1, vb = warps_bwd ? variant_of_warps(warps_bwd) : -1;
+    if ((warps_fwd && vf < 0) || (warps_bwd && vb < 0)) return AAS_LMFB_E_FLAGS;
+    plan->vfwd = vf; plan->vbwd = vb; plan->static_sched = static_schedule ? 1 : 0;
+    return AAS_LMFB_OK;
+}
+
+static size_t round16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+extern "C" size_t aas_lmfb_workspace_bytes(const aas_lmfb_plan* plan, int n, int tmax, uint32_t /*flags*/) {
+    if (!plan || n <= 0 || tmax <= 0) return 0;
+    size_t b = round16((size_t)n * (size_t)plan->n_mels * (size_t)tmax * sizeof(float));       // dE
+    if (!plan->banded) b += round16((size_t)n * (size_t)kDpRows * (size_t)tmax * sizeof(float));   // dP
+    return b;
 }
 
 namespace {
@@ -665,13 +724,29 @@ int ensure_attrs(const void* fn, int smem) {
     return 0;
 }
 
+// the calling thread's device for the duration of a call (autograd runs backward on another host
+// thread than forward: nothing here may depend on thread-local state set elsewhere)
+struct DeviceScope {
+    int prev = -1, rc = 0;
+    explicit DeviceScope(int want) {
+        if (want < 0) return;
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) { rc = (int)e; prev = -1; return; }
+        if (prev == want) { prev = -1; return; }
+        e = cudaSetDevice(want);
+        if (e != cudaSuccess) { rc = (int)e; prev = -1; }
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 template <class Fn, class Tab>
-int launch_k1(const K1Variant& v, Fn fn, K1Args& a, const Tab& tab, bool bwd, int n, cudaStream_t stream) {
+int launch_k1(const aas_lmfb_plan* plan, const K1Variant& v, Fn fn, K1Args& a, const Tab& tab, bool bwd,
+              long long units, cudaStream_t stream) {
     if (!fn) return AAS_LMFB_E_FLAGS;
     const int smem = smem_bytes(bwd) + 32;                         // + the scheduler's answer and barrier
     const int rc = ensure_attrs((const void*)fn, smem);
     if (rc) return rc;
-    const long long total = (long long)n * a.tiles_per_utt;
+    const long long total = units * a.tiles_per_utt;               // units: utterances (forward) or utterance-channels
     if (total <= 0) return AAS_LMFB_OK;
     if (total > 0x7fffffffLL) return AAS_LMFB_E_SHAPE;
     a.total_tiles = (int)total;
@@ -684,25 +759,37 @@ int launch_k1(const K1Variant& v, Fn fn, K1Args& a, const Tab& tab, bool bwd, in
     if (per_sm < 1) per_sm = 1;
     const long long resident = (long long)sms * per_sm;           // one persistent CTA per scratch slot
     // more tiles than resident CTAs: one CTA per tile, the resident ones take over the pending ones
-    static const bool use_clc = []{ const char* e = getenv("AAS_LMFB_SCHED"); return !(e && strcmp(e, "static") == 0); }();
-    a.dynamic = (use_clc && total > resident) ? 1 : 0;
+    a.dynamic = (!plan->static_sched && total > resident) ? 1 : 0;
     const unsigned blocks = (unsigned)(a.dynamic || total < resident ? total : resident);
     fn<<<blocks, kTile * v.warps, smem, stream>>>(a, tab);
     return (int)cudaPeekAtLastError();
 }
 
-int check_common(const aas_lmfb_plan* plan, const float* wave, const int32_t* lengths, int n,
-                 const float* mask_r, const float* mask_i, const float* window, int tmax,
-                 uint32_t flags) {
-    if (!plan || !window || (n > 0 && (!wave || !lengths))) return AAS_LMFB_E_NULL;
-    if (n < 0 || tmax < 1 || tmax > (1 << 22)) return AAS_LMFB_E_SHAPE;
-    const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
-    if (mask > 2u || cm > 2u || (flags >> 4)) return AAS_LMFB_E_FLAGS;
-    if (mask != AAS_LMFB_MASK_NONE && !mask_r) return AAS_LMFB_E_NULL;
-    if (mask == AAS_LMFB_MASK_REIM && !mask_i) return AAS_LMFB_E_NULL;
-    const uintptr_t al = (uintptr_t)wave | (uintptr_t)mask_r | (uintptr_t)mask_i | (uintptr_t)window;
+int check_common(const aas_lmfb_plan* plan, const aas_lmfb_io* io) {
+    if (!plan || !io) return AAS_LMFB_E_NULL;
+    if (io->struct_size < sizeof(aas_lmfb_io)) return AAS_LMFB_E_SHAPE;
+    if (!io->window || (io->n > 0 && (!io->wave || !io->lengths))) return AAS_LMFB_E_NULL;
+    if (io->n < 0 || io->n_ch < 1 || io->tmax < 1 || io->tmax > (1 << 22)) return AAS_LMFB_E_SHAPE;
+    const unsigned mask = io->flags & 3u, cm = (io->flags >> 2) & 3u;
+    if (mask > 2u || cm > 2u || (io->flags >> 4)) return AAS_LMFB_E_FLAGS;
+    if (mask != AAS_LMFB_MASK_NONE && !io->mask_r) return AAS_LMFB_E_NULL;
+    if (mask == AAS_LMFB_MASK_REIM && !io->mask_i) return AAS_LMFB_E_NULL;
+    if (mask != AAS_LMFB_MASK_NONE && (io->mask_stride_f < io->tmax || io->mask_stride_f > (1 << 22))) return AAS_LMFB_E_SHAPE;
+    const uintptr_t al = (uintptr_t)io->wave | (uintptr_t)io->mask_r | (uintptr_t)io->mask_i | (uintptr_t)io->window |
+                         (uintptr_t)io->mel_dev;
     if (al & 3u) return AAS_LMFB_E_ALIGN;
     return AAS_LMFB_OK;
+}
+
+void fill_args(K1Args& a, const aas_lmfb_io* io) {
+    memset(&a, 0, sizeof(a));
+    a.wave = io->wave; a.lengths = io->lengths; a.wave_stride = io->wave_stride;
+    a.wave_stride_ch = io->wave_stride_ch; a.wave_len = io->wave_len; a.n_ch = io->n_ch;
+    a.mask_r = io->mask_r; a.mask_i = io->mask_i; a.msn = io->mask_stride_n; a.msf = (unsigned)io->mask_stride_f;
+    a.window = io->window; a.tmax = io->tmax; a.mel = io->mel_dev;
+    a.tiles_per_utt = (io->tmax + kTile - 1) / kTile;
+    // 8-byte asynchronous copies need every row start 8-byte aligned
+    a.vec_ok = (((uintptr_t)io->wave & 7u) == 0 && (io->wave_stride & 1) == 0 && (io->wave_stride_ch & 1) == 0) ? 1 : 0;
 }
 
 void rec(void* const* prof, int i, cudaStream_t s) {
@@ -711,6 +798,154 @@ void rec(void* const* prof, int i, cudaStream_t s) {
 
 }  // namespace
 
+extern "C" int aas_lmfb_forward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io* io) {
+    int rc = check_common(plan, io);
+    if (rc) return rc;
+    const int n = io->n, tmax = io->tmax;
+    if (n == 0) return AAS_LMFB_OK;
+    const unsigned mask = io->flags & 3u, cm = (io->flags >> 2) & 3u;
+    float* out = io->out; float* stats = io->stats;
+    if (!out || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
+    if (((uintptr_t)out | (uintptr_t)stats) & 3u) return AAS_LMFB_E_ALIGN;
+    if (!plan->fwd.walkable && !io->mel_dev) return AAS_LMFB_E_MEL;
+    DeviceScope scope(io->device);
+    if (scope.rc) return scope.rc;
+    cudaStream_t stream = (cudaStream_t)io->cuda_stream;
+    void* const* prof = io->prof;
+
+    K1Args a;
+    fill_args(a, io);
+    a.out = out;
+#ifdef LMFB_TIMELINE
+    { const char* e = getenv("AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+#endif
+    const bool small = (long long)n * a.tiles_per_utt <= 148LL * 4;      // fits one wave at 4 CTAs per SM
+    const K1Variant& v = kVariants[plan->vfwd >= 0 ? plan->vfwd : (small ? kFwdVariantSmall : kFwdVariantBig)];
+    FwdTab band = plan->fwd;
+    set_warp_ranges(&band, plan->ml, v.warps);
+    rec(prof, 0, stream);
+    rc = launch_k1(plan, v, v.fwd[mask], a, band, false, n, stream);
+    rec(prof, 1, stream);
+    if (rc) return rc;
+    rec(prof, 2, stream);
+    if (cm != 0) {
+        const int rows = n * plan->n_mels;
+        const float eps = io->eps;
+        const int32_t* lengths = io->lengths;
+        const unsigned blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
+        if (cm == 1 && tmax <= 32 * 8) {
+            cmvn_fwd_rows<8><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len);
+        } else if (cm == 1 && tmax <= 32 * 24) {
+            cmvn_fwd_rows<24><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len);
+        } else if (cm == 1 && tmax <= 32 * 48) {
+            cmvn_fwd_rows<48><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len);
+        } else {
+            dim3 grid(cm == 1 ? plan->n_mels : 1, n);
+            cmvn_fwd<<<grid, kRowThreads, 0, stream>>>(out, stats, lengths, plan->n_mels, tmax, eps, (int)cm, io->wave_len);
+        }
+        rc = (int)cudaPeekAtLastError();
+    }
+    rec(prof, 3, stream);
+    return rc;
+}
+
+extern "C" int aas_lmfb_backward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io* io) {
+    int rc = check_common(plan, io);
+    if (rc) return rc;
+    const int n = io->n, tmax = io->tmax;
+    if (n == 0) return AAS_LMFB_OK;
+    const unsigned mask = io->flags & 3u, cm = (io->flags >> 2) & 3u;
+    float* grad_wave = io->grad_wave;
+    if (mask == AAS_LMFB_MASK_NONE && !grad_wave) return AAS_LMFB_E_FLAGS;        // nothing to differentiate into
+    if (!io->out || !io->grad_out || !io->workspace || (mask != AAS_LMFB_MASK_NONE && !io->grad_mask_r) || (cm != 0 && !io->stats)) return AAS_LMFB_E_NULL;
+    if ((uintptr_t)grad_wave & 7u) return AAS_LMFB_E_ALIGN;
+    if (mask == AAS_LMFB_MASK_REIM && !io->grad_mask_i) return AAS_LMFB_E_NULL;
+    if (((uintptr_t)io->out | (uintptr_t)io->grad_out | (uintptr_t)io->workspace | (uintptr_t)io->grad_mask_r |
+         (uintptr_t)io->grad_mask_i | (uintptr_t)io->stats) & 3u) return AAS_LMFB_E_ALIGN;
+    if (!plan->banded && !io->mel_dev) return AAS_LMFB_E_MEL;
+    // gradient rows of different utterances / channels must not overlap (they are written independently)
+    if (mask != AAS_LMFB_MASK_NONE && n > 1 && io->mask_stride_n < (int64_t)io->n_ch * kBins * io->mask_stride_f) return AAS_LMFB_E_SHAPE;
+    DeviceScope scope(io->device);
+    if (scope.rc) return scope.rc;
+    cudaStream_t stream = (cudaStream_t)io->cuda_stream;
+    void* const* prof = io->prof;
+    float* dE = (float*)io->workspace;
+    const float eps = io->eps;
+    const int32_t* lengths = io->lengths;
+    const float* out = io->out; const float* stats = io->stats; const float* grad_out = io->grad_out;
+
+    rec(prof, 2, stream);
+    {
+        const int rows = n * plan->n_mels;
+        const unsigned blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
+        if (cm != 2 && tmax <= 32 * 8) {
+            cmvn_bwd_rows<8><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, rows, tmax, eps, (int)cm, io->wave_len);
+        } else if (cm != 2 && tmax <= 32 * 24) {
+            cmvn_bwd_rows<24><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, rows, tmax, eps, (int)cm, io->wave_len);
+        } else if (cm != 2 && tmax <= kRowThreads * 8) {
+            cmvn_bwd_block<8><<<(unsigned)rows, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm, io->wave_len);
+        } else if (cm != 2 && tmax <= kRowThreads * 24) {
+            cmvn_bwd_block<24><<<(unsigned)rows, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm, io->wave_len);
+        } else {
+            dim3 grid(cm == 2 ? 1 : plan->n_mels, n);
+            cmvn_bwd<<<grid, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm, io->wave_len);
+        }
+        rc = (int)cudaPeekAtLastError();
+        if (rc == 0 && !plan->banded) {                          // generic basis: dP = 1/4 B^T dE, read through the identity table
+            float* dP = (float*)((char*)io->workspace + round16((size_t)n * plan->n_mels * tmax * sizeof(float)));
+            dim3 grid((unsigned)((tmax + 127) / 128), kDpRows, n);
+            dp_generic<<<grid, 128, 0, stream>>>(io->mel_dev, dE, dP, plan->n_mels, tmax);
+            rc = (int)cudaPeekAtLastError();
+            dE = dP;
+        }
+    }
+    rec(prof, 3, stream);
+    if (rc) return rc;
+
+    K1Args a;
+    fill_args(a, io);
+    a.dE = dE; a.gr = io->grad_mask_r; a.gi = io->grad_mask_i;
+#ifdef LMFB_TIMELINE
+    { const char* e = getenv("AAS_LMFB_TIMELINE_BWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+#endif
+    const long long units = (long long)n * io->n_ch;
+    const bool small = units * a.tiles_per_utt <= 148LL * 4;      // fits one wave at 4 CTAs per SM
+    const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
+    if (mask == AAS_LMFB_MASK_NONE) { a.mask_r = a.mask_i = io->wave; a.gr = a.gi = nullptr; a.msf = (unsigned)tmax; a.msn = 0; }   // never dereferenced
+    a.gwave = grad_wave;
+    if (grad_wave) {                                             // the kernel ADDS (overlapping frames, reflect padding)
+        const int64_t row = io->n_ch > 1 ? io->wave_stride_ch : io->wave_stride;       // rows are (n, ch) pairs
+        int64_t w64 = row < (int64_t)tmax * kHop ? row : (int64_t)tmax * kHop;
+        if (io->wave_len > 0 && io->wave_len < w64) w64 = io->wave_len;            // never past the end of a row
+        const size_t width = (size_t)w64;
+        cudaError_t e = cudaSuccess;
+        if (io->n_ch == 1 || io->wave_stride == io->wave_stride_ch * io->n_ch) {
+            e = cudaMemset2DAsync(grad_wave, (size_t)row * sizeof(float), 0, width * sizeof(float), (size_t)units, stream);
+        } else {
+            for (int i = 0; i < n && e == cudaSuccess; ++i)
+                e = cudaMemset2DAsync(grad_wave + (size_t)i * io->wave_stride, (size_t)row * sizeof(float), 0,
+                                      width * sizeof(float), (size_t)io->n_ch, stream);
+        }
+        if (e != cudaSuccess) return (int)e;
+    }
+    rec(prof, 0, stream);
+    rc = grad_wave ? launch_k1(plan, v, v.bwd_gw[mask], a, plan->bwd, true, units, stream)
+                   : launch_k1(plan, v, v.bwd[mask], a, plan->bwd, true, units, stream);
+    rec(prof, 1, stream);
+    return rc;
+}
+
+// ---- classic entry points: one channel, the calling thread's device -------------------------------
+static void classic_io(aas_lmfb_io& io, const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
+                       const float* mask_r, const float* mask_i, int64_t msn, int64_t msf, const float* window,
+                       int tmax, uint32_t flags, float eps, void* stream, void* const* prof) {
+    memset(&io, 0, sizeof(io));
+    io.struct_size = (uint32_t)sizeof(io); io.flags = flags; io.device = -1; io.n = n; io.n_ch = 1; io.tmax = tmax;
+    io.eps = eps; io.wave = wave; io.wave_stride = wave_stride; io.wave_stride_ch = 0; io.wave_len = 0;
+    io.lengths = lengths; io.mask_r = mask_r; io.mask_i = mask_i; io.mask_stride_n = msn; io.mask_stride_f = msf;
+    io.window = window; io.cuda_stream = stream; io.prof = prof;
+}
+
 extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
                                 const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
                                 const float* mask_r, const float* mask_i,
@@ -718,126 +953,11 @@ extern "C" int aas_lmfb_forward(const aas_lmfb_plan* plan,
                                 const float* window,
                                 float* out, float* stats, int tmax,
                                 uint32_t flags, float eps, void* cuda_stream, void* const* prof) {
-    int rc = check_common(plan, wave, lengths, n, mask_r, mask_i, window, tmax, flags);
-    if (rc) return rc;
-    if (n == 0) return AAS_LMFB_OK;
-    const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
-    if (mask != AAS_LMFB_MASK_NONE && (mask_stride_f < tmax || mask_stride_f > (1 << 22))) return AAS_LMFB_E_SHAPE;
-    if (!out || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
-    if (((uintptr_t)out | (uintptr_t)stats) & 3u) return AAS_LMFB_E_ALIGN;
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
-
-    K1Args a;
-    memset(&a, 0, sizeof(a));
-    a.wave = wave; a.lengths = lengths; a.wave_stride = wave_stride;
-    a.mask_r = mask_r; a.mask_i = mask_i; a.msn = mask_stride_n; a.msf = (unsigned)mask_stride_f;
-    a.window = window; a.out = out; a.tmax = tmax;
-    a.tiles_per_utt = (tmax + kTile - 1) / kTile;
-    a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
-#ifdef LMFB_TIMELINE
-    { const char* e = getenv(false ? "AAS_LMFB_TIMELINE_BWD" : "AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
-#endif
-
-    const bool small = (long long)n * a.tiles_per_utt <= 148LL * 4;      // fits one wave at 4 CTAs per SM
-    const K1Variant& v = kVariants[plan->vfwd >= 0 ? plan->vfwd : (small ? kFwdVariantSmall : kFwdVariantBig)];
-    FwdTab band = plan->fwd;
-    set_warp_ranges(&band, plan->ml, v.warps);
-    rec(prof, 0, stream);
-    rc = launch_k1(v, v.fwd[mask], a, band, false, n, stream);
-    rec(prof, 1, stream);
-    if (rc) return rc;
-    rec(prof, 2, stream);
-    if (cm != 0) {
-        const int rows = n * plan->n_mels;
-        const unsigned blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
-        if (cm == 1 && tmax <= 32 * 8) {
-            cmvn_fwd_rows<8><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps);
-        } else if (cm == 1 && tmax <= 32 * 24) {
-            cmvn_fwd_rows<24><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps);
-        } else if (cm == 1 && tmax <= 32 * 48) {
-            cmvn_fwd_rows<48><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps);
-        } else {
-            dim3 grid(cm == 1 ? plan->n_mels : 1, n);
-            cmvn_fwd<<<grid, kRowThreads, 0, stream>>>(out, stats, lengths, plan->n_mels, tmax, eps, (int)cm);
-        }
-        rc = (int)cudaPeekAtLastError();
-    }
-    rec(prof, 3, stream);
-    return rc;
+    aas_lmfb_io io;
+    classic_io(io, wave, lengths, n, wave_stride, mask_r, mask_i, mask_stride_n, mask_stride_f, window, tmax, flags, eps, cuda_stream, prof);
+    io.out = out; io.stats = stats;
+    return aas_lmfb_forward_ex(plan, &io);
 }
-
-static int backward_impl(const aas_lmfb_plan* plan,
-                                 const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
-                                 const float* mask_r, const float* mask_i,
-                                 int64_t mask_stride_n, int64_t mask_stride_f,
-                                 const float* window,
-                                 const float* out, const float* stats, const float* grad_out,
-                                 float* grad_mask_r, float* grad_mask_i, float* grad_wave,
-                                 void* workspace, int tmax,
-                                 uint32_t flags, float eps, void* cuda_stream, void* const* prof) {
-    int rc = check_common(plan, wave, lengths, n, mask_r, mask_i, window, tmax, flags);
-    if (rc) return rc;
-    if (n == 0) return AAS_LMFB_OK;
-    const unsigned mask = flags & 3u, cm = (flags >> 2) & 3u;
-    if (mask == AAS_LMFB_MASK_NONE && !grad_wave) return AAS_LMFB_E_FLAGS;        // nothing to differentiate into
-    if (mask != AAS_LMFB_MASK_NONE && (mask_stride_f < tmax || mask_stride_f > (1 << 22))) return AAS_LMFB_E_SHAPE;
-    if (!out || !grad_out || !workspace || (mask != AAS_LMFB_MASK_NONE && !grad_mask_r) || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
-    if ((uintptr_t)grad_wave & 7u) return AAS_LMFB_E_ALIGN;
-    if (mask == AAS_LMFB_MASK_REIM && !grad_mask_i) return AAS_LMFB_E_NULL;
-    if (((uintptr_t)out | (uintptr_t)grad_out | (uintptr_t)workspace | (uintptr_t)grad_mask_r |
-         (uintptr_t)grad_mask_i | (uintptr_t)stats) & 3u) return AAS_LMFB_E_ALIGN;
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
-    float* dE = (float*)workspace;
-
-    rec(prof, 2, stream);
-    {
-        const int rows = n * plan->n_mels;
-        const unsigned blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
-        if (cm != 2 && tmax <= 32 * 8) {
-            cmvn_bwd_rows<8><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, rows, tmax, eps, (int)cm);
-        } else if (cm != 2 && tmax <= 32 * 24) {
-            cmvn_bwd_rows<24><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, rows, tmax, eps, (int)cm);
-        } else if (cm != 2 && tmax <= kRowThreads * 8) {
-            cmvn_bwd_block<8><<<(unsigned)rows, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm);
-        } else if (cm != 2 && tmax <= kRowThreads * 24) {
-            cmvn_bwd_block<24><<<(unsigned)rows, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm);
-        } else {
-            dim3 grid(cm == 2 ? 1 : plan->n_mels, n);
-            cmvn_bwd<<<grid, kRowThreads, 0, stream>>>(out, stats, grad_out, dE, lengths, plan->n_mels, tmax, eps, (int)cm);
-        }
-        rc = (int)cudaPeekAtLastError();
-    }
-    rec(prof, 3, stream);
-    if (rc) return rc;
-
-    K1Args a;
-    memset(&a, 0, sizeof(a));
-    a.wave = wave; a.lengths = lengths; a.wave_stride = wave_stride;
-    a.mask_r = mask_r; a.mask_i = mask_i; a.msn = mask_stride_n; a.msf = (unsigned)mask_stride_f;
-    a.window = window; a.dE = dE; a.gr = grad_mask_r; a.gi = grad_mask_i; a.tmax = tmax;
-    a.tiles_per_utt = (tmax + kTile - 1) / kTile;
-    a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
-#ifdef LMFB_TIMELINE
-    { const char* e = getenv(true ? "AAS_LMFB_TIMELINE_BWD" : "AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
-#endif
-
-    const bool small = (long long)n * a.tiles_per_utt <= 148LL * 4;      // fits one wave at 4 CTAs per SM
-    const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
-    if (mask == AAS_LMFB_MASK_NONE) { a.mask_r = a.mask_i = wave; a.gr = a.gi = nullptr; a.msf = (unsigned)tmax; a.msn = 0; }   // never dereferenced
-    a.gwave = grad_wave;
-    if (grad_wave) {                                             // the kernel ADDS (overlapping frames, reflect padding)
-        const cudaError_t e = cudaMemset2DAsync(grad_wave, (size_t)wave_stride * sizeof(float), 0,
-                                                (size_t)(wave_stride < (int64_t)tmax * kHop ? wave_stride : (int64_t)tmax * kHop) * sizeof(float),
-                                                (size_t)n, stream);
-        if (e != cudaSuccess) return (int)e;
-    }
-    rec(prof, 0, stream);
-    rc = grad_wave ? launch_k1(v, v.bwd_gw[mask], a, plan->bwd, true, n, stream)
-                   : launch_k1(v, v.bwd[mask], a, plan->bwd, true, n, stream);
-    rec(prof, 1, stream);
-    return rc;
-}
-
 
 extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
                                  const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
@@ -848,9 +968,11 @@ extern "C" int aas_lmfb_backward(const aas_lmfb_plan* plan,
                                  float* grad_mask_r, float* grad_mask_i,
                                  void* workspace, int tmax,
                                  uint32_t flags, float eps, void* cuda_stream, void* const* prof) {
-    return backward_impl(plan, wave, lengths, n, wave_stride, mask_r, mask_i, mask_stride_n, mask_stride_f, window,
-                         out, stats, grad_out, grad_mask_r, grad_mask_i, nullptr, workspace, tmax, flags, eps,
-                         cuda_stream, prof);
+    aas_lmfb_io io;
+    classic_io(io, wave, lengths, n, wave_stride, mask_r, mask_i, mask_stride_n, mask_stride_f, window, tmax, flags, eps, cuda_stream, prof);
+    io.out = const_cast<float*>(out); io.stats = const_cast<float*>(stats); io.grad_out = grad_out;
+    io.grad_mask_r = grad_mask_r; io.grad_mask_i = grad_mask_i; io.workspace = workspace;
+    return aas_lmfb_backward_ex(plan, &io);
 }
 
 extern "C" int aas_lmfb_backward_wave(const aas_lmfb_plan* plan,
@@ -863,9 +985,11 @@ extern "C" int aas_lmfb_backward_wave(const aas_lmfb_plan* plan,
                                       void* workspace, int tmax,
                                       uint32_t flags, float eps, void* cuda_stream) {
     if (!grad_wave) return AAS_LMFB_E_NULL;
-    return backward_impl(plan, wave, lengths, n, wave_stride, mask_r, mask_i, mask_stride_n, mask_stride_f, window,
-                         out, stats, grad_out, grad_mask_r, grad_mask_i, grad_wave, workspace, tmax, flags, eps,
-                         cuda_stream, nullptr);
+    aas_lmfb_io io;
+    classic_io(io, wave, lengths, n, wave_stride, mask_r, mask_i, mask_stride_n, mask_stride_f, window, tmax, flags, eps, cuda_stream, nullptr);
+    io.out = const_cast<float*>(out); io.stats = const_cast<float*>(stats); io.grad_out = grad_out;
+    io.grad_mask_r = grad_mask_r; io.grad_mask_i = grad_mask_i; io.grad_wave = grad_wave; io.workspace = workspace;
+    return aas_lmfb_backward_ex(plan, &io);
 }
 
 // STFT as an output: what BRNNmultiCH.forward takes as its input, (N, 2*F, T) with the real rows first
@@ -875,23 +999,22 @@ extern "C" int aas_lmfb_stft(const aas_lmfb_plan* plan,
                              const float* wave, const int32_t* lengths, int n, int64_t wave_stride,
                              const float* window, float* out, int64_t out_stride_n, int tmax,
                              void* cuda_stream) {
-    int rc = check_common(plan, wave, lengths, n, nullptr, nullptr, window, tmax, AAS_LMFB_MASK_NONE);
+    aas_lmfb_io io;
+    classic_io(io, wave, lengths, n, wave_stride, nullptr, nullptr, 0, 0, window, tmax, AAS_LMFB_MASK_NONE, 0.0f, cuda_stream, nullptr);
+    int rc = check_common(plan, &io);
     if (rc) return rc;
     if (n == 0) return AAS_LMFB_OK;
     if (!out) return AAS_LMFB_E_NULL;
     if ((uintptr_t)out & 3u) return AAS_LMFB_E_ALIGN;
     if (out_stride_n < 2LL * kBins * tmax) return AAS_LMFB_E_SHAPE;
     K1Args a;
-    memset(&a, 0, sizeof(a));
-    a.wave = wave; a.lengths = lengths; a.wave_stride = wave_stride;
+    fill_args(a, &io);
     a.mask_r = a.mask_i = out;                                    // never read (clamped pointer arithmetic only)
     a.msn = out_stride_n; a.msf = (unsigned)tmax;
-    a.window = window; a.dE = out; a.gr = out; a.gi = out + (long long)kBins * tmax; a.tmax = tmax;
-    a.tiles_per_utt = (tmax + kTile - 1) / kTile;
-    a.vec_ok = (((uintptr_t)wave & 7u) == 0 && (wave_stride & 1) == 0) ? 1 : 0;
+    a.dE = out; a.gr = out; a.gi = out + (long long)kBins * tmax;
     const bool small = (long long)n * a.tiles_per_utt <= 148LL * 4;      // fits one wave at 4 CTAs per SM
     const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
-    return launch_k1(v, v.bwd[3], a, plan->bwd, true, n, (cudaStream_t)cuda_stream);
+    return launch_k1(plan, v, v.bwd[3], a, plan->bwd, true, n, (cudaStream_t)cuda_stream);
 }
 
 // ======================================================================================

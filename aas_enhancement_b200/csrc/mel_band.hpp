@@ -1,28 +1,39 @@
-// Host-side analysis of a mel basis into the banded-2 tables the kernels consume.
+// Host-side analysis of a mel basis into the tables the kernels consume.
 // Plain C++ (no CUDA) so that the CPU emulation harness can share it.
+//
+// The reference applies ANY (M, F) matrix with a k=1 conv1d (model.py:167, :196).  Here:
+//   forward  : "walkable" = banded-2 with a non-decreasing lower filter (every triangular filterbank):
+//              the bins are walked once with two running sums.  Otherwise every filter is gathered
+//              over its row [lo, hi] with the weights read from the caller's device copy of the matrix.
+//   backward : "banded" = every bin feeds at most two ADJACENT filters (again every triangular
+//              filterbank, in any frequency order of the bins): dP[f] = wl dE[d] + wh dE[d+1] straight
+//              from the table.  Otherwise the caller of the kernel first forms dP = 1/4 B^T dE
+//              (162 rows) and the kernel runs with the identity table below.
 #pragma once
 #include <string.h>
 #include "lmfb_core.cuh"
 
 namespace aas_lmfb {
 
-// mel: (n_mels, kBins) row-major.  Returns 0 on success, -1 if some bin feeds a filter outside the
-// two live ones (basis not banded / not frequency-ordered).  ml_out (kBins ints) receives the
-// lower filter of every bin (n_mels for bins above the last filter).
-inline int build_fwd_tab(const float* mel, int n_mels, FwdTab* out, int* ml_out) {
-    int hi[kMaxMels];                 // last bin with a non-zero weight, per filter (-1: empty)
+// mel: (n_mels, kBins) row-major.  Fills the forward table: the row descriptors always, and the
+// walk tables when the basis is banded-2 with a non-decreasing lower filter (out->walkable).
+inline void build_fwd_tab(const float* mel, int n_mels, FwdTab* out, int* ml_out) {
+    int hi[kMaxMels], lo[kMaxMels];   // last / first bin with a non-zero weight, per filter (hi = -1: empty)
     for (int m = 0; m < n_mels; ++m) {
-        hi[m] = -1;
-        for (int f = 0; f < kBins; ++f) if (mel[m * kBins + f] != 0.0f) hi[m] = f;
+        hi[m] = -1; lo[m] = kBins;
+        for (int f = 0; f < kBins; ++f) if (mel[m * kBins + f] != 0.0f) { if (f < lo[m]) lo[m] = f; hi[m] = f; }
     }
     memset(out, 0, sizeof(*out));
     out->n_mels = n_mels;
+    for (int m = 0; m < n_mels; ++m)
+        out->row[m] = hi[m] < 0 ? 0u : ((uint32_t)lo[m] | ((uint32_t)(hi[m] - lo[m] + 1) << 8));
+    out->walkable = 1;
     int ml = 0;
     for (int f = 0; f < kBins; ++f) {
         const int before = ml;
         while (ml < n_mels && hi[ml] < f) ++ml;              // lowest filter not yet finished
         for (int m = 0; m < n_mels; ++m)
-            if (mel[m * kBins + f] != 0.0f && (m < ml || m > ml + 1)) return -1;
+            if (mel[m * kBins + f] != 0.0f && (m < ml || m > ml + 1)) out->walkable = 0;
         ml_out[f] = ml;
         out->w[f].x = ml < n_mels ? 0.25f * mel[ml * kBins + f] : 0.0f;
         out->w[f].y = ml + 1 < n_mels ? 0.25f * mel[(ml + 1) * kBins + f] : 0.0f;
@@ -31,10 +42,9 @@ inline int build_fwd_tab(const float* mel, int n_mels, FwdTab* out, int* ml_out)
         if (adv != 0) out->hmask[f >> 3] |= (uint8_t)(1u << (f & 7));
         if (adv > 1) out->multi = 1;
     }
-    return 0;
 }
 
-// forward phase 3 with W warps: warp w walks the 8-bin groups [p3_g0(W, w), p3_g1(W, w)), the last
+// forward phase 3 (walk) with W warps: warp w walks the 8-bin groups [p3_g0(W, w), p3_g1(W, w)), the last
 // warp also bin 160, and produces partial sums for filters lo[w] .. hi[w] = ml(first bin) ..
 // ml(last bin) + 1
 inline void set_warp_ranges(FwdTab* tab, const int* ml, int warps) {
@@ -49,25 +59,52 @@ inline void set_warp_ranges(FwdTab* tab, const int* ml, int warps) {
     }
 }
 
-// Backward table from the forward one: per pass-2 step k2 and output k1, the weights of bins
-// f = (96 k1 + 65 k2) mod 160 and fp = 160 - f re-expressed on the always-valid row pair
-// (d, d + 1) of dE.  Needs n_mels >= 2.
-inline void build_bwd_tab(const FwdTab& fwd, const int* ml, BwdTab* bwd) {
+// Backward table (per pass-2 step k2 and output k1: bins f = (96 k1 + 65 k2) mod 160 and fp = 160 - f),
+// weights re-expressed on the always-valid row pair (d, d + 1) of dE and carrying the 1/4 that undoes
+// X' = 2X.  Returns 0, or -1 when some bin feeds filters that are not one or two adjacent rows
+// (then use build_bwd_tab_identity with a precomputed dP).  Needs n_mels >= 2.
+inline int build_bwd_tab(const float* mel, int n_mels, BwdTab* bwd) {
     memset(bwd, 0, sizeof(*bwd));
-    const int n_mels = fwd.n_mels;
     bwd->n_mels = n_mels;
     for (int k2 = 0; k2 < 17; ++k2)
         for (int k1 = 0; k1 < 5; ++k1)
             for (int side = 0; side < 2; ++side) {
                 const int f0 = bin_of(k2, k1), f = side ? kBins - 1 - f0 : f0;
-                float wl = fwd.w[f].x, wh = fwd.w[f].y;
-                int d;
-                if (ml[f] <= n_mels - 2)      { d = ml[f]; }
-                else if (ml[f] == n_mels - 1) { d = n_mels - 2; wh = wl; wl = 0.0f; }
-                else                          { d = 0; wl = wh = 0.0f; }
+                int first = -1, last = -1;
+                for (int m = 0; m < n_mels; ++m)
+                    if (mel[m * kBins + f] != 0.0f) { if (first < 0) first = m; last = m; }
+                float wl = 0.0f, wh = 0.0f;
+                int d = 0;
+                if (first >= 0) {
+                    if (last - first > 1) return -1;
+                    if (first <= n_mels - 2) {
+                        d = first;
+                        wl = 0.25f * mel[first * kBins + f];
+                        wh = 0.25f * mel[(first + 1) * kBins + f];
+                    } else {                                   // only the last filter: rows (M-2, M-1)
+                        d = n_mels - 2;
+                        wh = 0.25f * mel[first * kBins + f];
+                    }
+                }
                 bwd->w[k2][k1][2 * side] = wl;
                 bwd->w[k2][k1][2 * side + 1] = wh;
                 bwd->d[k2][k1][side] = (uint32_t)d;
+            }
+    return 0;
+}
+
+// The kernel reads dP itself: a tensor of kBins + 1 rows whose row f is dP[f] (row 161 is never
+// weighted), see dp_generic in lmfb_kernels.cu.
+constexpr int kDpRows = kBins + 1;
+inline void build_bwd_tab_identity(BwdTab* bwd) {
+    memset(bwd, 0, sizeof(*bwd));
+    bwd->n_mels = kDpRows;
+    for (int k2 = 0; k2 < 17; ++k2)
+        for (int k1 = 0; k1 < 5; ++k1)
+            for (int side = 0; side < 2; ++side) {
+                const int f0 = bin_of(k2, k1), f = side ? kBins - 1 - f0 : f0;
+                bwd->w[k2][k1][2 * side] = 1.0f;
+                bwd->d[k2][k1][side] = (uint32_t)f;
             }
 }
 

@@ -62,7 +62,9 @@ def slaney_mel_basis(sr: int = SAMPLE_RATE, n_fft: int = N_FFT, n_mels: int = 40
 
 
 class MelPlan:
-    """Host-side plan for one mel basis (wraps ``aas_lmfb_plan_create``)."""
+    """Host-side plan for one mel basis (wraps ``aas_lmfb_plan_create``).  Keeps the host matrix,
+    so that copies (``copy.deepcopy``, pickling, ``torch.save`` of a whole module) rebuild the
+    native handle instead of trying to serialise it."""
 
     def __init__(self, mel_basis):
         mel = np.ascontiguousarray(
@@ -73,12 +75,19 @@ class MelPlan:
         lib = _lib.load()
         status = ctypes.c_int(0)
         self._lib = lib
+        self.mel = mel
         self.n_mels = int(mel.shape[0])
         self.handle = lib.aas_lmfb_plan_create(mel.ctypes.data, mel.shape[0], mel.shape[1],
                                                ctypes.byref(status))
         if not self.handle:
             _lib.check(status.value)
             raise RuntimeError("aas_lmfb_plan_create failed")
+
+    def __reduce__(self):
+        return (MelPlan, (self.mel,))
+
+    def __deepcopy__(self, memo):
+        return MelPlan(self.mel)
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -90,6 +99,13 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _rows_disjoint(m):
+    """(N, 161, T) tensor whose rows do not overlap in memory (gradients are written with the same
+    strides, so an expanded / overlapping view would make utterances race on the same words)."""
+    n, f, t = m.shape
+    return m.stride(1) >= t and (n == 1 or m.stride(0) >= f * m.stride(1))
+
+
 def _check_f32_cuda(name, t, dev):
     if t.dtype != torch.float32 or t.device != dev:
         raise TypeError(f"{name} must be a float32 tensor on {dev}")
@@ -97,18 +113,21 @@ def _check_f32_cuda(name, t, dev):
 
 class LMFB(torch.autograd.Function):
     """``Z, frame_lens = LMFB.apply(wave, lengths, mask_r, mask_i, plan, window, mask_mode,
-    cmvn_mode, eps, tmax)``
+    cmvn_mode, eps, tmax, mel_dev)``
 
-    wave (N, Lmax) f32 cuda zero-padded; lengths (N,) int32 cuda (samples); masks
-    (N, 161, Tmax) f32 or None; plan a :class:`MelPlan`; window (320,) f32 cuda.
+    wave (N, Lmax) f32 cuda zero-padded -- or (N, nCH, Lmax) for multi-channel input, with masks
+    (N, nCH*161, Tmax) as in ``BRNNmultiCH`` (model.py:160-167, :186-198: the basis repeats over the
+    channels, i.e. the masked powers are summed); lengths (N,) int32 cuda (samples); masks
+    (N, 161, Tmax) f32 or None; plan a :class:`MelPlan`; window (320,) f32 cuda; ``mel_dev`` the
+    (M, 161) basis on the device (only read for bases off the fast path).
     Returns Z (N, M, Tmax) f32 with frames ``t >= T_i`` exactly zero, and frame_lens (N,)
     int32 (``T_i = 1 + L_i // 160``).  Gradients flow to mask_r / mask_i and, when ``wave``
-    requires grad, to the waveform (``aas_lmfb_backward_wave``).
+    requires grad, to the waveform.
     """
 
     @staticmethod
     def forward(ctx, wave, lengths, mask_r, mask_i, plan, window, mask_mode="reim",
-                cmvn_mode="per_bin", eps=0.0, tmax=None):
+                cmvn_mode="per_bin", eps=0.0, tmax=None, mel_dev=None):
         if not wave.is_cuda:
             raise RuntimeError("LMFB is CUDA-only (sm_100a); there is no CPU fallback")
         dev = wave.device
@@ -117,13 +136,18 @@ class LMFB(torch.autograd.Function):
             raise ValueError(f"bad mask_mode/cmvn_mode: {mask_mode!r}/{cmvn_mode!r}")
         _check_f32_cuda("wave", wave, dev)
         _check_f32_cuda("window", window, dev)
-        if wave.dim() != 2 or wave.stride(1) != 1:
-            raise ValueError("wave must be (N, Lmax) with unit sample stride")
+        if wave.dim() not in (2, 3) or wave.stride(-1) != 1:
+            raise ValueError("wave must be (N, Lmax) or (N, nCH, Lmax) with unit sample stride")
+        n = wave.shape[0]
+        n_ch = wave.shape[1] if wave.dim() == 3 else 1
+        lmax = wave.shape[-1]
+        if (n > 1 and wave.stride(0) < n_ch * lmax) or (wave.dim() == 3 and n_ch > 1 and wave.stride(1) < lmax):
+            wave = wave.contiguous()                   # overlapping rows (e.g. an expanded view)
         if lengths.dtype != torch.int32 or lengths.device != dev:
             lengths = lengths.to(device=dev, dtype=torch.int32)
         lengths = lengths.contiguous()
         window = window.contiguous()
-        n = wave.shape[0]
+        rows = n_ch * N_BINS
         use_r = mask_mode in ("reim", "power")
         use_i = mask_mode == "reim"
         if (use_r and mask_r is None) or (use_i and mask_i is None):
@@ -133,10 +157,10 @@ class LMFB(torch.autograd.Function):
         msn = msf = 0
         if use_r:
             _check_f32_cuda("mask_r", mask_r, dev)
-            if mask_r.dim() != 3 or mask_r.shape[0] != n or mask_r.shape[1] != N_BINS:
-                raise ValueError("mask_r must be (N, 161, Tmax)")
-            if mask_r.stride(2) != 1:
-                mask_r = mask_r.contiguous()
+            if mask_r.dim() != 3 or mask_r.shape[0] != n or mask_r.shape[1] != rows:
+                raise ValueError("mask_r must be (N, nCH*161, Tmax)")
+            if mask_r.stride(2) != 1 or not _rows_disjoint(mask_r):
+                mask_r = mask_r.contiguous()           # e.g. a mask expanded over the batch (stride 0)
             if tmax is None:
                 tmax = mask_r.shape[2]
             elif mask_r.shape[2] != tmax:
@@ -146,40 +170,45 @@ class LMFB(torch.autograd.Function):
             _check_f32_cuda("mask_i", mask_i, dev)
             if mask_i.shape != mask_r.shape:
                 raise ValueError("mask_i must have the shape of mask_r")
-            if mask_i.stride() != mask_r.stride():
+            if mask_i.stride() != mask_r.stride() or not _rows_disjoint(mask_i):
                 mask_i = mask_i.contiguous()
                 mask_r = mask_r.contiguous()
                 msn, msf = mask_r.stride(0), mask_r.stride(1)
         if tmax is None:
-            tmax = 1 + wave.shape[1] // HOP
+            tmax = 1 + lmax // HOP
         tmax = int(tmax)
+        if mel_dev is not None:
+            _check_f32_cuda("mel_dev", mel_dev, dev)
+            mel_dev = mel_dev.contiguous()
         flags = _lib.MASK_MODES[mask_mode] | _lib.CMVN_MODES[cmvn_mode]
         out = torch.empty((n, plan.n_mels, tmax), dtype=torch.float32, device=dev)
         stats = torch.empty((n, plan.n_mels, 2), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib.aas_lmfb_forward(plan.handle, wave.data_ptr(), lengths.data_ptr(), n,
-                                      wave.stride(0), _ptr(mask_r), _ptr(mask_i), msn, msf,
-                                      window.data_ptr(), out.data_ptr(), stats.data_ptr(), tmax,
-                                      flags, float(eps), stream, None)
-        _lib.check(rc)
-        frame_lens = torch.clamp(1 + torch.div(lengths, HOP, rounding_mode="floor"), max=tmax)
+        io = _lib.make_io(flags=flags, device=dev.index if dev.index is not None else -1, n=n, n_ch=n_ch, tmax=tmax,
+                          eps=float(eps), wave=wave.data_ptr(), wave_stride=_row_stride(wave, n_ch),
+                          wave_stride_ch=wave.stride(1) if wave.dim() == 3 else 0, wave_len=lmax,
+                          lengths=lengths.data_ptr(), mask_r=_ptr(mask_r), mask_i=_ptr(mask_i),
+                          mask_stride_n=msn, mask_stride_f=msf, window=window.data_ptr(), mel_dev=_ptr(mel_dev),
+                          out=out.data_ptr(), stats=stats.data_ptr(),
+                          cuda_stream=torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.aas_lmfb_forward_ex(plan.handle, ctypes.byref(io)))
+        frame_lens = torch.clamp(1 + torch.div(torch.clamp(lengths, max=lmax), HOP, rounding_mode="floor"), max=tmax)
         frame_lens = torch.where(lengths >= 1, frame_lens, torch.zeros_like(frame_lens)).to(torch.int32)
-        ctx.plan, ctx.flags, ctx.eps, ctx.tmax = plan, flags, float(eps), tmax
+        ctx.plan, ctx.flags, ctx.eps, ctx.tmax, ctx.n_ch = plan, flags, float(eps), tmax, n_ch
         ctx.strides = (msn, msf)
-        ctx.save_for_backward(wave, lengths, mask_r, mask_i, window, out, stats)
+        ctx.save_for_backward(wave, lengths, mask_r, mask_i, window, out, stats, mel_dev)
         ctx.mark_non_differentiable(frame_lens)
         return out, frame_lens
 
     @staticmethod
     def backward(ctx, grad_out, _grad_lens):
-        wave, lengths, mask_r, mask_i, window, out, stats = ctx.saved_tensors
+        wave, lengths, mask_r, mask_i, window, out, stats, mel_dev = ctx.saved_tensors
         want_wave = ctx.needs_input_grad[0]
         if mask_r is None and not want_wave:
-            return (None,) * 10
+            return (None,) * 11
         lib = _lib.load()
         dev = wave.device
-        n, plan, tmax = wave.shape[0], ctx.plan, ctx.tmax
+        n, plan, tmax, n_ch = wave.shape[0], ctx.plan, ctx.tmax, ctx.n_ch
+        lmax = wave.shape[-1]
         grad_out = grad_out.contiguous()
         if grad_out.dtype != torch.float32:
             grad_out = grad_out.float()
@@ -187,28 +216,51 @@ class LMFB(torch.autograd.Function):
             if mask_r is not None else None
         gi = torch.empty_strided(mask_i.shape, mask_i.stride(), dtype=torch.float32, device=dev) \
             if mask_i is not None else None
-        ws_bytes = lib.aas_lmfb_workspace_bytes(n, plan.n_mels, tmax, ctx.flags)
+        ws_bytes = lib.aas_lmfb_workspace_bytes(plan.handle, n, tmax, ctx.flags)
         ws = torch.empty((max(ws_bytes, 4) + 3) // 4, dtype=torch.float32, device=dev)
         msn, msf = ctx.strides
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            if want_wave:
-                # gradient into the samples too (a waveform-domain enhancer in front of this op)
-                gw = torch.zeros_like(wave)
-                rc = lib.aas_lmfb_backward_wave(plan.handle, wave.data_ptr(), lengths.data_ptr(), n,
-                                                wave.stride(0), _ptr(mask_r), _ptr(mask_i), msn, msf,
-                                                window.data_ptr(), out.data_ptr(), stats.data_ptr(),
-                                                grad_out.data_ptr(), _ptr(gr), _ptr(gi), gw.data_ptr(),
-                                                ws.data_ptr(), tmax, ctx.flags, ctx.eps, stream)
-            else:
-                gw = None
-                rc = lib.aas_lmfb_backward(plan.handle, wave.data_ptr(), lengths.data_ptr(), n,
-                                           wave.stride(0), _ptr(mask_r), _ptr(mask_i), msn, msf,
-                                           window.data_ptr(), out.data_ptr(), stats.data_ptr(),
-                                           grad_out.data_ptr(), gr.data_ptr(), _ptr(gi), ws.data_ptr(),
-                                           tmax, ctx.flags, ctx.eps, stream, None)
-        _lib.check(rc)
-        return gw, None, gr, gi, None, None, None, None, None, None
+        gw = None
+        if want_wave:
+            # gradient into the samples too (a waveform-domain enhancer in front of this op).  The C ABI
+            # has one set of strides for wave and grad_wave: zeros_like would return contiguous strides
+            # for a wave that is a slice of a larger buffer
+            gw = torch.empty_strided(wave.shape, wave.stride(), dtype=torch.float32, device=dev) \
+                if _dense_strides(wave) else None
+            if gw is None:
+                wave = wave.contiguous()
+                gw = torch.empty_like(wave)
+            gw.zero_()                                     # (the library zeroes what it accumulates into; this covers a caller-chosen smaller tmax)
+        io = _lib.make_io(flags=ctx.flags, device=dev.index if dev.index is not None else -1, n=n, n_ch=n_ch, tmax=tmax,
+                          eps=ctx.eps, wave=wave.data_ptr(), wave_stride=_row_stride(wave, n_ch),
+                          wave_stride_ch=wave.stride(1) if wave.dim() == 3 else 0, wave_len=lmax,
+                          lengths=lengths.data_ptr(), mask_r=_ptr(mask_r), mask_i=_ptr(mask_i),
+                          mask_stride_n=msn, mask_stride_f=msf, window=window.data_ptr(), mel_dev=_ptr(mel_dev),
+                          out=out.data_ptr(), stats=stats.data_ptr(), grad_out=grad_out.data_ptr(),
+                          grad_mask_r=_ptr(gr), grad_mask_i=_ptr(gi), grad_wave=_ptr(gw), workspace=ws.data_ptr(),
+                          cuda_stream=torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.aas_lmfb_backward_ex(plan.handle, ctypes.byref(io)))
+        return gw, None, gr, gi, None, None, None, None, None, None, None
+
+
+def _dense_strides(wave):
+    """Rows (and channels) of the wave do not overlap, so a gradient buffer with the SAME strides can
+    be allocated (a slice of a larger buffer qualifies, an expanded view does not)."""
+    lmax = wave.shape[-1]
+    if wave.dim() == 2:
+        return wave.shape[0] == 1 or wave.stride(0) >= lmax
+    n, c = wave.shape[0], wave.shape[1]
+    if c > 1 and wave.stride(1) < lmax:
+        return False
+    return n == 1 or wave.stride(0) >= (c - 1) * wave.stride(1) + lmax
+
+
+def _row_stride(wave, n_ch):
+    """Utterance stride handed to the C ABI; with a single utterance it is never multiplied by
+    anything but zero, so an even value keeps the 8-byte staging path available."""
+    if wave.shape[0] > 1:
+        return wave.stride(0)
+    tot = n_ch * wave.shape[-1] if wave.dim() == 2 else (n_ch - 1) * wave.stride(1) + wave.shape[-1]
+    return tot + (tot & 1)
 
 
 class LMFBFrontEnd(torch.nn.Module):
@@ -234,7 +286,31 @@ class LMFBFrontEnd(torch.nn.Module):
         self.register_buffer("mel_basis", mel)
         self.register_buffer("window", win)
         self.mask_mode, self.cmvn_mode, self.eps = mask_mode, cmvn_mode, float(eps)
-        self.plan = MelPlan(mel)
+        self._plan, self._plan_key = None, None
+        self._tuning = (0, 0, False)
+
+    def set_tuning(self, warps_fwd=0, warps_bwd=0, static_schedule=False):
+        """Tests / benchmarks: warps per 32-frame tile of the forward / backward kernel (2..5, 0 = the
+        measured default) and the static tile schedule.  Results do not depend on them."""
+        self._tuning = (int(warps_fwd), int(warps_bwd), bool(static_schedule))
+        self._plan_key = None
+        return self
+
+    @property
+    def plan(self):
+        """The native plan of the CURRENT ``mel_basis`` buffer: rebuilt when the buffer is replaced
+        (``.to()``) or written in place (``load_state_dict`` copies into it), so a checkpoint with a
+        different basis can never run on a stale plan."""
+        mel = self.mel_basis
+        key = (id(mel), mel._version, tuple(mel.shape))
+        if self._plan is None or key != self._plan_key:
+            host = mel.detach().cpu()
+            if self._plan is None or host.shape != self._plan.mel.shape or \
+                    not np.array_equal(host.numpy(), self._plan.mel):
+                self._plan = MelPlan(host)
+            _lib.check(self._plan._lib.aas_lmfb_plan_set_tuning(self._plan.handle, *[int(v) for v in self._tuning]))
+            self._plan_key = key
+        return self._plan
 
     @property
     def audio_conf(self):
@@ -247,7 +323,7 @@ class LMFBFrontEnd(torch.nn.Module):
 
     def forward(self, wave, lengths, mask_r=None, mask_i=None, tmax=None):
         return LMFB.apply(wave, lengths, mask_r, mask_i, self.plan, self.window,
-                          self.mask_mode, self.cmvn_mode, self.eps, tmax)
+                          self.mask_mode, self.cmvn_mode, self.eps, tmax, self.mel_basis)
 
     @torch.no_grad()
     def stft(self, wave, lengths, tmax=None):

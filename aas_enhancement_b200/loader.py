@@ -14,7 +14,8 @@ FeatSampler        (loader_functions.py:118-137)      WaveSampler   identical bu
                                                       ids in bins of ``batch_size``, ids shuffled
                                                       inside a bin, ``shuffle()`` permutes the bins
 FeatLoader(_paired)(loader_functions.py:107-116)      WaveLoader(_paired): torch DataLoader whose
-                                                      collate_fn is collate_wave(_paired), pinned
+                                                      collate_fn is collate_wave(_paired); pinned
+                                                      in the main process (pin_memory=True)
 DataLoader.next    (data_loader.py:8-83)              WaveDataLoader.next(cl_ny, type): same five
                                                       streams, same re-shuffle / restart on exhaustion
 _get_variable_*    (utils.py:139-160)                 to_device: one asynchronous H2D copy per tensor
@@ -107,22 +108,22 @@ class WaveSampler(Sampler):
         np.random.shuffle(self.bins)
 
 
-def _pinned(fn):
-    def collate(batch):
-        return fn(batch, pin_memory=torch.cuda.is_available())
-    return collate
-
-
 class WaveLoader(DataLoader):
+    """torch DataLoader with ``collate_wave`` (module-level, so it pickles under spawn/forkserver).
+    Nothing is pinned inside the collate function: with ``num_workers > 0`` it runs in a worker
+    process, where a pinned allocation would initialise CUDA (or fail after a fork).  Pass
+    ``pin_memory=True`` to let the DataLoader's pin thread do it in the main process, or let
+    :func:`to_device` pin (it does when the batch is not pinned yet)."""
+
     def __init__(self, *args, **kwargs):
+        kwargs.setdefault("collate_fn", collate_wave)
         super().__init__(*args, **kwargs)
-        self.collate_fn = _pinned(collate_wave)
 
 
 class WaveLoader_paired(DataLoader):
     def __init__(self, *args, **kwargs):
+        kwargs.setdefault("collate_fn", collate_wave_paired)
         super().__init__(*args, **kwargs)
-        self.collate_fn = _pinned(collate_wave_paired)
 
 
 class WaveDataLoader:
@@ -132,10 +133,12 @@ class WaveDataLoader:
     stream restarts (the reference's stray ``loader = self.te_dl`` at :74 is not reproduced)."""
 
     def __init__(self, batch_size, paired=False, tr_cl_manifest="", tr_ny_manifest="", trsub_manifest="",
-                 val_manifest="", val2_manifest="", labels=None, num_workers=0):
+                 val_manifest="", val2_manifest="", labels=None, num_workers=0, pin_memory=None):
         self.batch_size = batch_size
         self.labels = labels
         self.num_workers = num_workers
+        # pinned by the DataLoader's pin thread in the MAIN process (never inside a worker)
+        self.pin_memory = torch.cuda.is_available() if pin_memory is None else bool(pin_memory)
         self.Loader = WaveLoader_paired if paired else WaveLoader
         self._ds, self._sp, self._it = {}, {}, {}
         for key, manifest, sampled in (("cl/train", tr_cl_manifest, True), ("ny/train", tr_ny_manifest, True),
@@ -149,8 +152,10 @@ class WaveDataLoader:
 
     def _make(self, key):
         if key in self._sp:
-            return iter(self.Loader(self._ds[key], num_workers=self.num_workers, batch_sampler=self._sp[key]))
-        return iter(self.Loader(self._ds[key], batch_size=self.batch_size, num_workers=self.num_workers))
+            return iter(self.Loader(self._ds[key], num_workers=self.num_workers, batch_sampler=self._sp[key],
+                                    pin_memory=self.pin_memory))
+        return iter(self.Loader(self._ds[key], batch_size=self.batch_size, num_workers=self.num_workers,
+                                pin_memory=self.pin_memory))
 
     def next(self, cl_ny='', type=''):
         key = f"{cl_ny}/{type}"
@@ -167,12 +172,20 @@ class WaveDataLoader:
 
 def to_device(batch, device=None, stream=None):
     """utils.py:139-160 for a whole batch tuple: every tensor is copied host -> device
-    asynchronously (the collate functions above pin their outputs) on ``stream`` (default: the
-    current stream); non-tensors pass through."""
+    asynchronously on ``stream`` (default: the current stream); non-tensors pass through.  Host
+    tensors that are not pinned yet (``pin_memory=False`` loaders) are pinned here, in the calling
+    process, so that every copy is a true asynchronous DMA."""
     device = torch.device("cuda") if device is None else torch.device(device)
     ctx = torch.cuda.stream(stream) if stream is not None else _Null()
+
+    def move(t):
+        if not isinstance(t, torch.Tensor):
+            return t
+        if device.type == "cuda" and not t.is_cuda and not t.is_pinned() and t.numel() > 0:
+            t = t.pin_memory()
+        return t.to(device, non_blocking=True)
     with ctx:
-        return tuple(t.to(device, non_blocking=True) if isinstance(t, torch.Tensor) else t for t in batch)
+        return tuple(move(t) for t in batch)
 
 
 class _Null:

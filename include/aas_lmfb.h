@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define AAS_LMFB_ABI_VERSION 1
+#define AAS_LMFB_ABI_VERSION 2
 
 #define AAS_LMFB_N_FFT   320   /* int(16000 * 0.02), AM_training/train.py:39-40 */
 #define AAS_LMFB_HOP     160   /* int(16000 * 0.01), AM_training/train.py:41    */
@@ -49,7 +49,7 @@ extern "C" {
 #define AAS_LMFB_E_ALIGN        -2
 #define AAS_LMFB_E_SHAPE        -3
 #define AAS_LMFB_E_FLAGS        -4
-#define AAS_LMFB_E_MEL          -5   /* mel basis is not representable (see plan_create)       */
+#define AAS_LMFB_E_MEL          -5   /* generic mel basis: the call needs io.mel_dev (see plan_create) */
 #define AAS_LMFB_E_NOMEM        -6   /* host allocation failed                                 */
 
 typedef struct aas_lmfb_plan aas_lmfb_plan;
@@ -58,15 +58,61 @@ int aas_lmfb_abi_version(void);
 const char* aas_lmfb_strerror(int code);
 
 /* Build a host-side plan from the mel basis, a HOST (n_mels, 161) row-major fp32 matrix -- the
- * `mel_basis` constructor argument of BRNNmultiCH (model.py:148, :167).  The basis must be
- * "banded": every bin feeds at most two filters, adjacent in index, and filters are ordered
- * along frequency (true of every triangular mel filterbank).  Returns NULL and sets *status
- * otherwise.  No device work. */
+ * `mel_basis` constructor argument of BRNNmultiCH (model.py:148, :167).  ANY matrix is accepted, as
+ * the reference's k=1 conv1d accepts any (model.py:196).  Triangular filterbanks (every bin feeds at
+ * most two adjacent filters, rows short enough for the on-chip table) run on the fast path; other
+ * bases (dense, re-ordered, hand-made) run on a generic path that needs the caller's DEVICE copy of
+ * the same matrix (`mel_dev` of aas_lmfb_io) and more workspace.  No device work here. */
 aas_lmfb_plan* aas_lmfb_plan_create(const float* mel_host, int n_mels, int n_bins, int* status);
 void aas_lmfb_plan_destroy(aas_lmfb_plan* plan);
+/* What the analysis found: *fwd_compact / *bwd_banded are 1 on the fast paths (any may be NULL). */
+int aas_lmfb_plan_info(const aas_lmfb_plan* plan, int* n_mels, int* fwd_compact, int* bwd_banded);
+/* Tuning knobs (tests and benchmarks; 0 = the measured default): warps per 32-frame tile of the
+ * forward / backward kernel (2..5), and static_schedule = 1 to deal tiles round-robin instead of
+ * handing them out with cluster launch control.  Results do not depend on them. */
+int aas_lmfb_plan_set_tuning(aas_lmfb_plan* plan, int warps_fwd, int warps_bwd, int static_schedule);
 
-/* Bytes of device workspace `backward` needs (forward needs none). */
-size_t aas_lmfb_workspace_bytes(int n, int n_mels, int tmax, uint32_t flags);
+/* Bytes of device workspace `backward` needs for this plan (forward needs none). */
+size_t aas_lmfb_workspace_bytes(const aas_lmfb_plan* plan, int n, int tmax, uint32_t flags);
+
+/* ---- extended call: everything in one struct -------------------------------------------------
+ * Multi-channel input (BRNNmultiCH with nCH > 1, model.py:160-167, :186-198: masks are
+ * (N, nCH*161, T), the basis repeats over the channels, i.e. the masked powers of the channels are
+ * summed before the mel projection), generic bases, an explicit device and the readable length of
+ * the wave rows.  The classic entry points below are thin wrappers around these. */
+typedef struct aas_lmfb_io {
+    uint32_t       struct_size;     /* sizeof(aas_lmfb_io): lets the struct grow compatibly            */
+    uint32_t       flags;           /* mask mode | CMVN mode                                           */
+    int32_t        device;          /* CUDA device of the buffers; -1 = the calling thread's current   */
+    int32_t        n;               /* utterances                                                      */
+    int32_t        n_ch;            /* channels per utterance, >= 1                                    */
+    int32_t        tmax;
+    float          eps;
+    int32_t        reserved_;
+    const float*   wave;            /* (N, n_ch, .): sample (n, c, i) at n*wave_stride + c*wave_stride_ch + i */
+    int64_t        wave_stride;
+    int64_t        wave_stride_ch;
+    int64_t        wave_len;        /* samples of every row that may be read; lengths are clamped to it (0: trust lengths) */
+    const int32_t* lengths;         /* (N,) samples; all channels of an utterance share it             */
+    const float*   mask_r;          /* (N, n_ch*161, Tmax): row c*161 + f                              */
+    const float*   mask_i;
+    int64_t        mask_stride_n;
+    int64_t        mask_stride_f;
+    const float*   window;          /* device (320,)                                                   */
+    const float*   mel_dev;         /* device (n_mels, 161), contiguous: needed only by generic plans  */
+    float*         out;             /* (N, M, Tmax)                                                    */
+    float*         stats;           /* (N, M, 2)                                                       */
+    const float*   grad_out;        /* backward: (N, M, Tmax)                                          */
+    float*         grad_mask_r;     /* backward: strides of the masks                                  */
+    float*         grad_mask_i;
+    float*         grad_wave;       /* backward, optional: layout of `wave`                            */
+    void*          workspace;       /* backward: aas_lmfb_workspace_bytes() bytes, 16-byte aligned     */
+    void*          cuda_stream;
+    void* const*   prof;            /* optional 4 cudaEvent_t recorded around the two kernels          */
+} aas_lmfb_io;
+
+int aas_lmfb_forward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io* io);
+int aas_lmfb_backward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io* io);
 
 /* Forward: framing + Hamming window + STFT(320/160) + mask + mel + log1p (+ CMVN).
  * Stands in for the missing SpectrogramDataset front-end (AM_training/train.py:190-199,

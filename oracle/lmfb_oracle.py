@@ -180,6 +180,10 @@ def lmfb_forward(wave, lengths, mask_r=None, mask_i=None, mel=None, window=None,
     wave (N, Lmax), lengths (N,), masks (N, F, Tmax) or None.  Returns Z (N, M, Tmax)
     float64 with frames t >= T_i exactly 0 (collate zero-fill happens after the
     per-utterance normalisation, loader_functions.py:56, :66) and frame_lens (N,) int32.
+
+    Multi-channel (BRNNmultiCH with nCH > 1, model.py:160-167, :186-198): wave (N, nCH, Lmax),
+    masks (N, nCH*F, Tmax) with channel c in rows [c*F, (c+1)*F); the mel basis repeats over the
+    channels (``mel_basis.repeat(1, nCH)``, model.py:167), i.e. the masked powers are summed.
     """
     wave = np.asarray(wave, dtype=np.float64)
     lengths = np.asarray(lengths, dtype=np.int64)
@@ -201,12 +205,17 @@ def lmfb_forward(wave, lengths, mask_r=None, mask_i=None, mel=None, window=None,
     parts = []
     for i in range(n):
         t_i = int(frame_lens[i])
-        spec = stft_frames(wave[i], int(lengths[i]), window, n_fft, hop)
-        re, im = spec.real, spec.imag
-        mr = None if mask_r is None else np.asarray(mask_r[i, :, :t_i], dtype=np.float64)
-        mi = None if mask_i is None else np.asarray(mask_i[i, :, :t_i], dtype=np.float64)
-        p = masked_power(re, im, mr, mi, mask_mode)
-        e = mel @ p                                   # model.py:196 (k=1 conv == matmul)
+        chans = wave[i] if wave.ndim == 3 else wave[i][None]
+        n_bins = n_fft // 2 + 1
+        p = 0.0
+        for c in range(chans.shape[0]):
+            spec = stft_frames(chans[c], int(lengths[i]), window, n_fft, hop)
+            re, im = spec.real, spec.imag
+            rows = slice(c * n_bins, (c + 1) * n_bins)
+            mr = None if mask_r is None else np.asarray(mask_r[i, rows, :t_i], dtype=np.float64)
+            mi = None if mask_i is None else np.asarray(mask_i[i, rows, :t_i], dtype=np.float64)
+            p = p + masked_power(re, im, mr, mi, mask_mode)
+        e = mel @ p                                   # model.py:196 (k=1 conv == matmul; basis repeated over channels :167)
         y = np.log1p(e)                               # model.py:198
         zi, mean, rstd = cmvn(y, cmvn_mode, eps)
         z[i, :, :t_i] = zi
@@ -250,15 +259,19 @@ def lmfb_forward_torch(wave, lengths, mask_r=None, mask_i=None, mel=None, window
         t_i = frame_lens[i]
         idx = (np.arange(t_i)[:, None] * hop + np.arange(n_fft)[None, :]) - n_fft // 2
         idx = torch.as_tensor(reflect_index(idx, lengths[i]))
-        frames = wave[i].to(dtype)[idx] * win_t[None, :]         # (T, n_fft)
-        re = cos_m @ frames.T                                     # (F, T)
-        im = sin_m @ frames.T
-        if mask_mode == "reim":
-            p = (re * mask_r[i, :, :t_i].to(dtype)) ** 2 + (im * mask_i[i, :, :t_i].to(dtype)) ** 2
-        elif mask_mode == "power":
-            p = mask_r[i, :, :t_i].to(dtype) * (re ** 2 + im ** 2)
-        else:
-            p = re ** 2 + im ** 2
+        chans = wave[i] if wave.dim() == 3 else wave[i][None]
+        p = 0.0
+        for c in range(chans.shape[0]):
+            frames = chans[c].to(dtype)[idx] * win_t[None, :]     # (T, n_fft)
+            re = cos_m @ frames.T                                 # (F, T)
+            im = sin_m @ frames.T
+            fr = slice(c * n_bins, (c + 1) * n_bins)
+            if mask_mode == "reim":
+                p = p + (re * mask_r[i, fr, :t_i].to(dtype)) ** 2 + (im * mask_i[i, fr, :t_i].to(dtype)) ** 2
+            elif mask_mode == "power":
+                p = p + mask_r[i, fr, :t_i].to(dtype) * (re ** 2 + im ** 2)
+            else:
+                p = p + re ** 2 + im ** 2
         y = torch.log1p(mel_t @ p)
         if cmvn_mode == "per_bin":
             y = (y - y.mean(dim=1, keepdim=True)) / (y.std(dim=1, keepdim=True) + eps)

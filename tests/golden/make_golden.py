@@ -10,6 +10,7 @@ Fixtures written
                       autograd gradients w.r.t. both masks are stored.
   ref_glue_on_stft.npz  LIVE REFERENCE: the same tail fed with the oracle's STFT of a seeded wave,
                       so the CUDA path (STFT included) can be compared with the reference output.
+  ref_glue_2ch.npz    LIVE REFERENCE with nCH = 2 (masks (N, 2*161, T), basis repeated over the channels).
   ref_l1loss.npz      LIVE REFERENCE: L1Loss_mask (model.py:19-31) loss, nElement and gradients.
   ref_collate.npz     LIVE REFERENCE: _collate_fn / _collate_fn_paired outputs
                       (loader_functions.py:47-105) for a seeded ragged batch.
@@ -120,6 +121,60 @@ def make_ref_glue_on_stft():
     sys.path.remove(REF)
 
 
+def make_ref_glue_2ch():
+    """LIVE REFERENCE with nCH = 2: BRNNmultiCH(I = 2*2*161, nCH = 2) (model.py:148-200; the basis is
+    repeated over the channels at :167, so the conv1d at :196 sums the two channels' masked powers) fed
+    with the oracle's STFT of a seeded two-channel wave."""
+    sys.path.insert(0, REF)
+    import model as ref_model
+
+    torch.manual_seed(77)
+    f, h, n_ch = 161, 20, 2
+    b0 = _synth.make_batch(2, 2900, seed=41, ragged=True)
+    b1 = _synth.make_batch(2, 2900, seed=42, lengths=b0["lengths"])
+    win = orc.hamming_window().astype(np.float32).astype(np.float64)
+    mel = orc.mel_filterbank().astype(np.float32)
+    tmax = b0["tmax"]
+    re = np.zeros((2, n_ch * f, tmax)); im = np.zeros((2, n_ch * f, tmax))
+    for i in range(2):
+        for c, b in enumerate((b0, b1)):
+            sp = orc.stft_frames(b["wave"][i], int(b["lengths"][i]), win)
+            re[i, c * f:(c + 1) * f, :sp.shape[1]] = sp.real
+            im[i, c * f:(c + 1) * f, :sp.shape[1]] = sp.imag
+    x = torch.from_numpy(np.concatenate([re, im], axis=1).astype(np.float32))     # (N, nCH*F*2, T), model.py:170
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        net = ref_model.BRNNmultiCH(I=2 * n_ch * f, H=h, L=2, nCH=n_ch, mel_basis=mel).float()
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    with torch.no_grad():
+        net.final_linear_real.bias.fill_(0.7)
+        net.final_linear_imag.bias.fill_(0.6)
+        net.final_linear_real.weight.mul_(3.0)
+        net.final_linear_imag.weight.mul_(3.0)
+    captured = {}
+
+    def hook(name):
+        def fn(_m, _i, out):
+            out.retain_grad()
+            captured[name] = out
+        return fn
+
+    net.final_linear_real.register_forward_hook(hook("mr"))
+    net.final_linear_imag.register_forward_hook(hook("mi"))
+    out = net(x)
+    g = torch.from_numpy(b0["grad_out"][:, :, :out.shape[2]].copy())
+    out.backward(g)
+    np.savez_compressed(
+        os.path.join(HERE, "ref_glue_2ch.npz"),
+        seeds=np.asarray([41, 42]), n=2, max_len=2900,
+        mask_real=captured["mr"].detach().numpy(), mask_imag=captured["mi"].detach().numpy(),
+        output=out.detach().numpy(), grad_out=g.numpy(),
+        grad_mask_real=captured["mr"].grad.numpy(), grad_mask_imag=captured["mi"].grad.numpy())
+    sys.path.remove(REF)
+
+
 def make_ref_l1loss():
     """LIVE REFERENCE: L1Loss_mask.forward (model.py:19-31) + autograd on a padded, length-sorted batch."""
     sys.path.insert(0, REF)
@@ -210,6 +265,7 @@ def make_oracle_cases():
 if __name__ == "__main__":
     make_ref_glue()
     make_ref_glue_on_stft()
+    make_ref_glue_2ch()
     make_ref_l1loss()
     make_ref_collate()
     make_ref_ctc_sizes()

@@ -32,25 +32,53 @@ def test_exports_match_header(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.aas_lmfb_abi_version() == 1
+    assert lib.aas_lmfb_abi_version() == 2
     assert lib.aas_lmfb_strerror(0) == b"ok"
     for code in (-1, -2, -3, -4, -5, -6):
         assert b"aas_lmfb" in lib.aas_lmfb_strerror(code)
 
 
-def test_plan_create_accepts_triangular_and_rejects_dense(lib):
+def _info(lib, plan):
+    m, c, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.aas_lmfb_plan_info(plan.handle, ctypes.byref(m), ctypes.byref(c), ctypes.byref(b)) == 0
+    return m.value, c.value, b.value
+
+
+def test_plan_create_accepts_any_basis(lib):
+    """The reference applies any (M, F) matrix (model.py:167, :196): triangular filterbanks take the fast
+    path, dense / re-ordered ones the generic path; only the shape is checked."""
     from aas_enhancement_b200 import MelPlan, slaney_mel_basis
     for n_mels in (40, 64, 80):
-        assert MelPlan(slaney_mel_basis(n_mels=n_mels)).handle
-    with pytest.raises(RuntimeError, match="not banded"):
-        MelPlan(np.ones((40, 161), dtype=np.float32))
+        assert _info(lib, MelPlan(slaney_mel_basis(n_mels=n_mels))) == (n_mels, 1, 1)
+    assert _info(lib, MelPlan(np.ones((40, 161), dtype=np.float32))) == (40, 0, 0)
+    assert _info(lib, MelPlan(slaney_mel_basis()[::-1].copy())) == (40, 0, 1)      # reversed order: not walkable, but still two adjacent rows per bin
+    perm = slaney_mel_basis()[np.random.RandomState(0).permutation(40)]
+    assert _info(lib, MelPlan(perm)) == (40, 0, 0)
     with pytest.raises(RuntimeError, match="unsupported shape"):
         MelPlan(np.ones((40, 257), dtype=np.float32))
 
 
-def test_workspace_bytes(lib):
-    assert lib.aas_lmfb_workspace_bytes(30, 40, 601, 5) == 30 * 40 * 601 * 4
-    assert lib.aas_lmfb_workspace_bytes(0, 40, 601, 5) == 0
+def test_workspace_bytes_and_tuning(lib):
+    from aas_enhancement_b200 import MelPlan, slaney_mel_basis
+    plan = MelPlan(slaney_mel_basis())
+    assert lib.aas_lmfb_workspace_bytes(plan.handle, 30, 601, 5) == 30 * 40 * 601 * 4
+    assert lib.aas_lmfb_workspace_bytes(plan.handle, 0, 601, 5) == 0
+    dense = MelPlan(np.ones((40, 161), dtype=np.float32))
+    assert lib.aas_lmfb_workspace_bytes(dense.handle, 30, 601, 5) == 30 * (40 + 162) * 601 * 4
+    assert lib.aas_lmfb_plan_set_tuning(plan.handle, 4, 3, 1) == 0
+    assert lib.aas_lmfb_plan_set_tuning(plan.handle, 7, 0, 0) == -4
+    assert lib.aas_lmfb_plan_set_tuning(plan.handle, 0, 0, 0) == 0
+
+
+def test_io_struct_matches_the_header(lib):
+    """ctypes mirror of aas_lmfb_io: same field names, in the header's order."""
+    from aas_enhancement_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "aas_lmfb.h")).read()
+    body = text[text.index("typedef struct aas_lmfb_io {"):text.index("} aas_lmfb_io;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"([a-z_0-9]+)\s*;", body)
+    assert names == [f[0] for f in _lib.IO._fields_]
+    assert ctypes.sizeof(_lib.IO) == 8 * 4 + 8 * 20
 
 
 def test_argument_errors_do_not_touch_the_gpu(lib):
@@ -61,8 +89,16 @@ def test_argument_errors_do_not_touch_the_gpu(lib):
     assert rc == -1
     rc = lib.aas_lmfb_forward(plan.handle, 16, 16, 1, 0, 16, 16, 0, 0, 16, 16, 16, 10, 0xFF, 0.0, None, None)
     assert rc == -4
-    rc = lib.aas_lmfb_forward(plan.handle, 18, 16, 1, 0, 16, 16, 0, 0, 16, 16, 16, 10, 5, 0.0, None, None)
+    rc = lib.aas_lmfb_forward(plan.handle, 18, 16, 1, 0, 16, 16, 0, 10, 16, 16, 16, 10, 5, 0.0, None, None)
     assert rc == -2
+    # a generic basis without its device copy is refused before anything is launched
+    from aas_enhancement_b200 import _lib
+    dense = MelPlan(np.ones((40, 161), dtype=np.float32))
+    io = _lib.make_io(flags=5, n=1, tmax=10, wave=16, lengths=16, mask_r=16, mask_i=16, mask_stride_n=1610,
+                      mask_stride_f=10, window=16, out=16, stats=16)
+    assert lib.aas_lmfb_forward_ex(dense.handle, ctypes.byref(io)) == -5
+    io.struct_size = 8
+    assert lib.aas_lmfb_forward_ex(plan.handle, ctypes.byref(io)) == -3
 
 
 def test_python_front_end_refuses_cpu_tensors(lib):

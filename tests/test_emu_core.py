@@ -23,30 +23,32 @@ def emu(tmp_path_factory):
     vp = ctypes.c_void_p
     lib.emu_k1.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_longlong,
                            vp, vp, ctypes.c_longlong, ctypes.c_longlong, vp, vp, ctypes.c_int, vp, vp, vp, vp,
-                           ctypes.c_int, ctypes.c_int, vp]
-    lib.emu_mel_band.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+                           ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_longlong]
+    lib.emu_mel_tables.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
     return lib
 
 
 def _k1(lib, warps, bwd, mode, b, mel, window, dE=None, vec_ok=1, want_wave_grad=False):
+    """wave (N, L) or (N, nCH, L); masks (N, nCH*161, T)."""
     modes = {"none": 0, "reim": 1, "power": 2}
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     wave, mr, mi = f32(b["wave"]), f32(b["mask_r"]), f32(b["mask_i"])
     lens = np.ascontiguousarray(b["lengths"], dtype=np.int32)
     n, tmax = wave.shape[0], b["tmax"]
+    n_ch = wave.shape[1] if wave.ndim == 3 else 1
     melf, win = f32(mel), f32(window)
     out = np.full((n, mel.shape[0], tmax), np.nan, dtype=np.float32)
     gr = np.full_like(mr, np.nan)
     gi = np.full_like(mi, np.nan)
     dE = f32(dE) if dE is not None else np.zeros_like(out)
     gw = np.zeros_like(wave) if want_wave_grad else None
-    rc = lib.emu_k1(warps, int(bwd), modes[mode], wave.ctypes.data, lens.ctypes.data, n, wave.shape[1],
+    rc = lib.emu_k1(warps, int(bwd), modes[mode], wave.ctypes.data, lens.ctypes.data, n, n_ch * wave.shape[-1],
                     mr.ctypes.data if mode != "none" else None,
                     mi.ctypes.data if mode == "reim" else None,
                     mr.shape[1] * mr.shape[2], mr.shape[2], win.ctypes.data, melf.ctypes.data,
                     mel.shape[0], out.ctypes.data, dE.ctypes.data,
                     gr.ctypes.data if mode != "none" else None, gi.ctypes.data if mode == "reim" else None,
-                    tmax, vec_ok, gw.ctypes.data if want_wave_grad else None)
+                    tmax, vec_ok, gw.ctypes.data if want_wave_grad else None, n_ch, wave.shape[-1])
     assert rc == 0
     if want_wave_grad:
         return out, gr, gi, gw
@@ -165,24 +167,98 @@ def test_emulated_wave_gradient(emu, mode, warps, length):
         assert orc.rel_err(gi, g_ref["grad_mask_i"]) < tol
 
 
-def test_mel_band_tables(emu):
-    for n_mels in (40, 23, 64, 80):
+def _tables(emu, mel, warps=4):
+    mel = np.ascontiguousarray(mel, dtype=np.float32)
+    fwd = np.zeros_like(mel); bwd = np.zeros_like(mel)
+    walkable = ctypes.c_int(-1); banded = ctypes.c_int(-1)
+    lohi = np.zeros(16, np.int32)
+    rc = emu.emu_mel_tables(mel.ctypes.data, mel.shape[0], warps, fwd.ctypes.data, bwd.ctypes.data,
+                            ctypes.byref(walkable), ctypes.byref(banded), lohi.ctypes.data)
+    assert rc == 0
+    return fwd, bwd, walkable.value, banded.value
+
+
+def test_mel_tables_reproduce_the_basis(emu):
+    """The forward tables (walk or rows) and the backward (d, d+1) table, expanded back into dense
+    matrices, are the basis itself: triangular filterbanks are walkable + banded, anything else is generic."""
+    for n_mels in (40, 23, 64, 80, 2):
         for warps in (1, 2, 4, 5):
-            mel = np.ascontiguousarray(orc.mel_filterbank(n_mels=n_mels), dtype=np.float32)
-            wl = np.zeros(161, np.float32); wh = np.zeros(161, np.float32)
-            ml = np.zeros(161, np.int32); lohi = np.zeros(16, np.int32)
-            assert emu.emu_mel_band(mel.ctypes.data, n_mels, warps, wl.ctypes.data, wh.ctypes.data,
-                                    ml.ctypes.data, lohi.ctypes.data) == 0
-            rebuilt = np.zeros_like(mel)
-            for f in range(161):
-                if ml[f] < n_mels:
-                    rebuilt[ml[f], f] += 4 * wl[f]
-                if ml[f] + 1 < n_mels:
-                    rebuilt[ml[f] + 1, f] += 4 * wh[f]
-            assert np.array_equal(rebuilt, mel)
-            assert np.all(np.diff(ml) >= 0)
-    dense = np.ones((40, 161), dtype=np.float32)
-    wl = np.zeros(161, np.float32); wh = np.zeros(161, np.float32)
-    ml = np.zeros(161, np.int32); lohi = np.zeros(16, np.int32)
-    assert emu.emu_mel_band(dense.ctypes.data, 40, 4, wl.ctypes.data, wh.ctypes.data, ml.ctypes.data,
-                            lohi.ctypes.data) == -1
+            mel = np.ascontiguousarray(orc.mel_filterbank(n_mels=n_mels) if n_mels > 2 else
+                                       np.stack([np.linspace(1, 0, 161), np.linspace(0, 1, 161)]), dtype=np.float32)
+            fwd, bwd, walkable, banded = _tables(emu, mel, warps)
+            assert walkable == 1 and np.array_equal(fwd, mel)
+            assert banded == 1 and np.array_equal(bwd, mel)
+    dense = np.random.RandomState(0).rand(40, 161).astype(np.float32)
+    fwd, _, walkable, banded = _tables(emu, dense)
+    assert walkable == 0 and banded == 0 and np.array_equal(fwd, dense)
+    perm = orc.mel_filterbank()[np.random.RandomState(1).permutation(40)]   # re-ordered filters
+    fwd, _, walkable, banded = _tables(emu, perm)
+    assert walkable == 0 and banded == 0 and np.array_equal(fwd, perm.astype(np.float32))
+
+
+@pytest.mark.parametrize("kind,warps", [("dense", 3), ("permuted", 4), ("ones", 2), ("gappy", 5)])
+def test_emulated_generic_bases(emu, kind, warps):
+    """Any (M, 161) matrix is a valid basis (the reference applies it with a k=1 conv1d, model.py:196):
+    dense, re-ordered, all-ones (MelPlan(np.ones((40, 161)))), and rows with holes."""
+    rs = np.random.RandomState(11)
+    if kind == "dense":
+        mel = rs.rand(40, 161) * 0.02
+    elif kind == "permuted":
+        mel = orc.mel_filterbank()[rs.permutation(40)]
+    elif kind == "ones":
+        mel = np.ones((40, 161)) * 0.01
+    else:
+        mel = orc.mel_filterbank() * (rs.rand(40, 161) > 0.3)
+        mel[7] = 0.0                                                     # an empty filter
+    b = _synth.make_batch(2, 4000, seed=5, ragged=True)
+    window = orc.hamming_window()
+    mel32 = mel.astype(np.float32).astype(np.float64)
+    win32 = window.astype(np.float32).astype(np.float64)
+    y_ref, fl = orc.lmfb_forward(b["wave"], b["lengths"], b["mask_r"], b["mask_i"], mel32, win32,
+                                 mask_mode="reim", cmvn_mode="none")
+    y, _, _ = _k1(emu, warps, 0, "reim", b, mel, window)
+    assert not np.isnan(y).any()
+    assert orc.rel_err(y, y_ref) < 2e-5
+    g_ref = orc.lmfb_grads(b["wave"], b["lengths"], b["mask_r"], b["mask_i"], b["grad_out"], mel32, win32,
+                           mask_mode="reim", cmvn_mode="none")
+    dE = b["grad_out"].astype(np.float64) * np.exp(-y_ref)
+    for i in range(2):
+        dE[i, :, fl[i]:] = 0.0
+    _, gr, gi = _k1(emu, warps, 1, "reim", b, mel, window, dE=dE)
+    assert orc.rel_err(gr, g_ref["grad_mask_r"]) < 2e-5
+    assert orc.rel_err(gi, g_ref["grad_mask_i"]) < 2e-5
+
+
+@pytest.mark.parametrize("n_ch,mode,warps", [(2, "reim", 3), (3, "power", 4), (2, "none", 2)])
+def test_emulated_multi_channel(emu, n_ch, mode, warps):
+    """BRNNmultiCH with nCH > 1 (model.py:160-167, :186-198): masks (N, nCH*F, T), the basis repeats over
+    the channels, i.e. the masked powers of the channels are summed before the mel projection."""
+    rs = np.random.RandomState(n_ch)
+    base = _synth.make_batch(2, 3000, seed=31 + n_ch, ragged=True)
+    n, tmax, L = 2, base["tmax"], base["wave"].shape[1]
+    wave = np.zeros((n, n_ch, L), np.float32)
+    for i in range(n):
+        li = int(base["lengths"][i])
+        wave[i, :, :li] = (0.1 * rs.randn(n_ch, li)).astype(np.float32)
+    b = dict(wave=wave, lengths=base["lengths"], tmax=tmax,
+             mask_r=rs.uniform(0, 1, (n, n_ch * 161, tmax)).astype(np.float32),
+             mask_i=rs.uniform(0, 1, (n, n_ch * 161, tmax)).astype(np.float32))
+    mel, window = orc.mel_filterbank(), orc.hamming_window()
+    mel32 = mel.astype(np.float32).astype(np.float64)
+    win32 = window.astype(np.float32).astype(np.float64)
+    mr = b["mask_r"] if mode != "none" else None
+    mi = b["mask_i"] if mode == "reim" else None
+    y_ref, fl = orc.lmfb_forward(wave, b["lengths"], mr, mi, mel32, win32, mask_mode=mode, cmvn_mode="none")
+    y, _, _ = _k1(emu, warps, 0, mode, b, mel, window)
+    assert orc.rel_err(y, y_ref) < 2e-5
+    if mode == "none":
+        return
+    g = rs.randn(n, 40, tmax)
+    g_ref = orc.lmfb_grads(wave, b["lengths"], mr, mi, g, mel32, win32, mask_mode=mode, cmvn_mode="none")
+    dE = g * np.exp(-y_ref)
+    for i in range(n):
+        dE[i, :, fl[i]:] = 0.0
+    _, gr, gi = _k1(emu, warps, 1, mode, b, mel, window, dE=dE)
+    assert orc.rel_err(gr, g_ref["grad_mask_r"]) < 2e-5
+    if mode == "reim":
+        assert orc.rel_err(gi, g_ref["grad_mask_i"]) < 2e-5

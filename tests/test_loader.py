@@ -137,3 +137,24 @@ def test_paired_loader_tuple_order(corpus):
     assert inputs.shape == outputs.shape and mask.shape[0] == 4 and lengths.dtype == torch.int32
     for i in range(4):
         assert torch.all(outputs[i, int(lengths[i]):] == 0)
+
+
+def test_loader_with_a_worker_process_and_main_process_pinning(corpus):
+    """num_workers=1 is the reference's setting (data_loader.py:27).  The collate function runs in the
+    worker and must not touch CUDA / pinned memory; the loaders pickle (spawn / forkserver)."""
+    import pickle
+    from aas_enhancement_b200 import WaveLoader, WaveLoader_paired, collate_wave_paired
+    ds = WaveDataset(corpus["manifest"], LABELS)
+    ld = WaveLoader(ds, batch_size=3, num_workers=1)
+    pickle.dumps(ld.collate_fn)
+    batches = list(ld)
+    assert len(batches) == 3
+    inputs, targets, pct, sizes, mask, lengths = batches[0]
+    ref = collate_wave([ds[i] for i in range(3)])
+    assert torch.equal(inputs, ref[0]) and torch.equal(pct, ref[2]) and torch.equal(mask, ref[4])
+    assert not inputs.is_pinned()                      # pinning is the main process's job
+    dsp = WaveDataset(corpus["paired"], LABELS)
+    ldp = WaveLoader_paired(dsp, batch_size=2, num_workers=1)
+    assert ldp.collate_fn is collate_wave_paired
+    first = next(iter(ldp))
+    assert len(first) == 7 and first[0].shape == first[1].shape

@@ -5,7 +5,7 @@ echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tai
 for wf in 3 4 2 5; do for wb in 4 3 2; do
   if [ "$wf" != "3" ] && [ "$wb" != "4" ]; then continue; fi
   for wl in sweep_256x10s chime4_30x6s; do
-    AAS_LMFB_WARPS_FWD=$wf AAS_LMFB_WARPS_BWD=$wb timeout 300 python bench.py --workload $wl --steps 200 --warmup 5 --no-cpu > gpurun_out/v.json 2> gpurun_out/v.err || tail -3 gpurun_out/v.err
+    timeout 300 python bench.py --warps-fwd $wf --warps-bwd $wb --workload $wl --steps 200 --warmup 5 --no-cpu --no-e2e --no-large > gpurun_out/v.json 2> gpurun_out/v.err || tail -3 gpurun_out/v.err
     python - <<PY
 import json
 try:

@@ -27,9 +27,7 @@ buf_f = torch.zeros(8 * 64 * 8 * 8 + 4096, dtype=torch.int64, device=dev)
 buf_b = torch.zeros(8 * 64 * 8 * 8 + 4096, dtype=torch.int64, device=dev)
 os.environ["AAS_LMFB_TIMELINE_FWD"] = str(buf_f.data_ptr())
 os.environ["AAS_LMFB_TIMELINE_BWD"] = str(buf_b.data_ptr())
-os.environ["AAS_LMFB_WARPS_FWD"] = str(W)
-os.environ["AAS_LMFB_WARPS_BWD"] = str(W)
-fe = LMFBFrontEnd(mask_mode="reim", cmvn_mode="per_bin").to(dev)
+fe = LMFBFrontEnd(mask_mode="reim", cmvn_mode="per_bin").to(dev).set_tuning(W, W)
 wave = (0.1 * torch.randn(n, samples, device=dev)).clamp_(-1, 1)
 lens = torch.full((n,), samples, dtype=torch.int32, device=dev)
 mr = torch.rand(n, 161, tmax, device=dev, requires_grad=True)
