@@ -19,6 +19,7 @@ CMVN_MODES = {"none": 0 << 2, "per_bin": 1 << 2, "global": 2 << 2}
 
 EXPORTS = ("aas_lmfb_abi_version", "aas_lmfb_strerror", "aas_lmfb_plan_create",
            "aas_lmfb_plan_destroy", "aas_lmfb_plan_info", "aas_lmfb_plan_set_tuning",
+           "aas_lmfb_plan_tables_bytes", "aas_lmfb_plan_upload",
            "aas_lmfb_workspace_bytes", "aas_lmfb_forward_ex", "aas_lmfb_backward_ex", "aas_lmfb_forward",
            "aas_lmfb_backward", "aas_lmfb_backward_wave", "aas_lmfb_stft", "aas_l1_partial_count", "aas_l1_abs_sum", "aas_l1_abs_grad")
 
@@ -37,7 +38,7 @@ class IO(ctypes.Structure):
                 ("lengths", _vp), ("mask_r", _vp), ("mask_i", _vp), ("mask_stride_n", _i64),
                 ("mask_stride_f", _i64), ("window", _vp), ("mel_dev", _vp), ("out", _vp), ("stats", _vp),
                 ("grad_out", _vp), ("grad_mask_r", _vp), ("grad_mask_i", _vp), ("grad_wave", _vp),
-                ("workspace", _vp), ("cuda_stream", _vp), ("prof", _vp)]
+                ("workspace", _vp), ("cuda_stream", _vp), ("prof", _vp), ("tables", _vp)]
 
 
 def make_io(**kw) -> IO:
@@ -82,6 +83,10 @@ def load() -> ctypes.CDLL:
         lib.aas_lmfb_plan_info.argtypes = [_vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]
         lib.aas_lmfb_plan_set_tuning.restype = _i32
         lib.aas_lmfb_plan_set_tuning.argtypes = [_vp, _i32, _i32, _i32]
+        lib.aas_lmfb_plan_tables_bytes.restype = ctypes.c_size_t
+        lib.aas_lmfb_plan_tables_bytes.argtypes = [_vp]
+        lib.aas_lmfb_plan_upload.restype = _i32
+        lib.aas_lmfb_plan_upload.argtypes = [_vp, _vp, _vp]
         lib.aas_lmfb_workspace_bytes.restype = ctypes.c_size_t
         lib.aas_lmfb_workspace_bytes.argtypes = [_vp, _i32, _i32, _u32]
         lib.aas_lmfb_forward_ex.restype = _i32

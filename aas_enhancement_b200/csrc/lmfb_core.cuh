@@ -39,6 +39,7 @@
 // (mask -> power -> mel -> log1p), AM_training/train.py:39-42,:199 (320/160/hamming, 161 bins).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 #include "fft_codelets.cuh"
 
 #ifdef __CUDACC__
@@ -142,7 +143,14 @@ constexpr int kTabBytesBwd = (int)((sizeof(BwdSmem) + 15) / 16 * 16);
 template <bool BWD> struct TabOf;
 template <> struct TabOf<false> { typedef FwdTab Param; typedef FwdSmem Smem; };
 template <> struct TabOf<true>  { typedef BwdTab Param; typedef BwdSmem Smem; };
-constexpr int smem_bytes(bool bwd) { return kScratchBytes + (bwd ? kTabBytesBwd : kTabBytesFwd); }
+template <bool BWD> struct TabBytes { static constexpr int value = BWD ? kTabBytesBwd : kTabBytesFwd; };
+// scratch | tables | control block: scheduler answer (16), its barrier (8), the raw buffer's barrier (8),
+// the table copy's barrier (8), pad (8) | raw buffer
+constexpr int kCtlBytes = 48;
+constexpr int kRawBytes_ = (kTile + 1) * 164 * 4;
+constexpr int smem_bytes(bool bwd) { return kScratchBytes + (bwd ? kTabBytesBwd : kTabBytesFwd) + kCtlBytes + kRawBytes_; }
+// the device-resident image of both shared-memory tables (aas_lmfb_plan_upload): forward, then backward
+constexpr int kTabBlobBytes = kTabBytesFwd + kTabBytesBwd;
 
 // phase 3: warp w of W walks the 8-bin groups [p3_g0, p3_g1); the last warp also takes bin 160
 LMFB_CX int p3_per(int W) { return (kGroups + W - 1) / W; }
@@ -207,33 +215,46 @@ static inline void sts_if_noalias(float* p, float v, bool pred) { if (pred) *p =
 #endif
 
 // ---------------------------------------------------------------------------------------
-// Staging: the (32+1)*160 samples a tile needs go STRAIGHT from global memory into the 32 frame
-// columns with 8-byte asynchronous copies (cp.async / LDGSTS): no register round trip, every
-// copy of the tile in flight at once, one exposed memory round trip per tile.  The samples land
-// RAW and in PFA input order; the window is applied by pass 1 when it loads them (the window
-// table lives in the pad column of the scratch, window_fill()).  Lanes run along the
-// packed-sample index of a hop-row, so the global side is a coalesced 256-byte run and the
-// shared side is conflict-free (slot pitch 33).  Hop-row r feeds frame r (first half, r < 32)
-// and frame r-1 (second half, r >= 1).
+// Staging.  The (32+1)*160 samples a tile needs are ONE contiguous, 16-byte aligned run of the
+// waveform.  They land RAW in a buffer of their own, one hop-row (160 samples) per asynchronous
+// bulk copy (cp.async.bulk, the TMA engine: one instruction per 640 bytes issued by one lane, no
+// load/store-unit work, completion on an mbarrier), rows 164 floats apart so that the lanes of
+// pass 1 (lane = frame, i.e. one row apart) spread over the banks.  Because the buffer is free
+// again as soon as pass 1 has moved the tile into the FFT scratch, the NEXT tile's rows are
+// requested right there and fly under pass 2 / phase 3 of the current one: no staging latency is
+// exposed in steady state, and every hop-row is fetched once (the first half of frame r and the
+// second half of frame r-1 are the same row).  History: 8-byte cp.async (LDGSTS) straight into the
+// frame columns, every row twice -- 5,280 load/store-unit elements and 6-8 k exposed cycles per tile.
+// Rows that need the reflect padding (both ends of an utterance), rows past the last frame (zeros)
+// and waves that are not 16-byte aligned take a per-row path with plain loads and stores.
 // ---------------------------------------------------------------------------------------
+constexpr int kRawPitch = 164;                              // floats between hop-rows of the raw buffer
+constexpr int kRawBytes = (kTile + 1) * kRawPitch * 4;      // 21,648 B
+static_assert(kRawBytes == kRawBytes_, "raw buffer size");
+
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async8(unsigned dst, const float* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void bulk_row(float* dst, const float* src, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(kHop * 4), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.wait_all;" ::: "memory");
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 #else
-static inline void cp_async_wait_all() {}
+static inline void bulk_row(float* dst, const float* src, uint64_t*) { for (int i = 0; i < kHop; ++i) dst[i] = src[i]; }
+static inline void mbar_arrive_tx(uint64_t*, unsigned) {}
 #endif
 
-struct StageLane {                      // per-lane constants of the staging map
+struct StageLane {                      // per-lane constants of the slot map (used by the adjoint staging)
     int      slot_a[3], slot_b[3];      // float2 index of (slot * pitch) for packed samples c, c + 80
-    unsigned sa[3], sb[3];              // the same as shared-space byte addresses of column 0 (device only)
 };
 
-LMFB_HD void stage_lane_init(int lane, float2* S, StageLane& sl) {
+LMFB_HD void stage_lane_init(int lane, StageLane& sl) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         const int c = lane + 32 * q;                       // packed index inside a hop-row, < 80 valid
@@ -241,122 +262,113 @@ LMFB_HD void stage_lane_init(int lane, float2* S, StageLane& sl) {
         sl.slot_a[q] = slot_of_packed(cc) * kPitch;
         sl.slot_b[q] = slot_of_packed(cc + 80) * kPitch;
         LMFB_OPAQUE32(sl.slot_a[q]); LMFB_OPAQUE32(sl.slot_b[q]);
-#ifdef __CUDACC__
-        sl.sa[q] = smem_u32(S + sl.slot_a[q]);
-        sl.sb[q] = smem_u32(S + sl.slot_b[q]);
-        LMFB_OPAQUE32(sl.sa[q]); LMFB_OPAQUE32(sl.sb[q]);
-#else
-        sl.sa[q] = sl.sb[q] = 0;
-#endif
     }
-    (void)S;
 }
 
 // window table: pad column (index 32) of slot s holds the window pair of the packed sample that
-// lives in slot s.  Written once per persistent CTA; staging and the passes never touch column 32.
+// lives in slot s.  Written once per persistent CTA; the passes never touch column 32.
 LMFB_HD void window_fill(float2* __restrict__ S, const float* __restrict__ window, int idx, int cnt) {
     for (int j = idx; j < kSlots; j += cnt)
         S[slot_of_packed(j) * kPitch + kTile] = make_float2(LMFB_LDG(window + 2 * j), LMFB_LDG(window + 2 * j + 1));
 }
 
-// hop-row q of the unpadded signal lies fully inside [0, len) and can be copied as 8-byte pieces
+// hop-row q of the unpadded signal lies fully inside [0, len) and can be copied as a whole
 LMFB_HD bool row_interior(int q, int len, bool vec_ok) {
     return vec_ok && q >= 0 && (long long)(q + 1) * kHop <= (long long)len;
 }
 
-LMFB_HD void stage_store(const StageLane& sl, float2* __restrict__ S, int r, int q, float2 v) {
-    if (r < kTile)  S[sl.slot_a[q] + r]     = v;
-    if (r >= 1)     S[sl.slot_b[q] + r - 1] = v;
-}
-
-// one hop-row, any case (warp-uniform branches): rows >= n_rows feed no frame that exists and are
-// zero-filled; rows that need the reflect padding (either end of the utterance) or an unaligned
-// wave take a per-sample path with plain loads
-LMFB_HD void stage_row_any(int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
-                           int t0, int r, int n_rows, float2* __restrict__ S, bool vec_ok) {
-    const int q = t0 + r - 1;                                 // hop-row of the signal
-    float2 v[3];
-    v[0] = v[1] = v[2] = make_float2(0.0f, 0.0f);
-    if (r >= n_rows) {
-        // zero-fill
-    } else if (row_interior(q, len, vec_ok)) {
-        const float2* src = reinterpret_cast<const float2*>(wave_row + (long long)q * kHop) + lane;
-        v[0] = LMFB_LDG(src);
-        v[1] = LMFB_LDG(src + 32);
-        if (lane < 16) v[2] = LMFB_LDG(src + 64);
-    } else {
-        const int base = q * kHop;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {                         // all six loads in flight before the stores
-            const int c = lane + 32 * k;
-            if (c < 80) {
-                v[k].x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
-                v[k].y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
-            }
-        }
-    }
-    stage_store(sl, S, r, 0, v[0]);
-    stage_store(sl, S, r, 1, v[1]);
-    if (lane < 16) stage_store(sl, S, r, 2, v[2]);
-}
-
-// The 33 rows are dealt to the W warps in contiguous shares.  Fast path (every row of the share
-// valid and interior -- all tiles but the first and last of an utterance): straight-line
-// asynchronous copies, every address a register plus an immediate.
+// Warp w requests / fills its share of the tile's 33 hop-rows (rows w, w + W, ...) and then signals
+// the buffer's mbarrier once, with the bytes its bulk copies will deliver.  Plain stores of the
+// per-row path are ordered before the consumer by the block barrier that always lies between this
+// call and the pass 1 that reads the buffer.
 template <int W>
-LMFB_HD void stage_tile(int w, int lane, const StageLane& sl, const float* __restrict__ wave_row, int len,
-                        int t0, int n_rows, float2* __restrict__ S, bool vec_ok) {
-    constexpr int kShare = (kTile + 1 + W - 1) / W;               // rows per warp (the last warp may have fewer)
-    const int r_lo = w * kShare;
-    const int r_hi = r_lo + kShare < kTile + 1 ? r_lo + kShare : kTile + 1;
-#ifdef __CUDACC__
-    if (r_hi <= n_rows && row_interior(t0 + r_lo - 1, len, vec_ok) && row_interior(t0 + r_hi - 2, len, vec_ok)) {
-        const float* src = wave_row + (long long)(t0 + r_lo - 1) * kHop + 2 * lane;
-        LMFB_OPAQUE(src);
-        const unsigned ro = (unsigned)r_lo * 8u;
-        const unsigned a0 = sl.sa[0] + ro, a1 = sl.sa[1] + ro, a2 = sl.sa[2] + ro;
-        const unsigned b0 = sl.sb[0] + ro, b1 = sl.sb[1] + ro, b2 = sl.sb[2] + ro;
+LMFB_HD void stage_raw(int w, int lane, const float* __restrict__ wave_row, int len, int t0, int n_rows,
+                       float* __restrict__ raw, uint64_t* bar, bool vec16) {
+    // fast path (all tiles but the first and last of an utterance): every row is a whole interior hop-row
+    if (vec16 && n_rows == kTile + 1 && t0 >= 1 && (t0 + kTile) * kHop <= len) {       // (t0 < 2^22: no overflow)
+        if (lane == 0) {
+            const float* src = wave_row + (long long)(t0 - 1 + w) * kHop;
+            float* dst = raw + w * kRawPitch;
+            constexpr int kMine = (kTile + 1 + W - 1) / W;    // rows w, w + W, ... (the last may not exist)
 #pragma unroll
-        for (int i = 0; i < kShare; ++i) {
-            const int r = r_lo + i;                               // warp-uniform
-            if (r < r_hi) {
-                if (r < kTile) {
-                    cp_async8(a0 + i * 8, src + i * kHop);
-                    cp_async8(a1 + i * 8, src + i * kHop + 64);
-                    if (lane < 16) cp_async8(a2 + i * 8, src + i * kHop + 128);
-                }
-                if (r >= 1) {
-                    cp_async8(b0 + i * 8 - 8, src + i * kHop);
-                    cp_async8(b1 + i * 8 - 8, src + i * kHop + 64);
-                    if (lane < 16) cp_async8(b2 + i * 8 - 8, src + i * kHop + 128);
-                }
-            }
+            for (int i = 0; i < kMine; ++i)
+                if (w + i * W < kTile + 1) bulk_row(dst + i * W * kRawPitch, src + i * W * kHop, bar);
+            mbar_arrive_tx(bar, (unsigned)(((kTile + 1 - w + W - 1) / W) * kHop * 4));
         }
         return;
     }
-#endif
+    unsigned bytes = 0;
 #pragma unroll 1
-    for (int r = r_lo; r < r_hi; ++r) stage_row_any(lane, sl, wave_row, len, t0, r, n_rows, S, vec_ok);
+    for (int r = w; r < kTile + 1; r += W) {                  // warp-uniform
+        const int q = t0 + r - 1;                             // hop-row of the signal
+        float* dst = raw + r * kRawPitch;
+        if (r < n_rows && row_interior(q, len, vec16)) {
+            if (lane == 0) bulk_row(dst, wave_row + (long long)q * kHop, bar);
+            bytes += kHop * 4;
+        } else {
+            float2 v[3];
+            v[0] = v[1] = v[2] = make_float2(0.0f, 0.0f);         // rows >= n_rows feed no frame that exists
+            if (r < n_rows) {
+                const int base = q * kHop;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {                     // all six loads in flight before the stores
+                    const int c = lane + 32 * k;
+                    if (c < 80) {
+                        v[k].x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
+                        v[k].y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
+                    }
+                }
+            }
+            float2* d2 = reinterpret_cast<float2*>(dst);
+            d2[lane] = v[0];
+            d2[lane + 32] = v[1];
+            if (lane < 16) d2[lane + 64] = v[2];
+        }
+    }
+    if (lane == 0) mbar_arrive_tx(bar, bytes);
 }
 
 // ---------------------------------------------------------------------------------------
-// pass 1: the five in-register 32-point FFTs of a column, dealt round-robin to the W warps
+// pass 1: the five in-register 32-point FFTs of a column, dealt round-robin to the W warps.
+// The inputs come from the raw buffer: frame `lane` is rows lane and lane + 1, packed sample j at
+// float 2j of that 320-sample run; input i of sub-transform n1 is the packed sample whose PFA slot
+// is 32 n1 + i -- a literal offset once n1 is a literal, hence the dispatch over n1 (the loads are
+// the only per-sub-transform code; the codelet and the stores are shared).
 // ---------------------------------------------------------------------------------------
+LMFB_CX int packed_of_slot(int s) {            // inverse of slot_of_packed
+    for (int j = 0; j < kSlots; ++j) if (slot_of_packed(j) == s) return j;
+    return -1;
+}
+LMFB_CX int raw_off_of_packed(int j) { return j < 80 ? 2 * j : kRawPitch + 2 * (j - 80); }
+
+template <int N1>
+LMFB_HD void load_sub_raw(const float* __restrict__ rawl, const float2* __restrict__ win, float (&xr)[32], float (&xi)[32]) {
+    static_for<0, 32>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int off = raw_off_of_packed(packed_of_slot(N1 * 32 + i));
+        const float2 v = *reinterpret_cast<const float2*>(rawl + off);
+        const float2 g = win[(N1 * 32 + i) * kPitch];             // same address for every lane: broadcast
+        xr[i] = v.x * g.x; xi[i] = v.y * g.y;
+    });
+}
+
+//   rawl : raw + lane * kRawPitch;  col : S + lane;  win : S + kTile (the window table)
 template <int W>
-LMFB_HD void fft_pass1(int w, float2* __restrict__ col, const float2* __restrict__ win) {
+LMFB_HD void fft_pass1(int w, const float* __restrict__ rawl, float2* __restrict__ col, const float2* __restrict__ win) {
 #pragma unroll 1
     for (int n1 = w; n1 < 5; n1 += W) {
-        float2* p = col + n1 * 32 * kPitch;
-        const float2* wn = win + n1 * 32 * kPitch;                // same address for every lane: broadcast
         float xr[32], xi[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float2 v = p[i * kPitch], g = wn[i * kPitch];
-            xr[i] = v.x * g.x; xi[i] = v.y * g.y;
+        switch (n1) {
+            case 0:  load_sub_raw<0>(rawl, win, xr, xi); break;
+            case 1:  load_sub_raw<1>(rawl, win, xr, xi); break;
+            case 2:  load_sub_raw<2>(rawl, win, xr, xi); break;
+            case 3:  load_sub_raw<3>(rawl, win, xr, xi); break;
+            default: load_sub_raw<4>(rawl, win, xr, xi); break;
         }
 #ifndef LMFB_DBG_NOFFT
         fft32(xr, xi);
 #endif
+        float2* p = col + n1 * 32 * kPitch;
 #pragma unroll
         for (int i = 0; i < 32; ++i) p[i * kPitch] = make_float2(xr[i], xi[i]);
     }
@@ -440,6 +452,30 @@ LMFB_HD void fill_steps(StepEnt* st, int tid, int nthreads) {
         st[k2].f[k1] = kStepBin[k2][k1]; st[k2].sn[k1] = kStepSin[k2][k1]; st[k2].cs[k1] = kStepCos[k2][k1];
     }
 }
+// host: the same images, built once per plan for aas_lmfb_plan_upload (the kernels then fetch their
+// table with ONE bulk copy instead of ~800 divergent constant-bank reads per CTA, which were measured
+// at 4 us per CTA: a quarter of a one-wave launch)
+inline void fill_steps_host(StepEnt* st) {
+    for (int k2 = 0; k2 < 17; ++k2)
+        for (int k1 = 0; k1 < 5; ++k1) {
+            st[k2].f[k1] = kStepBinHost[k2][k1]; st[k2].sn[k1] = kStepSinHost[k2][k1]; st[k2].cs[k1] = kStepCosHost[k2][k1];
+        }
+}
+inline void tables_image(FwdSmem* sm, const FwdTab& tab) {
+    memset(sm, 0, sizeof(*sm));
+    fill_steps_host(sm->step);
+    memcpy(sm->w, tab.w, sizeof(sm->w));
+    memcpy(sm->hmask, tab.hmask, sizeof(sm->hmask));
+    memcpy(sm->adv, tab.adv, sizeof(sm->adv));
+    memcpy(sm->row, tab.row, sizeof(sm->row));
+}
+inline void tables_image(BwdSmem* sm, const BwdTab& tab) {
+    memset(sm, 0, sizeof(*sm));
+    fill_steps_host(sm->step);
+    memcpy(sm->w, tab.w, sizeof(sm->w));
+    memcpy(sm->d, tab.d, sizeof(sm->d));
+}
+
 LMFB_HD void tables_fill(FwdSmem* sm, const FwdTab& tab, int tid, int nthreads) {
     fill_steps(sm->step, tid, nthreads);
     if (tab.walkable) {
@@ -692,7 +728,13 @@ LMFB_HD void unstage_tile(int w, int lane, const StageLane& sl, float* __restric
 // the caller issues those loads before the block barrier that ends pass 1.
 template <int AHEAD>
 struct MaskSets { StepMasks m[AHEAD + 1]; };
-constexpr int kAheadFwd = 1, kAheadBwd = 1;
+#ifndef LMFB_AHEAD_FWD
+#  define LMFB_AHEAD_FWD 1
+#endif
+#ifndef LMFB_AHEAD_BWD
+#  define LMFB_AHEAD_BWD 1
+#endif
+constexpr int kAheadFwd = LMFB_AHEAD_FWD, kAheadBwd = LMFB_AHEAD_BWD;
 
 template <int W, int MASK, bool BWD, int AHEAD, bool GW, class SM>
 LMFB_HD void preload_masks(int w, const SM& sm, const float* __restrict__ mr, const float* __restrict__ mi,
@@ -770,6 +812,10 @@ LMFB_HD void phase3_walk(int w, float* __restrict__ pl, const FwdSmem& sm, const
     const float* pp = pl + g0 * 8 * kRow;
     const float2* wp = sm.w + g0 * 8;
     if (!tab.multi) {
+        // eight bins at a time: all sixteen loads of a group are in flight before the predicated
+        // hand-over chain starts.  (A piece-by-piece walk with counted loops and no per-bin predicates
+        // was measured: 20 % fewer instructions in this phase, but twice its duration -- short dependent
+        // load -> FMA loops leave a warp nothing to overlap; what a phase costs is its latency.)
 #pragma unroll 1
         for (int g = g0; g < g1; ++g) {
             float p[8]; float2 wg[8];
@@ -792,6 +838,15 @@ LMFB_HD void phase3_walk(int w, float* __restrict__ pl, const FwdSmem& sm, const
 }
 
 template <int W>
+LMFB_HD float finish_sum(const float* __restrict__ pl, const FwdTab& tab, int m) {
+    float e = 0.0f;
+#pragma unroll
+    for (int wi = 0; wi < W; ++wi)
+        if (m >= (int)tab.lo[wi] && m <= (int)tab.hi[wi]) e += pl[e_off(2 * wi) + m * kRow];
+    return e;
+}
+
+template <int W>
 LMFB_HD void phase3_finish(int w, const float* __restrict__ pl, const FwdTab& tab,
                            float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid,
                            bool first = true, bool last = true) {
@@ -799,12 +854,31 @@ LMFB_HD void phase3_finish(int w, const float* __restrict__ pl, const FwdTab& ta
     const int per = (n_mels + W - 1) / W;
     const int m_lo = w * per, m_hi = m_lo + per < n_mels ? m_lo + per : n_mels;
     float* op = at_row(out, (uint32_t)m_lo, som_bytes);
-#pragma unroll 2
-    for (int m = m_lo; m < m_hi; ++m) {
-        float e = 0.0f;
+    if (first && last) {
+        // single channel (the common case): four filters in flight -- the log1p chains are what this
+        // phase waits for
+        int m = m_lo;
+#pragma unroll 1
+        for (; m + 4 <= m_hi; m += 4) {
+            float e[4];
 #pragma unroll
-        for (int wi = 0; wi < W; ++wi)
-            if (m >= (int)tab.lo[wi] && m <= (int)tab.hi[wi]) e += pl[e_off(2 * wi) + m * kRow];
+            for (int i = 0; i < 4; ++i) e[i] = finish_sum<W>(pl, tab, m + i);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e[i] = valid ? log1pf(e[i]) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { st_if(op, e[i], inrow); op = at_row(op, 1u, som_bytes); }
+        }
+#pragma unroll 1
+        for (; m < m_hi; ++m) {
+            const float e = finish_sum<W>(pl, tab, m);
+            st_if(op, valid ? log1pf(e) : 0.0f, inrow);
+            op = at_row(op, 1u, som_bytes);
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int m = m_lo; m < m_hi; ++m) {
+        float e = finish_sum<W>(pl, tab, m);
         if (!first) e += inrow ? *op : 0.0f;                 // multi-channel: partial sums of E travel through `out`
         const float y = last ? (valid ? log1pf(e) : 0.0f) : e;
         st_if(op, y, inrow);

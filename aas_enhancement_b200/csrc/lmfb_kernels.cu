@@ -27,6 +27,28 @@
 
 namespace aas_lmfb {
 
+// division of a non-negative int < 2^31 by a fixed positive divisor as one multiply-high and a shift
+// (the tile decode runs in every warp of every tile: two signed divisions were ~60 instructions)
+struct FastDiv {
+    unsigned m; int s;                      // s < 0: the divisor is 1
+    __host__ __device__ int div(int n) const {
+#ifdef __CUDA_ARCH__
+        return s < 0 ? n : (int)(__umulhi((unsigned)n, m) >> s);
+#else
+        return s < 0 ? n : (int)(((unsigned long long)(unsigned)n * m) >> (32 + s));
+#endif
+    }
+};
+static inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    if (d <= 1) { f.m = 0; f.s = -1; return f; }
+    int c = 0;                              // c = ceil(log2 d)
+    while ((1LL << c) < d) ++c;
+    f.s = c - 1;
+    f.m = (unsigned)((((unsigned long long)1 << (32 + f.s)) + (unsigned)d - 1) / (unsigned)d);
+    return f;
+}
+
 struct K1Args {
     const float*   wave;
     const int32_t* lengths;
@@ -51,6 +73,8 @@ struct K1Args {
     int            n_ch;       // channels per utterance (model.py:167: the basis repeats over channels, i.e. power sums)
     long long      wave_stride_ch;   // samples between the channels of an utterance
     long long      wave_len;   // samples of a row that may be read (lengths are clamped to it); 0: trust lengths
+    const void*    tab_dev;    // device image of the shared-memory table (aas_lmfb_plan_upload), or NULL: fill from the parameter
+    FastDiv        div_tpu, div_nch;   // / tiles_per_utt, / n_ch
 };
 
 
@@ -100,6 +124,30 @@ __device__ __forceinline__ bool clc_answer(const uint4* resp, int& ctaid_x) {
     return ok != 0;
 }
 
+// where a (tile, channel) unit lives: decoded once, used by the staging request and by the passes
+struct Unit {
+    int tile, ch;          // tile index of the launch, channel inside the utterance
+    int n, t0, len, T;     // utterance, first frame, samples, frames
+    bool real;             // false: the tile lies entirely in the zero padding (nothing to stage)
+};
+
+template <bool BWD>
+__device__ __forceinline__ void decode_unit(const K1Args& a, int tile, int ch_fwd, Unit& u) {
+    // forward: a tile belongs to an utterance and loops over its channels (the power sums);
+    // backward: every (utterance, channel) has tiles of its own (they share only dE)
+    const int nn = a.div_tpu.div(tile);
+    u.tile = tile;
+    u.t0 = (tile - nn * a.tiles_per_utt) * kTile;
+    u.n  = BWD ? a.div_nch.div(nn) : nn;
+    u.ch = BWD ? nn - u.n * a.n_ch : ch_fwd;
+    int len = a.lengths[u.n];
+    if (a.wave_len > 0 && (long long)len > a.wave_len) len = (int)a.wave_len;
+    u.len = len;
+    int T = len >= 1 ? 1 + len / kHop : 0;
+    u.T = T < a.tmax ? T : a.tmax;
+    u.real = u.t0 < u.T;
+}
+
 template <int MASK, bool BWD, int W, int CTAS, bool GW = false>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf<BWD>::Param tab) {
@@ -109,6 +157,13 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
     constexpr int AHEAD = BWD ? kAheadBwd : kAheadFwd;
     extern __shared__ __align__(16) float2 S[];
     SM& sm = *reinterpret_cast<SM*>(reinterpret_cast<char*>(S) + kScratchBytes);
+    // behind the tables: the answer of the launch-control unit, its barrier, the raw buffer's barrier,
+    // and the raw buffer itself
+    uint4*    clc_resp = reinterpret_cast<uint4*>(reinterpret_cast<char*>(&sm) + TabBytes<BWD>::value);
+    uint64_t* clc_bar  = reinterpret_cast<uint64_t*>(clc_resp + 1);
+    uint64_t* raw_bar  = clc_bar + 1;
+    uint64_t* tab_bar  = clc_bar + 2;
+    float*    raw      = reinterpret_cast<float*>(reinterpret_cast<char*>(clc_resp) + kCtlBytes);
 #ifdef LMFB_TIMELINE
     unsigned long long gt_entry;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_entry));
@@ -116,84 +171,49 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
     const int lane = threadIdx.x & 31;
     const int w    = threadIdx.x >> 5;
     const int n_mels = tab.n_mels;
-    StageLane sl;
-    stage_lane_init(lane, S, sl);
-    bool filled = false;                                       // tables: filled under the first tile's staging copies
     float2* col = S + lane;
     float*  pl  = reinterpret_cast<float*>(S) + lane;
+    const float* rawl = raw + lane * kRawPitch;
     const unsigned msf_bytes = a.msf * 4u;
     const unsigned som = (unsigned)a.tmax, som_bytes = som * 4u;
+    const int nch_fwd = BWD ? 1 : a.n_ch;                      // channel units per forward tile
+    unsigned clc_phase = 0, raw_phase = 0;
 
+    if (threadIdx.x == 0) {
+        mbar_init(clc_bar, 1);
+        mbar_init(raw_bar, W);                                 // one arrival per warp and staged unit
+        mbar_init(tab_bar, 1);
+        if (a.tab_dev) {                                       // the table image: one bulk copy
+            mbar_arrive_tx(tab_bar, (unsigned)TabBytes<BWD>::value);
+            bulk_copy(&sm, a.tab_dev, (unsigned)TabBytes<BWD>::value, tab_bar);
+        }
+    }
+    __syncthreads();
+
+    // request the rows of a unit (no-op for a padding tile)
+    auto stage = [&](const Unit& u) {
+        if (!u.real) return;
+        const float* wave_row = a.wave + (long long)u.n * a.wave_stride + (long long)u.ch * a.wave_stride_ch;
+        const int n_rows = (u.T - u.t0 < kTile ? u.T - u.t0 : kTile) + 1;      // hop-rows that feed a valid frame
+        stage_raw<W>(w, lane, wave_row, u.len, u.t0, n_rows, raw, raw_bar, a.vec_ok != 0);
+    };
+
+    int cur_tile = (int)blockIdx.x, cur_ch = 0;              // only these two cross the passes; a unit is decoded where it is used
+    if (cur_tile < a.total_tiles) {
+        Unit first;
+        decode_unit<BWD>(a, cur_tile, 0, first);
+        stage(first);
+    }
+    // the per-CTA tables, under the first unit's copies
+    window_fill(S, a.window, threadIdx.x, kTile * W);          // pad column of the scratch <- window table
+    if (a.tab_dev) mbar_wait(tab_bar, 0);
+    else tables_fill(&sm, tab, threadIdx.x, kTile * W);
+    __syncthreads();
 #ifdef LMFB_TIMELINE
     unsigned long long gt_loop;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_loop));
     int n_done = 0;
-#endif
-    // scheduler state behind the tables: the answer of the launch-control unit and its barrier
-    uint4*    clc_resp = reinterpret_cast<uint4*>(reinterpret_cast<char*>(&sm) + sizeof(SM));
-    uint64_t* clc_bar  = reinterpret_cast<uint64_t*>(clc_resp + 1);
-    unsigned  clc_phase = 0;
-    if (a.dynamic) {
-        if (threadIdx.x == 0) mbar_init(clc_bar, 1);
-        __syncthreads();
-    }
-    // persistent CTA.  dynamic: the next tile is whichever pending CTA the hardware cancels for us
-    // (asked for at the start of a tile, read at its end); static: round-robin over the grid.
-    // Either way neighbouring tiles run at the same time, so the sectors they share hit L2.
-    for (int tile = blockIdx.x; tile < a.total_tiles; ) {
-      if (a.dynamic && threadIdx.x == 0) clc_request(clc_resp, clc_bar);
-      do {
-        // forward: a tile belongs to an utterance and loops over its channels (the power sums);
-        // backward: every (utterance, channel) has tiles of its own (they share only dE)
-        const int nn  = tile / a.tiles_per_utt;
-        const int t0  = (tile - nn * a.tiles_per_utt) * kTile;
-        const int n   = BWD ? nn / a.n_ch : nn;
-        const int ch0 = BWD ? nn - n * a.n_ch : 0;
-        const int nch = BWD ? 1 : a.n_ch;
-        const int t   = t0 + lane;
-        int len = a.lengths[n];
-        if (a.wave_len > 0 && (long long)len > a.wave_len) len = (int)a.wave_len;
-        int T = len >= 1 ? 1 + len / kHop : 0;
-        T = T < a.tmax ? T : a.tmax;
-        const bool inrow = t < a.tmax;
-        const bool valid = t < T;
-        const long long row_nm = (long long)n * n_mels * som + t;
-        const long long moff0 = (long long)n * a.msn + (long long)ch0 * kBins * a.msf + t;
-
-        if (t0 >= T) {                              // tile lies entirely in the zero padding
-            if (inrow) {
-                if (!BWD) {
-#pragma unroll 4
-                    for (int m = w; m < n_mels; m += W) a.out[row_nm + (unsigned)m * som] = 0.0f;
-                } else if (MASK != kMaskNone) {
-#pragma unroll 4
-                    for (int f = w; f < kBins; f += W) {
-                        a.gr[moff0 + (unsigned)f * a.msf] = 0.0f;
-                        if (MASK == kMaskReim || MASK == kStftOut) a.gi[moff0 + (unsigned)f * a.msf] = 0.0f;
-                    }
-                }
-            }
-            break;
-        }
-
-#ifdef LMFB_TIMELINE
-      long long tl[8];
-#endif
-      for (int ch = ch0; ch < ch0 + nch; ++ch) {
-        const long long moff = moff0 + (BWD ? 0 : (long long)ch * kBins * a.msf);
-        const float* wave_row = a.wave + (long long)n * a.wave_stride + (long long)ch * a.wave_stride_ch;
-        if (!BWD && ch > ch0) __syncthreads();      // the previous channel's gather has read the scratch
-
-#ifndef LMFB_DBG_NOPREFETCH
-        // pull this tile's mask rows (and dE rows) towards L2 while the FFT runs ...
-        if (LMFB_NEEDS_MASK_R(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (moff - t), a.msf, kBins, t0, a.tmax);
-        if (LMFB_NEEDS_MASK_I(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (moff - t), a.msf, kBins, t0, a.tmax);
-        if (BWD && MASK != kStftOut) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)n * n_mels * som, som, n_mels, t0, a.tmax);
-        // (prefetching the NEXT tile's samples was measured and dropped: in the backward kernel the
-        // lines are evicted before use and the wave is read from DRAM twice, 707 -> 578 MB per launch)
-#endif
-
-#ifdef LMFB_TIMELINE
+    long long tl[8];
 // after a barrier the clock is only meaningful once something protected by the barrier has been
 // touched (BAR.SYNC is deferred-blocking): read a shared word first
 #define LMFB_TICK(i) do { volatile float* vs_ = reinterpret_cast<volatile float*>(S); float x_ = vs_[lane]; \
@@ -201,21 +221,60 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
 #else
 #define LMFB_TICK(i) ((void)0)
 #endif
+
+    // persistent CTA over (tile, channel) units.  dynamic: the next tile is whichever pending CTA the
+    // hardware cancels for us (asked for when a tile starts, read after its pass 1); static:
+    // round-robin over the grid.  Either way neighbouring tiles run at the same time, so the sectors
+    // they share hit L2.
+    while (cur_tile < a.total_tiles) {
+        Unit cur;
+        decode_unit<BWD>(a, cur_tile, cur_ch, cur);
+        if (a.dynamic && (BWD || cur_ch == 0) && threadIdx.x == 0) clc_request(clc_resp, clc_bar);
+        const int t = cur.t0 + lane;
+        const bool inrow = t < a.tmax;
+        const bool valid = t < cur.T;
+        const long long row_nm = (long long)cur.n * n_mels * som + t;
+        const long long moff = (long long)cur.n * a.msn + (long long)cur.ch * kBins * a.msf + t;
+        const bool last_ch = BWD || cur.ch + 1 == nch_fwd;
+        Unit nxt;
+
+        if (!cur.real) {                            // tile lies entirely in the zero padding
+            if (inrow) {
+                if (!BWD) {
+#pragma unroll 4
+                    for (int m = w; m < n_mels; m += W) a.out[row_nm + (unsigned)m * som] = 0.0f;
+                } else if (MASK != kMaskNone) {
+#pragma unroll 4
+                    for (int f = w; f < kBins; f += W) {
+                        a.gr[moff + (unsigned)f * a.msf] = 0.0f;
+                        if (MASK == kMaskReim || MASK == kStftOut) a.gi[moff + (unsigned)f * a.msf] = 0.0f;
+                    }
+                }
+            }
+            int next_tile;
+            if (a.dynamic) {
+                mbar_wait(clc_bar, clc_phase);
+                clc_phase ^= 1u;
+                int x;
+                next_tile = clc_answer(clc_resp, x) ? x : a.total_tiles;
+            } else {
+                next_tile = cur.tile + (int)gridDim.x;
+            }
+            if (next_tile < a.total_tiles) { decode_unit<BWD>(a, next_tile, 0, nxt); stage(nxt); }
+            cur_tile = next_tile; cur_ch = 0;
+            __syncthreads();                        // (the scheduler's answer is free for the next request)
+            continue;
+        }
+
+#ifndef LMFB_DBG_NOPREFETCH
+        // pull this unit's mask rows (and dE rows) towards L2 while the FFT runs ...
+        if (LMFB_NEEDS_MASK_R(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + (moff - t), a.msf, kBins, cur.t0, a.tmax);
+        if (LMFB_NEEDS_MASK_I(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + (moff - t), a.msf, kBins, cur.t0, a.tmax);
+        if (BWD && MASK != kStftOut) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)cur.n * n_mels * som, som, n_mels, cur.t0, a.tmax);
+#endif
         LMFB_TICK(0);
         // loads of out-of-row lanes are redirected to the last column of the row (always readable)
         const long long clamp = inrow ? 0 : (long long)(a.tmax - 1 - t);
-        const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;          // hop-rows that feed a valid frame
-        stage_tile<W>(w, lane, sl, wave_row, len, t0, n_rows, S, a.vec_ok != 0);
-        if (!filled) {                              // once per CTA, while the staging copies are in flight
-            window_fill(S, a.window, threadIdx.x, kTile * W);      // pad column of the scratch <- window table
-            tables_fill(&sm, tab, threadIdx.x, kTile * W);         // both visible after the barrier below
-            filled = true;
-        }
-        LMFB_TICK(1);
-        cp_async_wait_all();
-        __syncthreads();
-        LMFB_TICK(2);
-        fft_pass1<W>(w, col, S + kTile);
         const float* mr = a.mask_r + moff + clamp;
         const float* mi = a.mask_i + moff + clamp;
         const float* de = a.dE + row_nm + clamp;
@@ -223,6 +282,12 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         float* gi = a.gi + moff;
         float* po = a.out + row_nm;
         LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
+
+        mbar_wait(raw_bar, raw_phase);              // this unit's rows have landed
+        raw_phase ^= 1u;
+        LMFB_TICK(1);
+        LMFB_TICK(2);
+        fft_pass1<W>(w, rawl, col, S + kTile);
         MaskSets<AHEAD> ms;                         // issued before the barrier: the latency hides behind it
         preload_masks<W, MASK, BWD, AHEAD, GW>(w, sm, mr, mi, msf_bytes, ms);
         if constexpr (MASK == kStftOut) {           // no masks: the slot carries the output scale
@@ -230,14 +295,37 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
             for (int i = 0; i <= AHEAD; ++i) ms.m[i].vr[0] = valid ? 0.5f : 0.0f;
         }
         LMFB_TICK(3);
-        __syncthreads();
+        __syncthreads();                            // the scratch is complete, the raw buffer is free
         LMFB_TICK(4);
+
+        // which unit comes next, and its rows: they fly under pass 2 / phase 3 of this one
+        int next_tile = cur_tile, next_ch = cur_ch + 1;
+        if (!last_ch) {
+            nxt = cur; nxt.ch = next_ch;
+            stage(nxt);
+        } else {
+            if (a.dynamic) {
+                mbar_wait(clc_bar, clc_phase);
+                clc_phase ^= 1u;
+                int x;
+                next_tile = clc_answer(clc_resp, x) ? x : a.total_tiles;
+            } else {
+                next_tile = cur_tile + (int)gridDim.x;
+            }
+            next_ch = 0;
+            if (next_tile < a.total_tiles) { decode_unit<BWD>(a, next_tile, 0, nxt); stage(nxt); }
+        }
+
         fft_pass2<W, MASK, BWD, AHEAD, GW>(w, col, pl, sm, ms, mr, mi, de, som_bytes, msf_bytes, gr, gi, inrow);
         if constexpr (BWD && GW) {                  // gradient into the waveform: adjoint pass 1, overlap-add
+            StageLane sl;
+            stage_lane_init(lane, sl);
+            const long long woff = (long long)cur.n * a.wave_stride + (long long)cur.ch * a.wave_stride_ch;
+            const int n_rows = (cur.T - cur.t0 < kTile ? cur.T - cur.t0 : kTile) + 1;
             __syncthreads();
             fft_pass1_adj<W>(w, col, S + kTile);
             __syncthreads();
-            unstage_tile<W>(w, lane, sl, a.gwave + (wave_row - a.wave), len, t0, n_rows, S, a.vec_ok != 0);
+            unstage_tile<W>(w, lane, sl, a.gwave + woff, cur.len, cur.t0, n_rows, S, (a.vec_ok & 2) != 0);
         }
         LMFB_TICK(5);
         if constexpr (!BWD) {
@@ -247,35 +335,24 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
                 phase3_walk<W>(w, pl, sm, tab);
                 __syncthreads();
                 LMFB_TICK(5);                   // (overwrites the pass-2 end stamp: phase 3 split A | B)
-                phase3_finish<W>(w, pl, tab, po, som_bytes, inrow, valid, ch == ch0, ch + 1 == ch0 + nch);
+                phase3_finish<W>(w, pl, tab, po, som_bytes, inrow, valid, cur.ch == 0, last_ch);
             } else {
-                phase3_gather<W>(w, pl, sm, n_mels, a.mel, po, som_bytes, inrow, valid, ch == ch0, ch + 1 == ch0 + nch);
+                phase3_gather<W>(w, pl, sm, n_mels, a.mel, po, som_bytes, inrow, valid, cur.ch == 0, last_ch);
             }
         }
 #ifdef LMFB_TIMELINE
         else tl[6] = tl[5];
 #endif
         LMFB_TICK(7);
-      }   // channels
 #ifdef LMFB_TIMELINE
         if (a.timeline && lane == 0 && blockIdx.x < 64 && n_done < 8) {
             long long* dst = a.timeline + ((long long)n_done * 64 + blockIdx.x) * (W * 8) + w * 8;
             for (int i = 0; i < 8; ++i) dst[i] = tl[i];
         }
+        ++n_done;
 #endif
-      } while (false);
-      if (a.dynamic) {
-          mbar_wait(clc_bar, clc_phase);
-          clc_phase ^= 1u;
-          int next;
-          tile = clc_answer(clc_resp, next) ? next : a.total_tiles;
-      } else {
-          tile += gridDim.x;
-      }
-#ifdef LMFB_TIMELINE
-      ++n_done;
-#endif
-      __syncthreads();                              // the scratch (and the scheduler's answer) is free for the next tile
+        cur_tile = next_tile; cur_ch = next_ch;
+        __syncthreads();                            // the scratch (and the scheduler's answer) is free for the next unit
     }
 #ifdef LMFB_TIMELINE
     // second view: every CTA's life, stamped with the global nanosecond timer
@@ -606,23 +683,17 @@ struct K1Variant { int warps, ctas; k1_fwd_fn fwd[3]; k1_bwd_fn bwd[4]; k1_bwd_f
       { lmfb_k1<kMaskNone, true, W, C, true>, lmfb_k1<kMaskReim, true, W, C, true>,        \
         lmfb_k1<kMaskPower, true, W, C, true> } }
 
-// (warps per tile, resident CTAs per SM the register budget is sized for)
+// (warps per tile, resident CTAs per SM the register budget is sized for).  Shared memory (scratch 42 KB
+// + raw buffer 21 KB + tables 3 KB) allows three tiles per SM; five warps per tile give every warp one
+// of the five sub-transforms of pass 1.
 static const K1Variant kVariants[] = {
-#ifdef LMFB_ONLY_W3
-    LMFB_VARIANT(3, 5),
+#ifdef LMFB_ONLY_W5
+    LMFB_VARIANT(5, 3),
 #else
-    LMFB_VARIANT(3, 5), LMFB_VARIANT(2, 5), LMFB_VARIANT(4, 4), LMFB_VARIANT(5, 3),
+    LMFB_VARIANT(5, 3), LMFB_VARIANT(4, 3), LMFB_VARIANT(6, 3),
 #endif
 };
-// Defaults measured on B200 (profiles/): forward 3 warps per tile (5 CTAs, 15 warps per SM), backward
-// 4 warps per tile (4 CTAs, 16 warps per SM: the 45 KB of shared memory it leaves unused become L1,
-// where the tile's dE rows, re-read 8 times, then stay).  Staging those rows in shared memory
-// explicitly was measured and is slower (253 vs 237 us on 256 x 10 s).
-#ifdef LMFB_ONLY_W3
 constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 0, kBwdVariantBig = 0, kBwdVariantSmall = 0;
-#else
-constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 2, kBwdVariantBig = 2, kBwdVariantSmall = 2;   // small: one wave of 4-warp CTAs
-#endif
 
 static int variant_of_warps(int warps) {
     for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
@@ -636,6 +707,7 @@ struct aas_lmfb_plan {
     int     ml[kBins];      // lower filter of every bin (walkable bases)
     int     n_mels;
     int     banded;         // backward fast path
+    alignas(16) unsigned char blob[kTabBlobBytes];   // device image of both shared-memory tables (aas_lmfb_plan_upload)
     int     vfwd, vbwd;     // forced kernel variants (-1: choose by problem size at launch)
     int     static_sched;   // deal tiles round-robin instead of cluster launch control
 };
@@ -671,6 +743,8 @@ extern "C" aas_lmfb_plan* aas_lmfb_plan_create(const float* mel, int n_mels, int
         build_fwd_tab(mel, n_mels, &p->fwd, p->ml);
         p->banded = build_bwd_tab(mel, n_mels, &p->bwd) == 0 ? 1 : 0;
         if (!p->banded) build_bwd_tab_identity(&p->bwd);
+        tables_image(reinterpret_cast<FwdSmem*>(p->blob), p->fwd);
+        tables_image(reinterpret_cast<BwdSmem*>(p->blob + kTabBytesFwd), p->bwd);
     } while (0);
     if (status) *status = st;
     return p;
@@ -692,6 +766,14 @@ extern "C" int aas_lmfb_plan_set_tuning(aas_lmfb_plan* plan, int warps_fwd, int 
     if ((warps_fwd && vf < 0) || (warps_bwd && vb < 0)) return AAS_LMFB_E_FLAGS;
     plan->vfwd = vf; plan->vbwd = vb; plan->static_sched = static_schedule ? 1 : 0;
     return AAS_LMFB_OK;
+}
+
+extern "C" size_t aas_lmfb_plan_tables_bytes(const aas_lmfb_plan* plan) { return plan ? (size_t)kTabBlobBytes : 0; }
+
+extern "C" int aas_lmfb_plan_upload(const aas_lmfb_plan* plan, void* tables_dev, void* cuda_stream) {
+    if (!plan || !tables_dev) return AAS_LMFB_E_NULL;
+    if ((uintptr_t)tables_dev & 15u) return AAS_LMFB_E_ALIGN;
+    return (int)cudaMemcpyAsync(tables_dev, plan->blob, kTabBlobBytes, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream);
 }
 
 static size_t round16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -743,7 +825,7 @@ template <class Fn, class Tab>
 int launch_k1(const aas_lmfb_plan* plan, const K1Variant& v, Fn fn, K1Args& a, const Tab& tab, bool bwd,
               long long units, cudaStream_t stream) {
     if (!fn) return AAS_LMFB_E_FLAGS;
-    const int smem = smem_bytes(bwd) + 32;                         // + the scheduler's answer and barrier
+    const int smem = smem_bytes(bwd);
     const int rc = ensure_attrs((const void*)fn, smem);
     if (rc) return rc;
     const long long total = units * a.tiles_per_utt;               // units: utterances (forward) or utterance-channels
@@ -777,7 +859,7 @@ int check_common(const aas_lmfb_plan* plan, const aas_lmfb_io* io) {
     if (mask != AAS_LMFB_MASK_NONE && (io->mask_stride_f < io->tmax || io->mask_stride_f > (1 << 22))) return AAS_LMFB_E_SHAPE;
     const uintptr_t al = (uintptr_t)io->wave | (uintptr_t)io->mask_r | (uintptr_t)io->mask_i | (uintptr_t)io->window |
                          (uintptr_t)io->mel_dev;
-    if (al & 3u) return AAS_LMFB_E_ALIGN;
+    if ((al & 3u) || ((uintptr_t)io->tables & 15u)) return AAS_LMFB_E_ALIGN;
     return AAS_LMFB_OK;
 }
 
@@ -787,9 +869,13 @@ void fill_args(K1Args& a, const aas_lmfb_io* io) {
     a.wave_stride_ch = io->wave_stride_ch; a.wave_len = io->wave_len; a.n_ch = io->n_ch;
     a.mask_r = io->mask_r; a.mask_i = io->mask_i; a.msn = io->mask_stride_n; a.msf = (unsigned)io->mask_stride_f;
     a.window = io->window; a.tmax = io->tmax; a.mel = io->mel_dev;
+    a.tab_dev = nullptr;
     a.tiles_per_utt = (io->tmax + kTile - 1) / kTile;
-    // 8-byte asynchronous copies need every row start 8-byte aligned
-    a.vec_ok = (((uintptr_t)io->wave & 7u) == 0 && (io->wave_stride & 1) == 0 && (io->wave_stride_ch & 1) == 0) ? 1 : 0;
+    a.div_tpu = make_fastdiv(a.tiles_per_utt);
+    a.div_nch = make_fastdiv(io->n_ch);
+    // bit 0: every row start is 16-byte aligned (bulk copies); bit 1: 8-byte aligned (vector atomics of the adjoint staging)
+    a.vec_ok = ((((uintptr_t)io->wave & 15u) == 0 && (io->wave_stride & 3) == 0 && (io->wave_stride_ch & 3) == 0) ? 1 : 0) |
+               ((((uintptr_t)io->wave & 7u) == 0 && (io->wave_stride & 1) == 0 && (io->wave_stride_ch & 1) == 0) ? 2 : 0);
 }
 
 void rec(void* const* prof, int i, cudaStream_t s) {
@@ -816,10 +902,11 @@ extern "C" int aas_lmfb_forward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io*
     K1Args a;
     fill_args(a, io);
     a.out = out;
+    a.tab_dev = io->tables;
 #ifdef LMFB_TIMELINE
     { const char* e = getenv("AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
 #endif
-    const bool small = (long long)n * a.tiles_per_utt <= 148LL * 4;      // fits one wave at 4 CTAs per SM
+    const bool small = (long long)n * a.tiles_per_utt <= 148LL * 3;      // fits one wave
     const K1Variant& v = kVariants[plan->vfwd >= 0 ? plan->vfwd : (small ? kFwdVariantSmall : kFwdVariantBig)];
     FwdTab band = plan->fwd;
     set_warp_ranges(&band, plan->ml, v.warps);
@@ -905,11 +992,12 @@ extern "C" int aas_lmfb_backward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io
     K1Args a;
     fill_args(a, io);
     a.dE = dE; a.gr = io->grad_mask_r; a.gi = io->grad_mask_i;
+    a.tab_dev = io->tables ? (const char*)io->tables + kTabBytesFwd : nullptr;
 #ifdef LMFB_TIMELINE
     { const char* e = getenv("AAS_LMFB_TIMELINE_BWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
 #endif
     const long long units = (long long)n * io->n_ch;
-    const bool small = units * a.tiles_per_utt <= 148LL * 4;      // fits one wave at 4 CTAs per SM
+    const bool small = units * a.tiles_per_utt <= 148LL * 3;      // fits one wave
     const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
     if (mask == AAS_LMFB_MASK_NONE) { a.mask_r = a.mask_i = io->wave; a.gr = a.gi = nullptr; a.msf = (unsigned)tmax; a.msn = 0; }   // never dereferenced
     a.gwave = grad_wave;
@@ -1012,7 +1100,7 @@ extern "C" int aas_lmfb_stft(const aas_lmfb_plan* plan,
     a.mask_r = a.mask_i = out;                                    // never read (clamped pointer arithmetic only)
     a.msn = out_stride_n; a.msf = (unsigned)tmax;
     a.dE = out; a.gr = out; a.gi = out + (long long)kBins * tmax;
-    const bool small = (long long)n * a.tiles_per_utt <= 148LL * 4;      // fits one wave at 4 CTAs per SM
+    const bool small = (long long)n * a.tiles_per_utt <= 148LL * 3;      // fits one wave
     const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
     return launch_k1(plan, v, v.bwd[3], a, plan->bwd, true, n, (cudaStream_t)cuda_stream);
 }

@@ -76,12 +76,28 @@ class MelPlan:
         status = ctypes.c_int(0)
         self._lib = lib
         self.mel = mel
+        self._tables = {}
         self.n_mels = int(mel.shape[0])
         self.handle = lib.aas_lmfb_plan_create(mel.ctypes.data, mel.shape[0], mel.shape[1],
                                                ctypes.byref(status))
         if not self.handle:
             _lib.check(status.value)
             raise RuntimeError("aas_lmfb_plan_create failed")
+
+    def tables(self, device):
+        """Device-resident lookup tables of this plan on ``device`` (uploaded on first use; the
+        kernels fetch them with one bulk copy per thread block).  Returns the device pointer."""
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        t = self._tables.get(key)
+        if t is None:
+            nbytes = self._lib.aas_lmfb_plan_tables_bytes(self.handle)
+            t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                _lib.check(self._lib.aas_lmfb_plan_upload(self.handle, t.data_ptr(),
+                                                          torch.cuda.current_stream(device).cuda_stream))
+                torch.cuda.current_stream(device).synchronize()     # pageable host source: do not race the plan's lifetime
+            self._tables[key] = t
+        return t.data_ptr()
 
     def __reduce__(self):
         return (MelPlan, (self.mel,))
@@ -188,7 +204,7 @@ class LMFB(torch.autograd.Function):
                           wave_stride_ch=wave.stride(1) if wave.dim() == 3 else 0, wave_len=lmax,
                           lengths=lengths.data_ptr(), mask_r=_ptr(mask_r), mask_i=_ptr(mask_i),
                           mask_stride_n=msn, mask_stride_f=msf, window=window.data_ptr(), mel_dev=_ptr(mel_dev),
-                          out=out.data_ptr(), stats=stats.data_ptr(),
+                          out=out.data_ptr(), stats=stats.data_ptr(), tables=plan.tables(dev),
                           cuda_stream=torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(lib.aas_lmfb_forward_ex(plan.handle, ctypes.byref(io)))
         frame_lens = torch.clamp(1 + torch.div(torch.clamp(lengths, max=lmax), HOP, rounding_mode="floor"), max=tmax)
@@ -237,7 +253,7 @@ class LMFB(torch.autograd.Function):
                           mask_stride_n=msn, mask_stride_f=msf, window=window.data_ptr(), mel_dev=_ptr(mel_dev),
                           out=out.data_ptr(), stats=stats.data_ptr(), grad_out=grad_out.data_ptr(),
                           grad_mask_r=_ptr(gr), grad_mask_i=_ptr(gi), grad_wave=_ptr(gw), workspace=ws.data_ptr(),
-                          cuda_stream=torch.cuda.current_stream(dev).cuda_stream)
+                          tables=plan.tables(dev), cuda_stream=torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(lib.aas_lmfb_backward_ex(plan.handle, ctypes.byref(io)))
         return gw, None, gr, gi, None, None, None, None, None, None, None
 

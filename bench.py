@@ -229,35 +229,40 @@ class Runner:
         gen.manual_seed(seed)                       # config.py:62 default seed (+ rank)
         self.slots = [Slot(self.n, self.samples, self.tmax, self.n_mels, gen, dev, self.paired, row_pad)
                       for _ in range(self.ring)]
+        self.tables = None if os.environ.get("AAS_BENCH_NO_TABLES") else fe.plan.tables(dev)   # (env: A/B of the table upload)
         self.step_bytes = B_FWD + B_BWD + (B_FWD_CLEAN if self.paired else 0)
         self.launches_per_step = None               # counted from the first profiled step (see count_launches)
 
-    def fwd(self, s, prof=None):
+    def _io(self, s, flags, wave, masked, out, stats, prof, backward=False):
+        import ctypes
         st = torch.cuda.current_stream().cuda_stream
-        fe, lib = self.fe, self.lib
-        self._lib.check(lib.aas_lmfb_forward(fe.plan.handle, s.wave.data_ptr(), s.lengths.data_ptr(), self.n,
-                                             s.wave.stride(0), s.mr.data_ptr(), s.mi.data_ptr(),
-                                             s.mr.stride(0), s.mr.stride(1), fe.window.data_ptr(),
-                                             s.out.data_ptr(), s.stats.data_ptr(), self.tmax, self.flags,
-                                             0.0, st, prof))
+        kw = dict(flags=flags, n=self.n, n_ch=1, tmax=self.tmax, eps=0.0, wave=wave.data_ptr(),
+                  wave_stride=wave.stride(0), wave_len=wave.shape[1], lengths=s.lengths.data_ptr(),
+                  window=self.fe.window.data_ptr(), mel_dev=self.fe.mel_basis.data_ptr(),
+                  out=out.data_ptr(), stats=stats.data_ptr(), tables=self.tables, cuda_stream=st,
+                  prof=ctypes.cast(prof, ctypes.c_void_p) if prof is not None else None)
+        if masked:
+            kw.update(mask_r=s.mr.data_ptr(), mask_i=s.mi.data_ptr(), mask_stride_n=s.mr.stride(0),
+                      mask_stride_f=s.mr.stride(1))
+        if backward:
+            kw.update(grad_out=s.gout.data_ptr(), grad_mask_r=s.gr.data_ptr(), grad_mask_i=s.gi.data_ptr(),
+                      workspace=s.ws.data_ptr())
+        return self._lib.make_io(**kw)
+
+    def fwd(self, s, prof=None):
+        import ctypes
+        io = self._io(s, self.flags, s.wave, True, s.out, s.stats, prof)
+        self._lib.check(self.lib.aas_lmfb_forward_ex(self.fe.plan.handle, ctypes.byref(io)))
 
     def fwd_clean(self, s):
-        st = torch.cuda.current_stream().cuda_stream
-        fe, lib = self.fe, self.lib
-        self._lib.check(lib.aas_lmfb_forward(fe.plan.handle, s.wave_c.data_ptr(), s.lengths.data_ptr(), self.n,
-                                             s.wave_c.stride(0), None, None, 0, 0, fe.window.data_ptr(),
-                                             s.out_c.data_ptr(), s.stats_c.data_ptr(), self.tmax,
-                                             self.flags_clean, 0.0, st, None))
+        import ctypes
+        io = self._io(s, self.flags_clean, s.wave_c, False, s.out_c, s.stats_c, None)
+        self._lib.check(self.lib.aas_lmfb_forward_ex(self.fe.plan.handle, ctypes.byref(io)))
 
     def bwd(self, s, prof=None):
-        st = torch.cuda.current_stream().cuda_stream
-        fe, lib = self.fe, self.lib
-        self._lib.check(lib.aas_lmfb_backward(fe.plan.handle, s.wave.data_ptr(), s.lengths.data_ptr(), self.n,
-                                              s.wave.stride(0), s.mr.data_ptr(), s.mi.data_ptr(),
-                                              s.mr.stride(0), s.mr.stride(1), fe.window.data_ptr(),
-                                              s.out.data_ptr(), s.stats.data_ptr(), s.gout.data_ptr(),
-                                              s.gr.data_ptr(), s.gi.data_ptr(), s.ws.data_ptr(), self.tmax,
-                                              self.flags, 0.0, st, prof))
+        import ctypes
+        io = self._io(s, self.flags, s.wave, True, s.out, s.stats, prof, backward=True)
+        self._lib.check(self.lib.aas_lmfb_backward_ex(self.fe.plan.handle, ctypes.byref(io)))
 
     def step(self, i, prof_f=None, prof_b=None):
         s = self.slots[i % self.ring]

@@ -72,6 +72,14 @@ int aas_lmfb_plan_info(const aas_lmfb_plan* plan, int* n_mels, int* fwd_compact,
  * handing them out with cluster launch control.  Results do not depend on them. */
 int aas_lmfb_plan_set_tuning(aas_lmfb_plan* plan, int warps_fwd, int warps_bwd, int static_schedule);
 
+/* Optional, recommended: a device-resident copy of the plan's lookup tables.  The caller allocates
+ * aas_lmfb_plan_tables_bytes() bytes (16-byte aligned) on the device it will run on, has them filled
+ * ONCE with aas_lmfb_plan_upload (an asynchronous host-to-device copy on `cuda_stream`; the plan must
+ * outlive it) and passes the pointer as aas_lmfb_io.tables on every call.  Without it every thread
+ * block rebuilds the tables from kernel parameters (about 4 us per block: a quarter of a small launch). */
+size_t aas_lmfb_plan_tables_bytes(const aas_lmfb_plan* plan);
+int aas_lmfb_plan_upload(const aas_lmfb_plan* plan, void* tables_dev, void* cuda_stream);
+
 /* Bytes of device workspace `backward` needs for this plan (forward needs none). */
 size_t aas_lmfb_workspace_bytes(const aas_lmfb_plan* plan, int n, int tmax, uint32_t flags);
 
@@ -109,6 +117,7 @@ typedef struct aas_lmfb_io {
     void*          workspace;       /* backward: aas_lmfb_workspace_bytes() bytes, 16-byte aligned     */
     void*          cuda_stream;
     void* const*   prof;            /* optional 4 cudaEvent_t recorded around the two kernels          */
+    const void*    tables;          /* optional: device tables filled by aas_lmfb_plan_upload          */
 } aas_lmfb_io;
 
 int aas_lmfb_forward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io* io);

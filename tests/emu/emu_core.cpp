@@ -21,15 +21,15 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
     typename TabOf<BWD>::Smem sm;
     tables_fill(&sm, tab, 0, 1);
     window_fill(S.data(), window, 0, 1);
+    std::vector<float> raw((kTile + 1) * kRawPitch, NAN);      // (uninitialised on the device)
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
-            StageLane sl;
-            stage_lane_init(lane, S.data(), sl);
             const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;
-            stage_tile<W>(w, lane, sl, wave_row, len, t0, n_rows, S.data(), vec_ok);
+            stage_raw<W>(w, lane, wave_row, len, t0, n_rows, raw.data(), nullptr, vec_ok);
         }
     for (int w = 0; w < W; ++w)
-        for (int lane = 0; lane < 32; ++lane) fft_pass1<W>(w, S.data() + lane, S.data() + kTile);
+        for (int lane = 0; lane < 32; ++lane)
+            fft_pass1<W>(w, raw.data() + lane * kRawPitch, S.data() + lane, S.data() + kTile);
     // pass 2: a real warp runs its lanes in lockstep (all loads of a step before its stores); the
     // emulation runs lane after lane, which is equivalent only if no lane's store can hit a word
     // another lane of the same step still has to read.  The compact P rows overlap the float2
@@ -62,7 +62,7 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
         for (int w = 0; w < W; ++w)
             for (int lane = 0; lane < 32; ++lane) {
                 StageLane sl;
-                stage_lane_init(lane, Sin.data(), sl);
+                stage_lane_init(lane, sl);
                 const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;
                 unstage_tile<W>(w, lane, sl, gwave_row, len, t0, n_rows, Sin.data(), vec_ok);
             }
@@ -181,6 +181,7 @@ extern "C" int emu_k1(int warps, int bwd, int mask_mode, const float* wave, cons
         case 3: CALL(3);
         case 4: CALL(4);
         case 5: CALL(5);
+        case 6: CALL(6);
     }
 #undef CALL
     return -3;

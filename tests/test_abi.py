@@ -65,7 +65,7 @@ def test_workspace_bytes_and_tuning(lib):
     assert lib.aas_lmfb_workspace_bytes(plan.handle, 0, 601, 5) == 0
     dense = MelPlan(np.ones((40, 161), dtype=np.float32))
     assert lib.aas_lmfb_workspace_bytes(dense.handle, 30, 601, 5) == 30 * (40 + 162) * 601 * 4
-    assert lib.aas_lmfb_plan_set_tuning(plan.handle, 4, 3, 1) == 0
+    assert lib.aas_lmfb_plan_set_tuning(plan.handle, 4, 6, 1) == 0
     assert lib.aas_lmfb_plan_set_tuning(plan.handle, 7, 0, 0) == -4
     assert lib.aas_lmfb_plan_set_tuning(plan.handle, 0, 0, 0) == 0
 
@@ -78,7 +78,7 @@ def test_io_struct_matches_the_header(lib):
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"([a-z_0-9]+)\s*;", body)
     assert names == [f[0] for f in _lib.IO._fields_]
-    assert ctypes.sizeof(_lib.IO) == 8 * 4 + 8 * 20
+    assert ctypes.sizeof(_lib.IO) == 8 * 4 + 8 * 21
 
 
 def test_argument_errors_do_not_touch_the_gpu(lib):

@@ -231,9 +231,18 @@ def main():
         rows_c.append(", ".join(lit(math.cos(2.0 * math.pi * f / 320.0)) for f in fs) + ", 0.0f, 0.0f, 0.0f")
         rows_f.append(", ".join(str(f) for f in fs) + ", 0, 0, 0")
     parts.append("// [k2][k1] (rows padded to 8 words): split twiddles and bin f = (96*k1 + 65*k2) mod 160")
-    parts.append("LMFB_CONST float kStepSin[17][8] = {\n  {" + "},\n  {".join(rows_s) + "}};")
-    parts.append("LMFB_CONST float kStepCos[17][8] = {\n  {" + "},\n  {".join(rows_c) + "}};")
-    parts.append("LMFB_CONST unsigned kStepBin[17][8] = {\n  {" + "},\n  {".join(rows_f) + "}};")
+    body_s = " = {\n  {" + "},\n  {".join(rows_s) + "}};"
+    body_c = " = {\n  {" + "},\n  {".join(rows_c) + "}};"
+    body_f = " = {\n  {" + "},\n  {".join(rows_f) + "}};"
+    parts.append("LMFB_CONST float kStepSin[17][8]" + body_s)
+    parts.append("LMFB_CONST float kStepCos[17][8]" + body_c)
+    parts.append("LMFB_CONST unsigned kStepBin[17][8]" + body_f)
+    # host copies (the library builds the shared-memory table image on the host once per plan)
+    parts.append("#ifdef __CUDACC__")
+    parts.append("static const float kStepSinHost[17][8]" + body_s)
+    parts.append("static const float kStepCosHost[17][8]" + body_c)
+    parts.append("static const unsigned kStepBinHost[17][8]" + body_f)
+    parts.append("#else\n#  define kStepSinHost kStepSin\n#  define kStepCosHost kStepCos\n#  define kStepBinHost kStepBin\n#endif")
     parts.append("}  // namespace aas_lmfb")
     with open(OUT, "w") as f:
         f.write("\n".join(parts) + "\n")

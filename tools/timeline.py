@@ -22,7 +22,7 @@ wl = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "
 n, samples = (256, 160000) if wl == "sweep" else (30, 96000)
 tmax = 1 + samples // 160
 dev = torch.device("cuda", 0)
-W = int(os.environ.get("TL_W", "3"))
+W = int(os.environ.get("TL_W", "5"))
 buf_f = torch.zeros(8 * 64 * 8 * 8 + 4096, dtype=torch.int64, device=dev)
 buf_b = torch.zeros(8 * 64 * 8 * 8 + 4096, dtype=torch.int64, device=dev)
 os.environ["AAS_LMFB_TIMELINE_FWD"] = str(buf_f.data_ptr())
