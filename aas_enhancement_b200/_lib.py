@@ -16,6 +16,7 @@ N_FFT, HOP, N_BINS = 320, 160, 161
 
 MASK_MODES = {"none": 0, "reim": 1, "power": 2}
 CMVN_MODES = {"none": 0 << 2, "per_bin": 1 << 2, "global": 2 << 2}
+WAVE_I16 = 1 << 4
 
 EXPORTS = ("aas_lmfb_abi_version", "aas_lmfb_strerror", "aas_lmfb_plan_create",
            "aas_lmfb_plan_destroy", "aas_lmfb_plan_info", "aas_lmfb_plan_set_tuning",

@@ -39,6 +39,7 @@
 // (mask -> power -> mel -> log1p), AM_training/train.py:39-42,:199 (320/160/hamming, 161 bins).
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 #include <string.h>
 #include "fft_codelets.cuh"
 
@@ -178,7 +179,11 @@ LMFB_HD int reflect_index(int i, int len) {
     return j >= len ? period - j : j;
 }
 
-// row `row` of a tensor whose rows are `stride_bytes` apart: one IMAD.WIDE when `row` is a constant
+// row `row` of a tensor whose rows are `stride_bytes` apart.  (Forcing one IMAD.WIDE per address with
+// inline PTX -- the compiler shares the product row * stride between tensors with equal strides and
+// then pays two IADD3 per address -- was measured: 700 fewer instructions per backward tile and 5 %
+// SLOWER.  IMAD.WIDE issues on the FMA pipe, which the FFT already saturates; the IADD3 pairs ride the
+// otherwise idle ALU pipe.)
 LMFB_HD const float* at_row(const float* p, uint32_t row, uint32_t stride_bytes) {
     return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p) +
                                           (unsigned long long)row * (unsigned long long)stride_bytes);
@@ -234,9 +239,9 @@ static_assert(kRawBytes == kRawBytes_, "raw buffer size");
 
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_row(float* dst, const float* src, uint64_t* bar) {
+__device__ __forceinline__ void bulk_row(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(kHop * 4), "r"(smem_u32(bar)) : "memory");
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_copy(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -246,7 +251,7 @@ __device__ __forceinline__ void mbar_arrive_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 #else
-static inline void bulk_row(float* dst, const float* src, uint64_t*) { for (int i = 0; i < kHop; ++i) dst[i] = src[i]; }
+static inline void bulk_row(void* dst, const void* src, unsigned bytes, uint64_t*) { memcpy(dst, src, bytes); }
 static inline void mbar_arrive_tx(uint64_t*, unsigned) {}
 #endif
 
@@ -267,9 +272,9 @@ LMFB_HD void stage_lane_init(int lane, StageLane& sl) {
 
 // window table: pad column (index 32) of slot s holds the window pair of the packed sample that
 // lives in slot s.  Written once per persistent CTA; the passes never touch column 32.
-LMFB_HD void window_fill(float2* __restrict__ S, const float* __restrict__ window, int idx, int cnt) {
+LMFB_HD void window_fill(float2* __restrict__ S, const float* __restrict__ window, int idx, int cnt, float scale = 1.0f) {
     for (int j = idx; j < kSlots; j += cnt)
-        S[slot_of_packed(j) * kPitch + kTile] = make_float2(LMFB_LDG(window + 2 * j), LMFB_LDG(window + 2 * j + 1));
+        S[slot_of_packed(j) * kPitch + kTile] = make_float2(scale * LMFB_LDG(window + 2 * j), scale * LMFB_LDG(window + 2 * j + 1));
 }
 
 // hop-row q of the unpadded signal lies fully inside [0, len) and can be copied as a whole
@@ -281,19 +286,24 @@ LMFB_HD bool row_interior(int q, int len, bool vec_ok) {
 // the buffer's mbarrier once, with the bytes its bulk copies will deliver.  Plain stores of the
 // per-row path are ordered before the consumer by the block barrier that always lies between this
 // call and the pass 1 that reads the buffer.
-template <int W>
-LMFB_HD void stage_raw(int w, int lane, const float* __restrict__ wave_row, int len, int t0, int n_rows,
+//   I16: the wave is int16 PCM (bytes on the wire and in HBM halved): the rows land
+//        as they are (320 bytes each, same row pitch) and pass 1 converts; 1/32768 is in the window table.
+template <int W, bool I16>
+LMFB_HD void stage_raw(int w, int lane, const void* __restrict__ wave_row_, int len, int t0, int n_rows,
                        float* __restrict__ raw, uint64_t* bar, bool vec16) {
+    typedef typename std::conditional<I16, int16_t, float>::type Sample;
+    const Sample* wave_row = static_cast<const Sample*>(wave_row_);
+    constexpr unsigned kRowBytes = kHop * sizeof(Sample);
     // fast path (all tiles but the first and last of an utterance): every row is a whole interior hop-row
     if (vec16 && n_rows == kTile + 1 && t0 >= 1 && (t0 + kTile) * kHop <= len) {       // (t0 < 2^22: no overflow)
         if (lane == 0) {
-            const float* src = wave_row + (long long)(t0 - 1 + w) * kHop;
+            const Sample* src = wave_row + (long long)(t0 - 1 + w) * kHop;
             float* dst = raw + w * kRawPitch;
             constexpr int kMine = (kTile + 1 + W - 1) / W;    // rows w, w + W, ... (the last may not exist)
 #pragma unroll
             for (int i = 0; i < kMine; ++i)
-                if (w + i * W < kTile + 1) bulk_row(dst + i * W * kRawPitch, src + i * W * kHop, bar);
-            mbar_arrive_tx(bar, (unsigned)(((kTile + 1 - w + W - 1) / W) * kHop * 4));
+                if (w + i * W < kTile + 1) bulk_row(dst + i * W * kRawPitch, src + i * W * kHop, kRowBytes, bar);
+            mbar_arrive_tx(bar, (unsigned)(((kTile + 1 - w + W - 1) / W) * kRowBytes));
         }
         return;
     }
@@ -303,26 +313,29 @@ LMFB_HD void stage_raw(int w, int lane, const float* __restrict__ wave_row, int 
         const int q = t0 + r - 1;                             // hop-row of the signal
         float* dst = raw + r * kRawPitch;
         if (r < n_rows && row_interior(q, len, vec16)) {
-            if (lane == 0) bulk_row(dst, wave_row + (long long)q * kHop, bar);
-            bytes += kHop * 4;
+            if (lane == 0) bulk_row(dst, wave_row + (long long)q * kHop, kRowBytes, bar);
+            bytes += kRowBytes;
         } else {
-            float2 v[3];
-            v[0] = v[1] = v[2] = make_float2(0.0f, 0.0f);         // rows >= n_rows feed no frame that exists
+            Sample v[3][2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v[k][0] = v[k][1] = (Sample)0;   // rows >= n_rows feed no frame that exists
             if (r < n_rows) {
                 const int base = q * kHop;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {                     // all six loads in flight before the stores
                     const int c = lane + 32 * k;
                     if (c < 80) {
-                        v[k].x = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
-                        v[k].y = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
+                        v[k][0] = LMFB_LDG(wave_row + reflect_index(base + 2 * c, len));
+                        v[k][1] = LMFB_LDG(wave_row + reflect_index(base + 2 * c + 1, len));
                     }
                 }
             }
-            float2* d2 = reinterpret_cast<float2*>(dst);
-            d2[lane] = v[0];
-            d2[lane + 32] = v[1];
-            if (lane < 16) d2[lane + 64] = v[2];
+            Sample* d = reinterpret_cast<Sample*>(dst);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int c = lane + 32 * k;
+                if (c < 80) { d[2 * c] = v[k][0]; d[2 * c + 1] = v[k][1]; }
+            }
         }
     }
     if (lane == 0) mbar_arrive_tx(bar, bytes);
@@ -341,29 +354,38 @@ LMFB_CX int packed_of_slot(int s) {            // inverse of slot_of_packed
 }
 LMFB_CX int raw_off_of_packed(int j) { return j < 80 ? 2 * j : kRawPitch + 2 * (j - 80); }
 
-template <int N1>
+// (int16 samples: packed sample j is the 4-byte pair at byte 4j of the frame's first row, or of its second row)
+LMFB_CX int raw_off_of_packed_i16(int j) { return j < 80 ? j : kRawPitch + (j - 80); }    // in 4-byte words
+
+template <int N1, bool I16>
 LMFB_HD void load_sub_raw(const float* __restrict__ rawl, const float2* __restrict__ win, float (&xr)[32], float (&xi)[32]) {
     static_for<0, 32>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
-        constexpr int off = raw_off_of_packed(packed_of_slot(N1 * 32 + i));
-        const float2 v = *reinterpret_cast<const float2*>(rawl + off);
+        constexpr int j = packed_of_slot(N1 * 32 + i);
         const float2 g = win[(N1 * 32 + i) * kPitch];             // same address for every lane: broadcast
-        xr[i] = v.x * g.x; xi[i] = v.y * g.y;
+        if constexpr (I16) {
+            const uint32_t u = reinterpret_cast<const uint32_t*>(rawl)[raw_off_of_packed_i16(j)];
+            xr[i] = (float)(int16_t)(u & 0xffffu) * g.x;
+            xi[i] = (float)((int32_t)u >> 16) * g.y;
+        } else {
+            const float2 v = *reinterpret_cast<const float2*>(rawl + raw_off_of_packed(j));
+            xr[i] = v.x * g.x; xi[i] = v.y * g.y;
+        }
     });
 }
 
 //   rawl : raw + lane * kRawPitch;  col : S + lane;  win : S + kTile (the window table)
-template <int W>
+template <int W, bool I16 = false>
 LMFB_HD void fft_pass1(int w, const float* __restrict__ rawl, float2* __restrict__ col, const float2* __restrict__ win) {
 #pragma unroll 1
     for (int n1 = w; n1 < 5; n1 += W) {
         float xr[32], xi[32];
         switch (n1) {
-            case 0:  load_sub_raw<0>(rawl, win, xr, xi); break;
-            case 1:  load_sub_raw<1>(rawl, win, xr, xi); break;
-            case 2:  load_sub_raw<2>(rawl, win, xr, xi); break;
-            case 3:  load_sub_raw<3>(rawl, win, xr, xi); break;
-            default: load_sub_raw<4>(rawl, win, xr, xi); break;
+            case 0:  load_sub_raw<0, I16>(rawl, win, xr, xi); break;
+            case 1:  load_sub_raw<1, I16>(rawl, win, xr, xi); break;
+            case 2:  load_sub_raw<2, I16>(rawl, win, xr, xi); break;
+            case 3:  load_sub_raw<3, I16>(rawl, win, xr, xi); break;
+            default: load_sub_raw<4, I16>(rawl, win, xr, xi); break;
         }
 #ifndef LMFB_DBG_NOFFT
         fft32(xr, xi);
@@ -927,7 +949,11 @@ LMFB_HD void phase3_gather(int w, const float* __restrict__ pl, const FwdSmem& s
 }
 
 // L2 prefetch of the row segments a tile will read: threads take rows idx, idx+cnt, ...; a
-// 128-byte segment may straddle two lines, so both ends are touched.  (Touching all five sectors
+// 128-byte segment may straddle two lines, so both ends are touched.  Issued when the tile starts.
+// Measured alternatives on 256 x 10 s (forward / backward ms): this 0.194 / 0.204; none 0.212 / 0.242;
+// a tile AHEAD (when the next tile's rows are requested) 0.201 / 0.246 -- the lines are gone again by the
+// time they are used (the L2 turns over in ~12 us under this traffic); step by step, two steps ahead of
+// the loads, 0.199 / 0.213 (the extra live values spill).  (Touching all five sectors
 // of a row was measured: slower, the extra prefetches cost more load/store-unit time than they save.)
 LMFB_HD void prefetch_rows_l2(int idx, int cnt, const float* __restrict__ base, unsigned sf, int rows, int t0, int tmax) {
     if (t0 >= tmax) return;

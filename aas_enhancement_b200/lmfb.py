@@ -131,7 +131,8 @@ class LMFB(torch.autograd.Function):
     """``Z, frame_lens = LMFB.apply(wave, lengths, mask_r, mask_i, plan, window, mask_mode,
     cmvn_mode, eps, tmax, mel_dev)``
 
-    wave (N, Lmax) f32 cuda zero-padded -- or (N, nCH, Lmax) for multi-channel input, with masks
+    wave (N, Lmax) f32 cuda zero-padded (or int16 PCM, value / 32768: converted inside the kernel, half
+    the bytes on the wire) -- or (N, nCH, Lmax) for multi-channel input, with masks
     (N, nCH*161, Tmax) as in ``BRNNmultiCH`` (model.py:160-167, :186-198: the basis repeats over the
     channels, i.e. the masked powers are summed); lengths (N,) int32 cuda (samples); masks
     (N, 161, Tmax) f32 or None; plan a :class:`MelPlan`; window (320,) f32 cuda; ``mel_dev`` the
@@ -150,7 +151,11 @@ class LMFB(torch.autograd.Function):
         lib = _lib.load()
         if mask_mode not in _lib.MASK_MODES or cmvn_mode not in _lib.CMVN_MODES:
             raise ValueError(f"bad mask_mode/cmvn_mode: {mask_mode!r}/{cmvn_mode!r}")
-        _check_f32_cuda("wave", wave, dev)
+        if wave.dtype == torch.int16:                  # PCM as stored in wave files: converted inside the kernel
+            if wave.device != dev:
+                raise TypeError("wave must live on one device")
+        else:
+            _check_f32_cuda("wave", wave, dev)
         _check_f32_cuda("window", window, dev)
         if wave.dim() not in (2, 3) or wave.stride(-1) != 1:
             raise ValueError("wave must be (N, Lmax) or (N, nCH, Lmax) with unit sample stride")
@@ -196,7 +201,7 @@ class LMFB(torch.autograd.Function):
         if mel_dev is not None:
             _check_f32_cuda("mel_dev", mel_dev, dev)
             mel_dev = mel_dev.contiguous()
-        flags = _lib.MASK_MODES[mask_mode] | _lib.CMVN_MODES[cmvn_mode]
+        flags = _lib.MASK_MODES[mask_mode] | _lib.CMVN_MODES[cmvn_mode] | (_lib.WAVE_I16 if wave.dtype == torch.int16 else 0)
         out = torch.empty((n, plan.n_mels, tmax), dtype=torch.float32, device=dev)
         stats = torch.empty((n, plan.n_mels, 2), dtype=torch.float32, device=dev)
         io = _lib.make_io(flags=flags, device=dev.index if dev.index is not None else -1, n=n, n_ch=n_ch, tmax=tmax,
@@ -306,9 +311,9 @@ class LMFBFrontEnd(torch.nn.Module):
         self._tuning = (0, 0, False)
 
     def set_tuning(self, warps_fwd=0, warps_bwd=0, static_schedule=False):
-        """Tests / benchmarks: warps per 32-frame tile of the forward / backward kernel (2..5, 0 = the
+        """Tests / benchmarks: warps per 32-frame tile of the forward / backward kernel (4..6, 0 = the
         measured default) and the static tile schedule.  Results do not depend on them."""
-        self._tuning = (int(warps_fwd), int(warps_bwd), bool(static_schedule))
+        self._tuning = (int(warps_fwd), int(warps_bwd), int(bool(static_schedule)))
         self._plan_key = None
         return self
 

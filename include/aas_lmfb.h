@@ -35,13 +35,16 @@ extern "C" {
 #define AAS_LMFB_HOP     160   /* int(16000 * 0.01), AM_training/train.py:41    */
 #define AAS_LMFB_N_BINS  161   /* AM_training/train.py:199                      */
 
-/* flags: bits 0-1 mask mode, bits 2-3 CMVN mode */
+/* flags: bits 0-1 mask mode, bits 2-3 CMVN mode, bit 4 sample format */
 #define AAS_LMFB_MASK_NONE    0u   /* P = Re^2 + Im^2                                        */
 #define AAS_LMFB_MASK_REIM    1u   /* P = (Re*Mr)^2 + (Im*Mi)^2   (model.py:191-194)          */
 #define AAS_LMFB_MASK_POWER   2u   /* P = M * (Re^2 + Im^2)                                   */
 #define AAS_LMFB_CMVN_NONE    (0u << 2)
 #define AAS_LMFB_CMVN_PER_BIN (1u << 2)   /* mean/std per mel bin over the utterance's frames */
 #define AAS_LMFB_CMVN_GLOBAL  (2u << 2)   /* scalar mean/std over the utterance's (M, T) matrix */
+#define AAS_LMFB_WAVE_I16     (1u << 4)   /* `wave` is int16 PCM (value / 32768): what wave files hold
+                                           * (loader.py save_wave(int16=True)); halves the bytes on the wire
+                                           * and in HBM; converted inside the kernel; no waveform gradient   */
 
 /* return codes: 0 ok, <0 argument errors, >0 a cudaError_t from the launch */
 #define AAS_LMFB_OK              0
@@ -68,7 +71,7 @@ void aas_lmfb_plan_destroy(aas_lmfb_plan* plan);
 /* What the analysis found: *fwd_compact / *bwd_banded are 1 on the fast paths (any may be NULL). */
 int aas_lmfb_plan_info(const aas_lmfb_plan* plan, int* n_mels, int* fwd_compact, int* bwd_banded);
 /* Tuning knobs (tests and benchmarks; 0 = the measured default): warps per 32-frame tile of the
- * forward / backward kernel (2..5), and static_schedule = 1 to deal tiles round-robin instead of
+ * forward / backward kernel (4..6), and static_schedule = 1 to deal tiles round-robin instead of
  * handing them out with cluster launch control.  Results do not depend on them. */
 int aas_lmfb_plan_set_tuning(aas_lmfb_plan* plan, int warps_fwd, int warps_bwd, int static_schedule);
 
@@ -97,7 +100,8 @@ typedef struct aas_lmfb_io {
     int32_t        tmax;
     float          eps;
     int32_t        reserved_;
-    const float*   wave;            /* (N, n_ch, .): sample (n, c, i) at n*wave_stride + c*wave_stride_ch + i */
+    const void*    wave;            /* fp32 (or int16 with AAS_LMFB_WAVE_I16), (N, n_ch, .): sample (n, c, i) at
+                                     * n*wave_stride + c*wave_stride_ch + i (strides in samples)         */
     int64_t        wave_stride;
     int64_t        wave_stride_ch;
     int64_t        wave_len;        /* samples of every row that may be read; lengths are clamped to it (0: trust lengths) */

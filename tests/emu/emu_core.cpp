@@ -25,7 +25,7 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane) {
             const int n_rows = (T - t0 < kTile ? T - t0 : kTile) + 1;
-            stage_raw<W>(w, lane, wave_row, len, t0, n_rows, raw.data(), nullptr, vec_ok);
+            stage_raw<W, false>(w, lane, wave_row, len, t0, n_rows, raw.data(), nullptr, vec_ok);
         }
     for (int w = 0; w < W; ++w)
         for (int lane = 0; lane < 32; ++lane)

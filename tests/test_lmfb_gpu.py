@@ -759,3 +759,45 @@ def test_oversized_lengths_are_clamped_not_read(be):
     z, fl = fe(wave, big)
     z2, fl2 = fe(wave, torch.from_numpy(b["lengths"]).cuda())
     assert torch.equal(z, z2) and torch.equal(fl, fl2)
+
+
+def test_int16_wave_is_converted_in_the_kernel(be):
+    """int16 PCM on the wire and in HBM; the kernel converts (x / 32768).  Bit-identical
+    to the float path fed with the same values converted on the host; boundary tiles, ragged lengths, a
+    row stride that is not a multiple of 8 samples (no bulk copies) and a CLC-scheduled launch included."""
+    rs = np.random.RandomState(3)
+    for n, lmax, pad in ((4, 20000, 0), (3, 7003, 3), (60, 80000, 0)):
+        base = _synth.make_batch(n, lmax, seed=80 + n, ragged=True)
+        pcm = np.round(base["wave"] * 32768.0).clip(-32768, 32767).astype(np.int16)
+        store = torch.zeros(n, lmax + pad, dtype=torch.int16, device="cuda")
+        w16 = store[:, :lmax]
+        w16.copy_(torch.from_numpy(pcm))
+        wf = torch.from_numpy(pcm.astype(np.float32) / 32768.0).cuda()
+        lengths = torch.from_numpy(base["lengths"]).cuda()
+        fe = _fe(be, "reim", "per_bin")
+        outs = []
+        for wave in (w16, wf):
+            mr = torch.from_numpy(base["mask_r"]).cuda().requires_grad_(True)
+            mi = torch.from_numpy(base["mask_i"]).cuda().requires_grad_(True)
+            z, fl = fe(wave, lengths, mr, mi)
+            z.backward(torch.from_numpy(base["grad_out"]).cuda())
+            outs.append((z.detach(), fl, mr.grad, mi.grad))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+        if n == 4:
+            b2 = dict(base)
+            b2["wave"] = pcm.astype(np.float32) / 32768.0
+            z_ref, fl_ref, g_ref = _oracle(b2, "reim", "per_bin")
+            assert orc.rel_err(outs[0][0].cpu().numpy(), z_ref) < TOL
+            assert orc.rel_err(outs[0][2].cpu().numpy(), g_ref["grad_mask_r"]) < TOL
+        zc, _ = _fe(be, "none", "per_bin")(w16, lengths)
+        zf, _ = _fe(be, "none", "per_bin")(wf, lengths)
+        assert torch.equal(zc, zf)
+
+
+def test_utterance_longer_than_the_register_resident_cmvn(be):
+    """34 s = 3,401 frames: beyond the block-per-row register-resident CMVN kernels (3,072), i.e. the
+    three-pass fallback, forward and backward."""
+    b = _synth.make_batch(1, 16000 * 34, seed=34)
+    assert b["tmax"] == 3401
+    _check(be, b, "reim", "per_bin")

@@ -1,0 +1,28 @@
+#!/bin/bash
+# 8-GPU box: BASELINE.json configs[2] (AAS step), configs[3] (paired, 2/4/8) and configs[4] (sweep) under torchrun
+mkdir -p gpurun_out/scaling
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+run() { # name nproc port args...
+  name=$1; np=$2; port=$3; shift 3
+  if [ "$np" = "1" ]; then timeout 900 python bench.py --gpus 1 "$@" > gpurun_out/scaling/$name.json 2> gpurun_out/scaling/$name.err
+  else timeout 900 $TR --nproc-per-node $np --master-port $port bench.py --gpus $np "$@" > gpurun_out/scaling/$name.json 2> gpurun_out/scaling/$name.err; fi
+  python - gpurun_out/scaling/$name.json $name <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    r=d.get("roofline",{}); print("%-22s n_gpus %d value %.4e ms/step %.4f e2e %.4e step_frac %s" % (sys.argv[2], d["n_gpus"], d["value"], d["ms_per_step"], d["e2e"]["value"], r.get("step_frac")))
+    if "aas_step" in d: print("   aas_step:", {k:v for k,v in d["aas_step"].items() if k!="models"})
+except Exception as e:
+    print(sys.argv[2], "FAILED", e); print(open(sys.argv[1].replace(".json",".err")).read()[-1500:])
+PY
+}
+nvidia-smi -L | head -8
+run r3_chime_n8 8 29601 --steps 20 --warmup 5 --no-cpu
+run r3_chime_n1 1 0 --steps 20 --warmup 5 --no-cpu
+for np in 2 4 8; do run r3_paired_n$np $np 2961$np --workload paired_30x6s --steps 20 --warmup 5 --no-large --no-cpu; done
+run r3_paired_n1 1 0 --workload paired_30x6s --steps 20 --warmup 5 --no-large
+run r3_sweep256_n8 8 29621 --workload sweep_256x10s --steps 20 --warmup 5 --no-cpu --no-e2e
+run r3_aas_n8 8 29631 --workload aas_step_30x6s --steps 8 --warmup 3
+run r3_aas_n2 2 29632 --workload aas_step_30x6s --steps 8 --warmup 3
+echo "== sweep quick at 8 GPUs"
+timeout 900 $TR --nproc-per-node 8 --master-port 29641 tools/sweep.py gpurun_out/scaling/r3_sweep_n8.md --quick 2>&1 | tail -14
