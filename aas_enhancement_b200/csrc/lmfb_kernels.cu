@@ -388,7 +388,11 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
 // counts the last tile normalising the utterance out of L2 -- was built, is correct, and was measured:
 // forward 0.287 ms against 0.203 + 0.019 ms on 256 x 10 s and 58 against 31 + 8 us on 30 x 6 s.  One block
 // normalising 40 rows is a serial tail that 1,200 rows spread over the whole GPU do not have, and the
-// count's fence and round trip sit on every tile.  The normalisation stays a launch of its own.)
+// count's fence and round trip sit on every tile.  The normalisation stays a launch of its own.
+// Programmatic dependent launch of the second kernel of a call (CMVN behind K1, K1 behind the CMVN
+// gradient, its prologue + staging + pass 1 ahead of griddepcontrol.wait) was measured too, inside the
+// CUDA graph of the benchmark: 55.6 vs 54.9 us per step on 30 x 6 s, 0.4329 vs 0.4326 ms on 256 x 10 s:
+// nothing, as in round 1.)
 constexpr int kRowThreads = 128;
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -750,15 +754,19 @@ static const k1_bwd_fn kBwdI16[4] = { nullptr, lmfb_k1<kMaskReim, true, 5, 3, fa
 
 // (warps per tile, resident CTAs per SM the register budget is sized for).  Shared memory (scratch 42 KB
 // + raw buffer 21 KB + tables 3 KB) allows three tiles per SM; five warps per tile give every warp one
-// of the five sub-transforms of pass 1.
+// of the five sub-transforms of pass 1.  Launches of at most two rounds of 2 x 148 tiles (config #2: 570
+// tiles) are latency- not throughput-bound and take EIGHT warps per tile, two tiles per SM: a tile's
+// pass 2 is then 3 steps deep instead of 4 and both rounds are full (measured on 30 x 6 s: forward 26.8
+// vs 28.9 us, backward 22.9 vs 27.1 us, step 47.5 vs 54.3 us).
 static const K1Variant kVariants[] = {
 #ifdef LMFB_ONLY_W5
-    LMFB_VARIANT(5, 3),
+    LMFB_VARIANT(5, 3), LMFB_VARIANT(5, 3), LMFB_VARIANT(5, 3), LMFB_VARIANT(8, 2),
 #else
-    LMFB_VARIANT(5, 3), LMFB_VARIANT(4, 3), LMFB_VARIANT(6, 3),
+    LMFB_VARIANT(5, 3), LMFB_VARIANT(4, 3), LMFB_VARIANT(6, 3), LMFB_VARIANT(8, 2),
 #endif
 };
-constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 0, kBwdVariantBig = 0, kBwdVariantSmall = 0;
+constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 3, kBwdVariantBig = 0, kBwdVariantSmall = 3;
+constexpr long long kSmallTiles = 148LL * 2 * 2;            // two rounds of the eight-warp shape
 
 static int variant_of_warps(int warps) {
     for (size_t i = 0; i < sizeof(kVariants) / sizeof(kVariants[0]); ++i)
@@ -972,7 +980,7 @@ extern "C" int aas_lmfb_forward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io*
 #ifdef LMFB_TIMELINE
     { const char* e = getenv("AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
 #endif
-    const bool small = (long long)n * a.tiles_per_utt <= 148LL * 3;      // fits one wave
+    const bool small = (long long)n * a.tiles_per_utt <= kSmallTiles;
     const bool i16 = (io->flags & AAS_LMFB_WAVE_I16) != 0;
     const K1Variant& v = kVariants[i16 ? 0 : (plan->vfwd >= 0 ? plan->vfwd : (small ? kFwdVariantSmall : kFwdVariantBig))];
     FwdTab band = plan->fwd;
@@ -1071,7 +1079,7 @@ extern "C" int aas_lmfb_backward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io
     { const char* e = getenv("AAS_LMFB_TIMELINE_BWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
 #endif
     const long long units = (long long)n * io->n_ch;
-    const bool small = units * a.tiles_per_utt <= 148LL * 3;      // fits one wave
+    const bool small = units * a.tiles_per_utt <= kSmallTiles;
     const K1Variant& v = kVariants[i16 ? 0 : (plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig))];
     if (mask == AAS_LMFB_MASK_NONE) { a.mask_r = a.mask_i = (const float*)io->wave; a.gr = a.gi = nullptr; a.msf = (unsigned)tmax; a.msn = 0; }   // never dereferenced
     a.gwave = grad_wave;
@@ -1175,7 +1183,7 @@ extern "C" int aas_lmfb_stft(const aas_lmfb_plan* plan,
     a.mask_r = a.mask_i = out;                                    // never read (clamped pointer arithmetic only)
     a.msn = out_stride_n; a.msf = (unsigned)tmax;
     a.dE = out; a.gr = out; a.gi = out + (long long)kBins * tmax;
-    const bool small = (long long)n * a.tiles_per_utt <= 148LL * 3;      // fits one wave
+    const bool small = (long long)n * a.tiles_per_utt <= kSmallTiles;
     const K1Variant& v = kVariants[plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig)];
     return launch_k1(plan, v, v.bwd[3], a, plan->bwd, true, n, (cudaStream_t)cuda_stream);
 }

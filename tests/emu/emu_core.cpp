@@ -182,6 +182,7 @@ extern "C" int emu_k1(int warps, int bwd, int mask_mode, const float* wave, cons
         case 4: CALL(4);
         case 5: CALL(5);
         case 6: CALL(6);
+        case 8: CALL(8);
     }
 #undef CALL
     return -3;

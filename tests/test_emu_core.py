@@ -81,7 +81,7 @@ def test_emulated_stft_matches_oracle(emu, length, sym):
             assert np.abs(got - ref).max() / scale < 3e-6, (lo, which)
 
 
-@pytest.mark.parametrize("warps", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("warps", [1, 2, 3, 4, 5, 6, 8])
 @pytest.mark.parametrize("mode", ["reim", "power", "none"])
 def test_emulated_k1_forward_and_backward(emu, mode, warps):
     b = _synth.make_batch(3, 5000, seed=17, ragged=True, tonal=(mode == "power"))

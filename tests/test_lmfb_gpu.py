@@ -392,7 +392,7 @@ def test_eps_variant(be):
     assert orc.rel_err(mr.grad.cpu().numpy(), g_ref["grad_mask_r"]) < TOL
 
 
-@pytest.mark.parametrize("warps", [4, 5, 6])
+@pytest.mark.parametrize("warps", [4, 5, 6, 8])
 def test_every_kernel_variant(be, warps):
     """All warps-per-tile variants of K1 (aas_lmfb_plan_set_tuning) give the same answers."""
     b = _synth.make_batch(4, 11000, seed=33, ragged=True)
