@@ -22,7 +22,7 @@ EXPORTS = ("aas_lmfb_abi_version", "aas_lmfb_strerror", "aas_lmfb_plan_create",
            "aas_lmfb_plan_destroy", "aas_lmfb_plan_info", "aas_lmfb_plan_set_tuning",
            "aas_lmfb_plan_tables_bytes", "aas_lmfb_plan_upload",
            "aas_lmfb_workspace_bytes", "aas_lmfb_forward_ex", "aas_lmfb_backward_ex", "aas_lmfb_forward",
-           "aas_lmfb_backward", "aas_lmfb_backward_wave", "aas_lmfb_stft", "aas_l1_partial_count", "aas_l1_abs_sum", "aas_l1_abs_grad")
+           "aas_lmfb_backward", "aas_lmfb_backward_wave", "aas_lmfb_stft", "aas_l1_partial_count", "aas_l1_abs_sum", "aas_l1_rows_sum", "aas_l1_abs_grad")
 
 _lock = threading.Lock()
 _lib = None
@@ -39,7 +39,8 @@ class IO(ctypes.Structure):
                 ("lengths", _vp), ("mask_r", _vp), ("mask_i", _vp), ("mask_stride_n", _i64),
                 ("mask_stride_f", _i64), ("window", _vp), ("mel_dev", _vp), ("out", _vp), ("stats", _vp),
                 ("grad_out", _vp), ("grad_mask_r", _vp), ("grad_mask_i", _vp), ("grad_wave", _vp),
-                ("workspace", _vp), ("cuda_stream", _vp), ("prof", _vp), ("tables", _vp)]
+                ("workspace", _vp), ("cuda_stream", _vp), ("prof", _vp), ("tables", _vp),
+                ("l1_target", _vp), ("l1_rows", _vp), ("frame_lens", _vp)]
 
 
 def make_io(**kw) -> IO:
@@ -108,6 +109,8 @@ def load() -> ctypes.CDLL:
         lib.aas_l1_partial_count.restype = _i32
         lib.aas_l1_abs_sum.restype = _i32
         lib.aas_l1_abs_sum.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]
+        lib.aas_l1_rows_sum.restype = _i32
+        lib.aas_l1_rows_sum.argtypes = [_vp, _i32, _vp, _vp]
         lib.aas_l1_abs_grad.restype = _i32
         lib.aas_l1_abs_grad.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]
         if lib.aas_lmfb_abi_version() != ABI_VERSION:

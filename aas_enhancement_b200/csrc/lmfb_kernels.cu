@@ -75,6 +75,7 @@ struct K1Args {
     long long      wave_len;   // samples of a row that may be read (lengths are clamped to it); 0: trust lengths
     const void*    tab_dev;    // device image of the shared-memory table (aas_lmfb_plan_upload), or NULL: fill from the parameter
     FastDiv        div_tpu, div_nch;   // / tiles_per_utt, / n_ch
+    int32_t*       frame_lens; // forward, optional: (N,) receives T_n = 1 + lengths[n] / 160 clipped to Tmax (0 for an empty utterance)
 };
 
 
@@ -247,6 +248,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         const long long moff = (long long)cur.n * a.msn + (long long)cur.ch * kBins * a.msf + t;
         const bool last_ch = BWD || cur.ch + 1 == nch_fwd;
         Unit nxt;
+        if (!BWD && a.frame_lens && cur.t0 == 0 && cur.ch == 0 && threadIdx.x == 0) a.frame_lens[cur.n] = cur.T;
 
         if (!cur.real) {                            // tile lies entirely in the zero padding
             if (inrow) {
@@ -417,18 +419,28 @@ __device__ __forceinline__ int frames_of(const int32_t* lengths, int n, int tmax
 // mode: 1 = per mel bin (grid.x = M rows), 2 = global (grid.x = 1, block walks all M rows)
 __global__ void __launch_bounds__(kRowThreads)
 cmvn_fwd(float* __restrict__ out, float* __restrict__ stats, const int32_t* __restrict__ lengths,
-         int n_mels, int tmax, float eps, int mode, long long wave_len) {
+         int n_mels, int tmax, float eps, int mode, long long wave_len,
+         const float* __restrict__ l1_target, float* __restrict__ l1_rows) {
     __shared__ double red[kRowThreads / 32];
     const int n = blockIdx.y;
     const int T = frames_of(lengths, n, tmax, wave_len);
     const int m0 = mode == 1 ? blockIdx.x : 0;
     const int m1 = mode == 1 ? m0 + 1 : n_mels;
     float* base = out + (long long)n * n_mels * tmax;
+    const float* tgt = l1_target ? l1_target + (long long)n * n_mels * tmax : nullptr;
     const long long cnt = (long long)(m1 - m0) * T;
     if (T == 0) {                                   // empty utterance: rows are already zero
         for (int m = m0 + threadIdx.x; m < m1; m += kRowThreads) {
             stats[((long long)n * n_mels + m) * 2 + 0] = 0.0f;
             stats[((long long)n * n_mels + m) * 2 + 1] = 1.0f;
+        }
+        if (tgt) {                                  // (block-uniform) |0 - target| over the whole rows
+            for (int m = m0; m < m1; ++m) {
+                float a = 0.0f;
+                for (int t = threadIdx.x; t < tmax; t += kRowThreads) a += fabsf(tgt[(long long)m * tmax + t]);
+                const double tot = block_sum((double)a, red);
+                if (threadIdx.x == 0) l1_rows[(long long)n * n_mels + m] = (float)tot;
+            }
         }
         return;
     }
@@ -446,13 +458,20 @@ cmvn_fwd(float* __restrict__ out, float* __restrict__ stats, const int32_t* __re
     const double var = block_sum((double)v, red) / (double)(cnt - 1);
     const float rstd = 1.0f / ((float)sqrt(var) + eps);
     for (int m = m0; m < m1; ++m) {
-        for (int t = threadIdx.x; t < T; t += kRowThreads) {
+        float a = 0.0f;
+        for (int t = threadIdx.x; t < tmax; t += kRowThreads) {
             const long long i = (long long)m * tmax + t;
-            base[i] = (base[i] - mean) * rstd;
+            float z = 0.0f;
+            if (t < T) { z = (base[i] - mean) * rstd; base[i] = z; }
+            if (tgt) a += fabsf(z - tgt[i]);
         }
         if (threadIdx.x == 0) {
             stats[((long long)n * n_mels + m) * 2 + 0] = mean;
             stats[((long long)n * n_mels + m) * 2 + 1] = rstd;
+        }
+        if (tgt) {                                  // block-uniform
+            const double tot = block_sum((double)a, red);
+            if (threadIdx.x == 0) l1_rows[(long long)n * n_mels + m] = (float)tot;
         }
     }
 }
@@ -522,15 +541,23 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <int KMAX>
 __global__ void __launch_bounds__(32 * kRowWarps)
 cmvn_fwd_rows(float* __restrict__ out, float* __restrict__ stats, const int32_t* __restrict__ lengths,
-              int n_mels, int rows, int tmax, float eps, long long wave_len) {
+              int n_mels, int rows, int tmax, float eps, long long wave_len,
+              const float* __restrict__ l1_target, float* __restrict__ l1_rows) {
     const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const int n = row / n_mels;
     const int T = frames_of(lengths, n, tmax, wave_len);
     float* base = out + (long long)row * tmax;
+    const float* tgt = l1_target ? l1_target + (long long)row * tmax : nullptr;
     if (T == 0) {
         if (lane == 0) { stats[2 * (long long)row] = 0.0f; stats[2 * (long long)row + 1] = 1.0f; }
+        if (tgt) {
+            float a = 0.0f;
+            for (int t = lane; t < tmax; t += 32) a += fabsf(tgt[t]);
+            const double tot = warp_sum((double)a);
+            if (lane == 0) l1_rows[row] = (float)tot;
+        }
         return;
     }
     float v[KMAX];
@@ -550,12 +577,19 @@ cmvn_fwd_rows(float* __restrict__ out, float* __restrict__ stats, const int32_t*
     }
     const double var = warp_sum((double)q) / (double)(T - 1);
     const float rstd = 1.0f / ((float)sqrt(var) + eps);
-#pragma unroll
+    float a = 0.0f;                                 // optional epilogue: sum |Z - target| of the row (L1Loss_mask,
+#pragma unroll                                      // model.py:19-31), while Z is in registers: Z is read once
     for (int k = 0; k < KMAX; ++k) {
         const int t = lane + 32 * k;
-        if (t < T) base[t] = (v[k] - mean) * rstd;
+        const float z = t < T ? (v[k] - mean) * rstd : 0.0f;
+        if (t < T) base[t] = z;
+        if (tgt && t < tmax) a += fabsf(z - tgt[t]);
     }
     if (lane == 0) { stats[2 * (long long)row] = mean; stats[2 * (long long)row + 1] = rstd; }
+    if (tgt) {                                      // warp-uniform
+        const double tot = warp_sum((double)a);
+        if (lane == 0) l1_rows[row] = (float)tot;
+    }
 }
 
 template <int KMAX>
@@ -616,14 +650,22 @@ cmvn_bwd_rows(const float* __restrict__ z, const float* __restrict__ stats,
 template <int K>
 __global__ void __launch_bounds__(kRowThreads)
 cmvn_fwd_block(float* __restrict__ out, float* __restrict__ stats, const int32_t* __restrict__ lengths,
-               int n_mels, int tmax, float eps, long long wave_len) {
+               int n_mels, int tmax, float eps, long long wave_len,
+               const float* __restrict__ l1_target, float* __restrict__ l1_rows) {
     __shared__ double red[kRowThreads / 32];
     const int row = blockIdx.x;
     const int n = row / n_mels;
     const int T = frames_of(lengths, n, tmax, wave_len);
     float* base = out + (long long)row * tmax;
+    const float* tgt = l1_target ? l1_target + (long long)row * tmax : nullptr;
     if (T == 0) {                                   // block-uniform
         if (threadIdx.x == 0) { stats[2 * (long long)row] = 0.0f; stats[2 * (long long)row + 1] = 1.0f; }
+        if (tgt) {
+            float a = 0.0f;
+            for (int t = threadIdx.x; t < tmax; t += kRowThreads) a += fabsf(tgt[t]);
+            const double tot = block_sum((double)a, red);
+            if (threadIdx.x == 0) l1_rows[row] = (float)tot;
+        }
         return;
     }
     float v[K];
@@ -643,12 +685,19 @@ cmvn_fwd_block(float* __restrict__ out, float* __restrict__ stats, const int32_t
     }
     const double var = block_sum((double)q, red) / (double)(T - 1);
     const float rstd = 1.0f / ((float)sqrt(var) + eps);
+    float a = 0.0f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int t = threadIdx.x + kRowThreads * k;
-        if (t < T) base[t] = (v[k] - mean) * rstd;
+        const float z = t < T ? (v[k] - mean) * rstd : 0.0f;
+        if (t < T) base[t] = z;
+        if (tgt && t < tmax) a += fabsf(z - tgt[t]);
     }
     if (threadIdx.x == 0) { stats[2 * (long long)row] = mean; stats[2 * (long long)row + 1] = rstd; }
+    if (tgt) {                                      // block-uniform
+        const double tot = block_sum((double)a, red);
+        if (threadIdx.x == 0) l1_rows[row] = (float)tot;
+    }
 }
 
 // ---- block-per-row backward for rows too long for one warp's registers: the row is read ONCE,
@@ -760,12 +809,13 @@ static const k1_bwd_fn kBwdI16[4] = { nullptr, lmfb_k1<kMaskReim, true, 5, 3, fa
 // vs 28.9 us, backward 22.9 vs 27.1 us, step 47.5 vs 54.3 us).
 static const K1Variant kVariants[] = {
 #ifdef LMFB_ONLY_W5
-    LMFB_VARIANT(5, 3), LMFB_VARIANT(5, 3), LMFB_VARIANT(5, 3), LMFB_VARIANT(8, 2),
+    LMFB_VARIANT(5, 3), LMFB_VARIANT(4, 3), LMFB_VARIANT(5, 3), LMFB_VARIANT(8, 2),
 #else
     LMFB_VARIANT(5, 3), LMFB_VARIANT(4, 3), LMFB_VARIANT(6, 3), LMFB_VARIANT(8, 2),
 #endif
 };
 constexpr int kFwdVariantBig = 0, kFwdVariantSmall = 3, kBwdVariantBig = 0, kBwdVariantSmall = 3;
+constexpr int kBwdVariantGradWave = 1;
 constexpr long long kSmallTiles = 148LL * 2 * 2;            // two rounds of the eight-warp shape
 
 static int variant_of_warps(int warps) {
@@ -968,6 +1018,9 @@ extern "C" int aas_lmfb_forward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io*
     if (!out || (cm != 0 && !stats)) return AAS_LMFB_E_NULL;
     if (((uintptr_t)out | (uintptr_t)stats) & 3u) return AAS_LMFB_E_ALIGN;
     if (!plan->fwd.walkable && !io->mel_dev) return AAS_LMFB_E_MEL;
+    if ((io->l1_target != nullptr) != (io->l1_rows != nullptr)) return AAS_LMFB_E_NULL;
+    if (io->l1_target && cm == 0) return AAS_LMFB_E_FLAGS;          // the epilogue lives in the CMVN kernel
+    if (((uintptr_t)io->l1_target | (uintptr_t)io->l1_rows) & 3u) return AAS_LMFB_E_ALIGN;
     DeviceScope scope(io->device);
     if (scope.rc) return scope.rc;
     cudaStream_t stream = (cudaStream_t)io->cuda_stream;
@@ -977,6 +1030,7 @@ extern "C" int aas_lmfb_forward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io*
     fill_args(a, io);
     a.out = out;
     a.tab_dev = io->tables;
+    a.frame_lens = io->frame_lens;
 #ifdef LMFB_TIMELINE
     { const char* e = getenv("AAS_LMFB_TIMELINE_FWD"); a.timeline = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
 #endif
@@ -997,18 +1051,18 @@ extern "C" int aas_lmfb_forward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io*
         const int32_t* lengths = io->lengths;
         const unsigned blocks = (unsigned)((rows + kRowWarps - 1) / kRowWarps);
         if (cm == 1 && tmax <= 32 * 8) {
-            cmvn_fwd_rows<8><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len);
+            cmvn_fwd_rows<8><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len, io->l1_target, io->l1_rows);
         } else if (cm == 1 && tmax <= 32 * 24) {
-            cmvn_fwd_rows<24><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len);
+            cmvn_fwd_rows<24><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len, io->l1_target, io->l1_rows);
         } else if (cm == 1 && tmax <= 32 * 32) {
-            cmvn_fwd_rows<32><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len);
+            cmvn_fwd_rows<32><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len, io->l1_target, io->l1_rows);
         } else if (cm == 1 && tmax <= 32 * 48) {
-            cmvn_fwd_rows<48><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len);
+            cmvn_fwd_rows<48><<<blocks, 32 * kRowWarps, 0, stream>>>(out, stats, lengths, plan->n_mels, rows, tmax, eps, io->wave_len, io->l1_target, io->l1_rows);
         } else if (cm == 1 && tmax <= kRowThreads * 24) {
-            cmvn_fwd_block<24><<<(unsigned)rows, kRowThreads, 0, stream>>>(out, stats, lengths, plan->n_mels, tmax, eps, io->wave_len);
+            cmvn_fwd_block<24><<<(unsigned)rows, kRowThreads, 0, stream>>>(out, stats, lengths, plan->n_mels, tmax, eps, io->wave_len, io->l1_target, io->l1_rows);
         } else {
             dim3 grid(cm == 1 ? plan->n_mels : 1, n);
-            cmvn_fwd<<<grid, kRowThreads, 0, stream>>>(out, stats, lengths, plan->n_mels, tmax, eps, (int)cm, io->wave_len);
+            cmvn_fwd<<<grid, kRowThreads, 0, stream>>>(out, stats, lengths, plan->n_mels, tmax, eps, (int)cm, io->wave_len, io->l1_target, io->l1_rows);
         }
         rc = (int)cudaPeekAtLastError();
     }
@@ -1080,7 +1134,9 @@ extern "C" int aas_lmfb_backward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io
 #endif
     const long long units = (long long)n * io->n_ch;
     const bool small = units * a.tiles_per_utt <= kSmallTiles;
-    const K1Variant& v = kVariants[i16 ? 0 : (plan->vbwd >= 0 ? plan->vbwd : (small ? kBwdVariantSmall : kBwdVariantBig))];
+    // (with the waveform gradient: four warps per tile -- 168 registers, no spills; measured 0.65 vs 0.73 ms on 256 x 10 s)
+    const K1Variant& v = kVariants[i16 ? 0 : (plan->vbwd >= 0 ? plan->vbwd : grad_wave ? kBwdVariantGradWave
+                                                                 : (small ? kBwdVariantSmall : kBwdVariantBig))];
     if (mask == AAS_LMFB_MASK_NONE) { a.mask_r = a.mask_i = (const float*)io->wave; a.gr = a.gi = nullptr; a.msf = (unsigned)tmax; a.msn = 0; }   // never dereferenced
     a.gwave = grad_wave;
     if (grad_wave) {                                             // the kernel ADDS (overlapping frames, reflect padding)
@@ -1263,6 +1319,14 @@ extern "C" int aas_l1_abs_sum(const float* a, const float* b, const uint8_t* mas
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     l1_abs_partial<<<(unsigned)blocks, kL1Threads, 0, stream>>>(a, b, mask, total, c, tmax, partial);
     l1_abs_final<<<1, kL1Threads, 0, stream>>>(partial, (int)blocks, out);
+    return (int)cudaPeekAtLastError();
+}
+
+// sum of the per-row partial sums the forward's L1 epilogue wrote (aas_lmfb_io.l1_rows), in a fixed order
+extern "C" int aas_l1_rows_sum(const float* rows, int count, float* out, void* cuda_stream) {
+    if (!rows || !out) return AAS_LMFB_E_NULL;
+    if (count < 0) return AAS_LMFB_E_SHAPE;
+    l1_abs_final<<<1, kL1Threads, 0, (cudaStream_t)cuda_stream>>>(rows, count, out);
     return (int)cudaPeekAtLastError();
 }
 

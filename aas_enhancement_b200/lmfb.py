@@ -144,7 +144,7 @@ class LMFB(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, wave, lengths, mask_r, mask_i, plan, window, mask_mode="reim",
-                cmvn_mode="per_bin", eps=0.0, tmax=None, mel_dev=None):
+                cmvn_mode="per_bin", eps=0.0, tmax=None, mel_dev=None, l1_target=None):
         if not wave.is_cuda:
             raise RuntimeError("LMFB is CUDA-only (sm_100a); there is no CPU fallback")
         dev = wave.device
@@ -204,28 +204,40 @@ class LMFB(torch.autograd.Function):
         flags = _lib.MASK_MODES[mask_mode] | _lib.CMVN_MODES[cmvn_mode] | (_lib.WAVE_I16 if wave.dtype == torch.int16 else 0)
         out = torch.empty((n, plan.n_mels, tmax), dtype=torch.float32, device=dev)
         stats = torch.empty((n, plan.n_mels, 2), dtype=torch.float32, device=dev)
+        frame_lens = torch.empty((n,), dtype=torch.int32, device=dev)      # written by the kernel (no torch arithmetic per call)
+        l1_rows = None
+        if l1_target is not None:                      # L1Loss_mask epilogue of the CMVN kernel: Z is read once
+            if cmvn_mode == "none":
+                raise ValueError("l1_target needs a CMVN mode (the epilogue lives in the CMVN kernel)")
+            _check_f32_cuda("l1_target", l1_target, dev)
+            if tuple(l1_target.shape) != (n, plan.n_mels, tmax):
+                raise ValueError("l1_target must be (N, n_mels, Tmax)")
+            l1_target = l1_target.detach().contiguous()
+            l1_rows = torch.empty((n, plan.n_mels), dtype=torch.float32, device=dev)
         io = _lib.make_io(flags=flags, device=dev.index if dev.index is not None else -1, n=n, n_ch=n_ch, tmax=tmax,
                           eps=float(eps), wave=wave.data_ptr(), wave_stride=_row_stride(wave, n_ch),
                           wave_stride_ch=wave.stride(1) if wave.dim() == 3 else 0, wave_len=lmax,
                           lengths=lengths.data_ptr(), mask_r=_ptr(mask_r), mask_i=_ptr(mask_i),
                           mask_stride_n=msn, mask_stride_f=msf, window=window.data_ptr(), mel_dev=_ptr(mel_dev),
                           out=out.data_ptr(), stats=stats.data_ptr(), tables=plan.tables(dev),
+                          l1_target=_ptr(l1_target), l1_rows=_ptr(l1_rows), frame_lens=frame_lens.data_ptr(),
                           cuda_stream=torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(lib.aas_lmfb_forward_ex(plan.handle, ctypes.byref(io)))
-        frame_lens = torch.clamp(1 + torch.div(torch.clamp(lengths, max=lmax), HOP, rounding_mode="floor"), max=tmax)
-        frame_lens = torch.where(lengths >= 1, frame_lens, torch.zeros_like(frame_lens)).to(torch.int32)
         ctx.plan, ctx.flags, ctx.eps, ctx.tmax, ctx.n_ch = plan, flags, float(eps), tmax, n_ch
         ctx.strides = (msn, msf)
         ctx.save_for_backward(wave, lengths, mask_r, mask_i, window, out, stats, mel_dev)
         ctx.mark_non_differentiable(frame_lens)
+        if l1_rows is not None:
+            ctx.mark_non_differentiable(l1_rows)
+            return out, frame_lens, l1_rows
         return out, frame_lens
 
     @staticmethod
-    def backward(ctx, grad_out, _grad_lens):
+    def backward(ctx, grad_out, _grad_lens, _grad_rows=None):
         wave, lengths, mask_r, mask_i, window, out, stats, mel_dev = ctx.saved_tensors
         want_wave = ctx.needs_input_grad[0]
         if mask_r is None and not want_wave:
-            return (None,) * 11
+            return (None,) * 12
         lib = _lib.load()
         dev = wave.device
         n, plan, tmax, n_ch = wave.shape[0], ctx.plan, ctx.tmax, ctx.n_ch
@@ -250,7 +262,8 @@ class LMFB(torch.autograd.Function):
             if gw is None:
                 wave = wave.contiguous()
                 gw = torch.empty_like(wave)
-            gw.zero_()                                     # (the library zeroes what it accumulates into; this covers a caller-chosen smaller tmax)
+            if HOP * tmax < lmax:                          # (the library zeroes the first min(Lmax, 160 tmax) samples of every
+                gw.zero_()                                 #  row; only a caller-chosen smaller tmax leaves a tail)
         io = _lib.make_io(flags=ctx.flags, device=dev.index if dev.index is not None else -1, n=n, n_ch=n_ch, tmax=tmax,
                           eps=ctx.eps, wave=wave.data_ptr(), wave_stride=_row_stride(wave, n_ch),
                           wave_stride_ch=wave.stride(1) if wave.dim() == 3 else 0, wave_len=lmax,
@@ -260,7 +273,7 @@ class LMFB(torch.autograd.Function):
                           grad_mask_r=_ptr(gr), grad_mask_i=_ptr(gi), grad_wave=_ptr(gw), workspace=ws.data_ptr(),
                           tables=plan.tables(dev), cuda_stream=torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(lib.aas_lmfb_backward_ex(plan.handle, ctypes.byref(io)))
-        return gw, None, gr, gi, None, None, None, None, None, None, None
+        return gw, None, gr, gi, None, None, None, None, None, None, None, None
 
 
 def _dense_strides(wave):
@@ -342,9 +355,13 @@ class LMFBFrontEnd(torch.nn.Module):
                     n_mels=int(self.mel_basis.shape[0]), mask_mode=self.mask_mode,
                     cmvn_mode=self.cmvn_mode, eps=self.eps)
 
-    def forward(self, wave, lengths, mask_r=None, mask_i=None, tmax=None):
+    def forward(self, wave, lengths, mask_r=None, mask_i=None, tmax=None, l1_target=None):
+        """-> ``(features, frame_lens)``; with ``l1_target`` (the ``target`` of the ``L1Loss_mask`` that
+        follows, e.g. the clean features in trainer_DCE.py) -> ``(features, frame_lens, l1_rows)``: the
+        per-row sums ``sum_t |Z - target|`` formed by the CMVN kernel while Z is in registers; hand them to
+        ``L1Loss_mask()(features, target, mask, rows=l1_rows)`` and Z is not read again for the loss."""
         return LMFB.apply(wave, lengths, mask_r, mask_i, self.plan, self.window,
-                          self.mask_mode, self.cmvn_mode, self.eps, tmax, self.mel_basis)
+                          self.mask_mode, self.cmvn_mode, self.eps, tmax, self.mel_basis, l1_target)
 
     @torch.no_grad()
     def stft(self, wave, lengths, tmax=None):

@@ -19,7 +19,7 @@ from . import _lib
 
 class _L1AbsSum(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, input, target, mask_or_none):
+    def forward(ctx, input, target, mask_or_none, rows=None):
         if not input.is_cuda:
             raise RuntimeError("L1Loss_mask is CUDA-only (sm_100a); there is no CPU fallback")
         lib = _lib.load()
@@ -33,12 +33,20 @@ class _L1AbsSum(torch.autograd.Function):
             m = mask_or_none.contiguous().to(torch.uint8)
             if m.shape != (n, 1, tmax):
                 raise ValueError("mask must be (N, 1, Tmax)")
-        partial = torch.empty(lib.aas_l1_partial_count(), dtype=torch.float32, device=a.device)
         out = torch.empty(1, dtype=torch.float32, device=a.device)
         with torch.cuda.device(a.device):
-            rc = lib.aas_l1_abs_sum(a.data_ptr(), b.data_ptr(), None if m is None else m.data_ptr(),
-                                    n, c, tmax, partial.data_ptr(), out.data_ptr(),
-                                    torch.cuda.current_stream(a.device).cuda_stream)
+            stream = torch.cuda.current_stream(a.device).cuda_stream
+            if rows is not None and m is None:
+                # the per-row sums come from the front-end's CMVN kernel (LMFBFrontEnd(..., l1_target=target)):
+                # only the (N*C)-term final sum is left, `input` is not read again
+                r = rows.contiguous().float()
+                if r.numel() != n * c:
+                    raise ValueError("rows must hold one partial sum per (utterance, channel) row")
+                rc = lib.aas_l1_rows_sum(r.data_ptr(), n * c, out.data_ptr(), stream)
+            else:
+                partial = torch.empty(lib.aas_l1_partial_count(), dtype=torch.float32, device=a.device)
+                rc = lib.aas_l1_abs_sum(a.data_ptr(), b.data_ptr(), None if m is None else m.data_ptr(),
+                                        n, c, tmax, partial.data_ptr(), out.data_ptr(), stream)
         _lib.check(rc)
         ctx.save_for_backward(a, b, m)
         return out[0]
@@ -52,7 +60,7 @@ class _L1AbsSum(torch.autograd.Function):
         ga = torch.empty_like(a) if need_a else None
         gb = torch.empty_like(b) if need_b else None
         if ga is None and gb is None:
-            return None, None, None
+            return None, None, None, None
         scale = grad.reshape(1).to(torch.float32).contiguous()
         with torch.cuda.device(a.device):
             rc = lib.aas_l1_abs_grad(a.data_ptr(), b.data_ptr(), None if m is None else m.data_ptr(),
@@ -61,7 +69,7 @@ class _L1AbsSum(torch.autograd.Function):
                                      None if gb is None else gb.data_ptr(),
                                      torch.cuda.current_stream(a.device).cuda_stream)
         _lib.check(rc)
-        return ga, gb, None
+        return ga, gb, None, None
 
 
 class L1Loss_mask(torch.nn.Module):
@@ -72,14 +80,18 @@ class L1Loss_mask(torch.nn.Module):
         super().__init__()
         self.fix_masking = fix_masking
 
-    def forward(self, input, target, mask):
+    def forward(self, input, target, mask, rows=None):
+        """``rows``: optional per-row sums ``sum_t |input - target|`` from the front-end's epilogue
+        (``LMFBFrontEnd.forward(..., l1_target=target)``); the loss value then costs one tiny kernel and
+        ``input`` is not read again (not with ``fix_masking``, whose sum skips the padded frames)."""
         mask_sum = mask.sum()
         if bool(mask[0][0][0] == 0):                      # data_as_0 = True (model.py:25)
             n_element = mask.nelement() - mask_sum
         else:                                             # the reference hits an UnboundLocalError here
             raise RuntimeError("L1Loss_mask: mask[0][0][0] != 0 -- nElement is undefined in the reference "
                                "(model.py:25-26); batches are length-sorted, so the first frame is never padding")
-        err_sum = _L1AbsSum.apply(input, target, mask if self.fix_masking else None)
+        err_sum = _L1AbsSum.apply(input, target, mask if self.fix_masking else None,
+                                  None if self.fix_masking else rows)
         loss = err_sum / n_element
         return loss, n_element
 

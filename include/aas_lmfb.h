@@ -122,6 +122,12 @@ typedef struct aas_lmfb_io {
     void*          cuda_stream;
     void* const*   prof;            /* optional 4 cudaEvent_t recorded around the two kernels          */
     const void*    tables;          /* optional: device tables filled by aas_lmfb_plan_upload          */
+    const float*   l1_target;       /* forward, optional (needs a CMVN mode): (N, M, Tmax) target of the
+                                     * L1Loss_mask that follows (model.py:19-31) ...                     */
+    float*         l1_rows;         /* ... and (N, M) floats that receive sum_t |Z - target| of every row,
+                                     * formed while Z is in registers (Z is read once); aas_l1_rows_sum
+                                     * adds them up in a fixed order                                     */
+    int32_t*       frame_lens;      /* forward, optional: (N,) receives the frame counts T_n                 */
 } aas_lmfb_io;
 
 int aas_lmfb_forward_ex(const aas_lmfb_plan* plan, const aas_lmfb_io* io);
@@ -198,6 +204,8 @@ int aas_lmfb_stft(const aas_lmfb_plan* plan,
 int aas_l1_partial_count(void);
 int aas_l1_abs_sum(const float* a, const float* b, const uint8_t* mask, int n, int c, int tmax,
                    float* partial, float* out, void* cuda_stream);
+/* Sum of `count` per-row partial sums (aas_lmfb_io.l1_rows) into one float, deterministic. */
+int aas_l1_rows_sum(const float* rows, int count, float* out, void* cuda_stream);
 /* d/da and d/db of scale * sum|a - b|: grad_a = scale * sign(a - b), grad_b = -grad_a (either may be
  * NULL); `scale` is a device scalar so that no host sync is needed. */
 int aas_l1_abs_grad(const float* a, const float* b, const uint8_t* mask, int n, int c, int tmax,

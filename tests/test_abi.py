@@ -78,7 +78,7 @@ def test_io_struct_matches_the_header(lib):
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"([a-z_0-9]+)\s*;", body)
     assert names == [f[0] for f in _lib.IO._fields_]
-    assert ctypes.sizeof(_lib.IO) == 8 * 4 + 8 * 21
+    assert ctypes.sizeof(_lib.IO) == 8 * 4 + 8 * 24
 
 
 def test_argument_errors_do_not_touch_the_gpu(lib):

@@ -803,3 +803,37 @@ def test_utterance_longer_than_the_register_resident_cmvn(be):
     b = _synth.make_batch(1, 16000 * 34, seed=34)
     assert b["tmax"] == 3401
     _check(be, b, "reim", "per_bin")
+
+
+@pytest.mark.parametrize("seconds", [3, 17, 34])
+def test_l1_epilogue_of_the_cmvn_kernel(be, seconds):
+    """SURVEY 8(f) rank 1 as written: L1Loss_mask (model.py:19-31) as an epilogue of the CMVN kernel.  The
+    per-row sums |Z - target| are formed while Z is in registers (warp-per-row, block-per-row and the
+    three-pass kernel: 301 / 1,701 / 3,401 frames); loss, nElement and the gradients equal the stand-alone
+    loss on the same tensors (value to float32 summation-order accuracy) and the oracle."""
+    b = _synth.make_batch(3, 16000 * seconds, seed=50 + seconds, ragged=True)
+    fe = _fe(be, "reim", "per_bin")
+    wave, lengths, mr, mi = _dev(b, "reim")
+    rs = np.random.RandomState(seconds)
+    target = torch.from_numpy(rs.randn(3, 40, b["tmax"]).astype(np.float32)).cuda()
+    z, fl, rows = fe(wave, lengths, mr, mi, l1_target=target)
+    mask = torch.zeros(3, 1, b["tmax"], dtype=torch.uint8, device="cuda")
+    for i in range(3):
+        mask[i, :, int(fl[i]):] = 1
+    loss_f, n_f = be.L1Loss_mask()(z, target, mask, rows=rows)
+    loss_f.backward()
+    g_fused = mr.grad.clone()
+    mr.grad = None
+    mi.grad = None
+    z2, _ = fe(wave, lengths, mr, mi)
+    assert torch.equal(z, z2)                                            # the epilogue does not change Z
+    loss_s, n_s = be.L1Loss_mask()(z2, target, mask)
+    loss_s.backward()
+    assert int(n_f) == int(n_s)
+    assert abs(float(loss_f) - float(loss_s)) < 2e-6 * abs(float(loss_s))
+    assert torch.equal(g_fused, mr.grad)                                 # same gradient kernels, same scale ...
+    want, want_n = orc.l1loss_mask(z.detach().cpu().numpy(), target.cpu().numpy(), mask.cpu().numpy())
+    assert int(n_f) == want_n and abs(float(loss_f) - want) < 1e-5 * want
+    # per-row sums against numpy
+    ref_rows = np.abs(z.detach().cpu().numpy().astype(np.float64) - target.cpu().numpy()).sum(axis=2)
+    assert orc.rel_err(rows.cpu().numpy(), ref_rows) < 1e-5

@@ -20,6 +20,25 @@ for mode in ("reim", "power", "none"):
     s, _ = fe.stft(wave, lengths)
     torch.cuda.synchronize()
     print(mode, float(z.abs().sum()), float(s.abs().sum()))
+# this round's paths: int16 PCM waves, two channels, a dense (generic) basis, the waveform gradient
+import numpy as np
+b = _synth.make_batch(3, 9000, seed=6, ragged=True)
+lengths = torch.from_numpy(b["lengths"]).cuda()
+g = torch.from_numpy(b["grad_out"]).cuda()
+def masks(rows=161):
+    rs = np.random.RandomState(1)
+    return (torch.from_numpy(rs.rand(3, rows, b["tmax"]).astype(np.float32)).cuda().requires_grad_(True),
+            torch.from_numpy(rs.rand(3, rows, b["tmax"]).astype(np.float32)).cuda().requires_grad_(True))
+fe = LMFBFrontEnd(mask_mode="reim", cmvn_mode="per_bin").cuda()
+pcm = torch.from_numpy(np.round(b["wave"] * 32768).clip(-32768, 32767).astype(np.int16)).cuda()
+mr, mi = masks(); z, _ = fe(pcm, lengths, mr, mi); z.backward(g); print("int16", float(z.abs().sum()))
+w2 = torch.from_numpy(np.stack([b["wave"], b["wave"][::-1].copy()], axis=1)).cuda()
+mr, mi = masks(322); z, _ = fe(w2, lengths, mr, mi); z.backward(g); print("2ch", float(z.abs().sum()))
+fd = LMFBFrontEnd(mel_basis=np.random.RandomState(2).rand(40, 161) * 0.02, mask_mode="reim", cmvn_mode="per_bin").cuda()
+mr, mi = masks(); z, _ = fd(torch.from_numpy(b["wave"]).cuda(), lengths, mr, mi); z.backward(g); print("dense", float(z.abs().sum()))
+wg = torch.from_numpy(b["wave"]).cuda().requires_grad_(True)
+mr, mi = masks(); z, _ = fe(wg, lengths, mr, mi); z.backward(g); print("grad_wave", float(wg.grad.abs().sum()))
+torch.cuda.synchronize()
 PY
 for tool in memcheck racecheck; do
   echo "== $tool"

@@ -18,7 +18,8 @@ P = os.path.join(ROOT, "profiles")
 tag = sys.argv[1]
 os.makedirs(P, exist_ok=True)
 
-for name in (f"bench_{tag}.json", f"bench_sweep_{tag}.json", f"host_{tag}.txt", f"smi_{tag}.txt",
+for name in (f"bench_{tag}.json", f"bench_sweep_{tag}.json", f"bench_paired_{tag}.json", f"bench_ref_{tag}.json",
+             f"modes_{tag}.txt", f"host_{tag}.txt", f"smi_{tag}.txt",
              f"pytest_{tag}.txt", f"smoke_{tag}.txt", f"launches_{tag}.csv"):
     src = os.path.join(G, name)
     if os.path.exists(src):
@@ -117,10 +118,12 @@ with open(os.path.join(P, f"{tag}_sass_summary.txt"), "w") as f:
                 if t:
                     op = t[1] if t[0].startswith("@") and len(t) > 1 else t[0]
                     ops[op.split(".")[0].rstrip(";")] += 1
-        f.write(f"{sum(ops.values()):6d}  {k}\n        " + " ".join(f"{o}:{c}" for o, c in ops.most_common(14)) + "\n")
+        extra = " ".join(f"{o}:{ops[o]}" for o in ("UBLKCP", "UGETNEXTWORKID", "SYNCS", "LDGSTS") if ops[o])
+        f.write(f"{sum(ops.values()):6d}  {k}\n        " + " ".join(f"{o}:{c}" for o, c in ops.most_common(14)) +
+                (f"   | sm_100 / async: {extra}" if extra else "") + "\n")
 for k, lines in blocks.items():
-    if "lmfb_k1ILi1ELb1ELi4ELi4" in k or "lmfb_k1ILi1ELb0ELi3ELi5" in k:      # the default reim kernels
-        short = "k1_bwd_reim_w4" if "Lb1" in k else "k1_fwd_reim_w3"
+    if "lmfb_k1ILi1ELb1ELi5ELi3ELb0ELb0" in k or "lmfb_k1ILi1ELb0ELi5ELi3ELb0ELb0" in k:      # the default reim kernels
+        short = "k1_bwd_reim_w5" if "Lb1ELi5" in k else "k1_fwd_reim_w5"
         with open(os.path.join(P, f"{tag}_sass_{short}.txt"), "w") as f:
             f.write(f"# {k}\n")
             import re as _re
