@@ -804,12 +804,14 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, float* __restrict__ pl, 
 // ---------------------------------------------------------------------------------------
 struct Walk { float acc0, acc1; float* cur; };
 
-// one bin; `h`: the band moves on by one filter before this bin
+// one bin; `h` (warp-uniform): the band moves on by one filter before this bin.  A real branch: three
+// bins in four take the short path (two FMAs); the predicated, branch-free form (store, two selects and a
+// pointer select per bin) was 1 - 2 % slower in the forward.
 LMFB_HD void walk_bin(Walk& wk, float p, float2 wgt, bool h) {
-    sts_if_noalias(wk.cur, wk.acc0, h);
-    wk.acc0 = h ? wk.acc1 : wk.acc0;
-    wk.acc1 = h ? 0.0f : wk.acc1;
-    wk.cur += h ? kRow : 0;
+    if (h) {
+        sts_if_noalias(wk.cur, wk.acc0, true);
+        wk.acc0 = wk.acc1; wk.acc1 = 0.0f; wk.cur += kRow;
+    }
     wk.acc0 = fmaf(wgt.x, p, wk.acc0);
     wk.acc1 = fmaf(wgt.y, p, wk.acc1);
 }
@@ -840,8 +842,8 @@ LMFB_HD void phase3_walk(int w, float* __restrict__ pl, const FwdSmem& sm, const
     const float* pp = pl + g0 * 8 * kRow;
     const float2* wp = sm.w + g0 * 8;
     if (!tab.multi) {
-        // eight bins at a time: all sixteen loads of a group are in flight before the predicated
-        // hand-over chain starts.  (A piece-by-piece walk with counted loops and no per-bin predicates
+        // eight bins at a time: all sixteen loads of a group are in flight before the hand-over
+        // chain starts.  (A piece-by-piece walk with counted loops and no per-bin predicates
         // was measured: 20 % fewer instructions in this phase, but twice its duration -- short dependent
         // load -> FMA loops leave a warp nothing to overlap; what a phase costs is its latency.)
 #pragma unroll 1
