@@ -285,6 +285,23 @@ def run(args, world, rank, local, dev):
         t = torch.tensor([ms_allreduce], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_allreduce = float(t.item())
+    # ... and by itself, all ranks released together by a barrier (the in-step figure also contains the wait for
+    # the slowest rank of a 590 ms step)
+    ms_ar_iso = None
+    if world > 1:
+        iso = []
+        for _ in range(5):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(job.grads.flat, op=dist.ReduceOp.AVG)
+            e1.record()
+            torch.cuda.synchronize()
+            iso.append(e0.elapsed_time(e1))
+        t = torch.tensor([statistics.median(iso)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_ar_iso = float(t.item())
     # the front-end work of the step in isolation
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)
@@ -338,7 +355,8 @@ def run(args, world, rank, local, dev):
             "ms_frontend_isolated": ms_fe, "ms_models_and_losses": ms_nosync - ms_fe,
             "frontend_share_of_step": ms_fe / ms_step,
             "allreduce_bytes": grad_bytes,
-            "allreduce_busbw_gbs": (2 * (world - 1) / world) * grad_bytes / (ms_allreduce / 1e3) / 1e9 if world > 1 and ms_allreduce > 0 else None,
+            "ms_allreduce_isolated": ms_ar_iso,
+            "allreduce_busbw_gbs": (2 * (world - 1) / world) * grad_bytes / (ms_ar_iso / 1e3) / 1e9 if ms_ar_iso else None,
             "params": job.n_params, "nccl_ranks": world,
             "sync_batchnorm": world > 1,
             "models": "stand-ins re-declared from model.py:203-252 (G with a 322-row mask head, D) and :256-335 "

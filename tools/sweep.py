@@ -22,6 +22,24 @@ import torch.distributed as dist              # noqa: E402
 import bench                                  # noqa: E402
 from aas_enhancement_b200 import LMFBFrontEnd, _lib   # noqa: E402
 
+import json                                   # noqa: E402
+CPU_CACHE = os.path.join(ROOT, "gpurun_out", "cpu_sweep_cache.json")
+if "--cpu-only" in sys.argv:
+    # the CPU column, measured by ONE process with the machine to itself (under torchrun the other ranks'
+    # polling threads would share the cores); cached for the multi-GPU runs on the same box
+    secs_list = (1, 6, 30) if "--quick" in sys.argv else (1, 2, 4, 6, 10, 15, 30)
+    out = {}
+    for secs in secs_list:
+        n_s = 32 if secs <= 10 else 8
+        step, _ = bench._cpu_step_fns(n_s, int(secs * bench.SR), False)
+        torch.set_num_threads(os.cpu_count() or 1)
+        t, _ = bench._median_time(step, warm=2, reps=5, budget_s=20.0)
+        out[str(secs)] = n_s * secs / t
+        print("cpu", secs, "s:", out[str(secs)], "audio-s/s")
+    os.makedirs(os.path.dirname(CPU_CACHE), exist_ok=True)
+    json.dump({"cores": os.cpu_count(), "audio_s_per_s": out}, open(CPU_CACHE, "w"))
+    sys.exit(0)
+
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -45,6 +63,10 @@ class _NoClock:
 
 def cpu_rate(secs):
     """audio-s/s of the batched CPU path at this utterance length (32 utterances, all threads)."""
+    if not cpu_cache and os.path.exists(CPU_CACHE):
+        cpu_cache.update({int(k): v for k, v in json.load(open(CPU_CACHE))["audio_s_per_s"].items()})
+    if secs not in cpu_cache and world > 1:
+        return float("nan")                     # (never time the CPU path next to seven other ranks)
     if secs not in cpu_cache:
         n_s = 32 if secs <= 10 else 8
         step, _ = bench._cpu_step_fns(n_s, int(secs * bench.SR), False)
