@@ -16,7 +16,7 @@ DEPS = [SRC, os.path.join(HERE, "csrc", "lmfb_core.cuh"), os.path.join(HERE, "cs
 LIB = os.path.join(HERE, "libaas_lmfb.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "--split-compile", "0"]      # (the kernels are optimised in parallel)
 
 
 def find_nvcc() -> str:

@@ -113,7 +113,7 @@ with open(os.path.join(P, f"{tag}_sass_summary.txt"), "w") as f:
         ops = collections.Counter()
         for l in lines:
             parts = l.split("*/")
-            if len(parts) >= 2 and parts[0].strip().startswith("/*") and len(parts[0].strip()) == 6:
+            if len(parts) >= 2 and parts[0].strip().startswith("/*") and len(parts[0].strip()) in (6, 7):
                 t = parts[1].strip().split()
                 if t:
                     op = t[1] if t[0].startswith("@") and len(t) > 1 else t[0]
@@ -129,7 +129,7 @@ for k, lines in blocks.items():
             import re as _re
             keep = []
             for l in lines:
-                if _re.match(r"\s+/\*[0-9a-f]{4}\*/", l):            # instruction line: drop the hex encoding
+                if _re.match(r"\s+/\*[0-9a-f]{4,5}\*/", l):          # instruction line: drop the hex encoding
                     keep.append(_re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip())
                 elif l.strip().startswith(".") or "headerflags" in l:
                     keep.append(l.rstrip())
