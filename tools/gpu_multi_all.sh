@@ -1,4 +1,5 @@
 #!/bin/bash
+TAG=${1:-r3}
 # 8-GPU box: BASELINE.json configs[2] (AAS step), configs[3] (paired, 2/4/8) and configs[4] (sweep) under torchrun
 mkdir -p gpurun_out/scaling
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
@@ -18,16 +19,16 @@ PY
 }
 nvidia-smi -L | head -8
 echo "== CPU column of the sweep (one process)"; timeout 600 python tools/sweep.py --cpu-only --quick 2>&1 | tail -4
-run r3_chime_n1 1 0 --steps 20 --warmup 5 --no-cpu --no-large
-for np in 2 4 8; do run r3_chime_n$np $np 2960$np --steps 20 --warmup 5 --no-cpu --no-large; done
-run r3_paired_n1 1 0 --workload paired_30x6s --steps 20 --warmup 5 --no-large --no-cpu
-for np in 2 4 8; do run r3_paired_n$np $np 2961$np --workload paired_30x6s --steps 20 --warmup 5 --no-large --no-cpu; done
-run r3_sweep256_n1 1 0 --workload sweep_256x10s --steps 20 --warmup 5 --no-cpu --no-e2e
-run r3_sweep256_n8 8 29621 --workload sweep_256x10s --steps 20 --warmup 5 --no-cpu --no-e2e
-run r3_aas_n1 1 0 --workload aas_step_30x6s --steps 6 --warmup 3
-run r3_aas_n8 8 29631 --workload aas_step_30x6s --steps 6 --warmup 3
+run ${TAG}_chime_n1 1 0 --steps 20 --warmup 5 --no-cpu --no-large
+for np in 2 4 8; do run ${TAG}_chime_n$np $np 2960$np --steps 20 --warmup 5 --no-cpu --no-large; done
+run ${TAG}_paired_n1 1 0 --workload paired_30x6s --steps 20 --warmup 5 --no-large --no-cpu
+for np in 2 4 8; do run ${TAG}_paired_n$np $np 2961$np --workload paired_30x6s --steps 20 --warmup 5 --no-large --no-cpu; done
+run ${TAG}_sweep256_n1 1 0 --workload sweep_256x10s --steps 20 --warmup 5 --no-cpu --no-e2e
+run ${TAG}_sweep256_n8 8 29621 --workload sweep_256x10s --steps 20 --warmup 5 --no-cpu --no-e2e
+run ${TAG}_aas_n1 1 0 --workload aas_step_30x6s --steps 6 --warmup 3
+run ${TAG}_aas_n8 8 29631 --workload aas_step_30x6s --steps 6 --warmup 3
 echo "== host-fabric ceiling"
-timeout 300 python tools/pcie_ceiling.py | tee gpurun_out/scaling/r3_pcie_n1.json
-timeout 300 $TR --nproc-per-node 8 --master-port 29651 tools/pcie_ceiling.py 2>/dev/null | tail -1 | tee gpurun_out/scaling/r3_pcie_n8.json
+timeout 300 python tools/pcie_ceiling.py | tee gpurun_out/scaling/${TAG}_pcie_n1.json
+timeout 300 $TR --nproc-per-node 8 --master-port 29651 tools/pcie_ceiling.py 2>/dev/null | tail -1 | tee gpurun_out/scaling/${TAG}_pcie_n8.json
 echo "== sweep quick at 8 GPUs"
-timeout 900 $TR --nproc-per-node 8 --master-port 29641 tools/sweep.py gpurun_out/scaling/r3_sweep_n8.md --quick 2>&1 | tail -14
+timeout 900 $TR --nproc-per-node 8 --master-port 29641 tools/sweep.py gpurun_out/scaling/${TAG}_sweep_n8.md --quick 2>&1 | tail -14
