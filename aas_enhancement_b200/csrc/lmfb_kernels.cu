@@ -149,6 +149,8 @@ __device__ __forceinline__ void decode_unit(const K1Args& a, int tile, int ch_fw
     u.real = u.t0 < u.T;
 }
 
+// (Which warps take the 17 mod W longer shares of pass 2 does not matter: giving them to the highest warp
+// indices instead of the lowest was measured, 0.4385 vs 0.4345 ms per step on 256 x 10 s.)
 template <int MASK, bool BWD, int W, int CTAS, bool GW = false, bool I16 = false>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf<BWD>::Param tab) {

@@ -452,7 +452,7 @@ def test_l1loss_on_front_end_output_full_size(be):
 
 def test_dynamic_and_static_tile_schedules_agree():
     """A launch with more tiles than resident CTAs is scheduled with cluster launch control; the
-    result must be bit-identical to the static round-robin schedule (AAS_LMFB_SCHED=static)."""
+    result must be bit-identical to the static round-robin schedule (`set_tuning(static_schedule=True)`)."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
