@@ -119,10 +119,16 @@ struct FwdTab {                                // forward kernel parameter
     // "walkable" bases (banded-2: bin f feeds filters ml(f) (weight wl) and ml(f)+1 (weight wh) with ml
     // non-decreasing -- every triangular filterbank); weights carry the 1/4 that undoes X' = 2X
     float2   w[kBins];                         // (wl, wh) of bin f
-    uint8_t  hmask[kGroups + 4];               // bit i of byte g: the band moves on before bin 8g+i (adv != 0)
+    uint8_t  hmask[kGroups + 8];               // bit f & 7 of byte f >> 3: the band moves on before bin f (adv != 0); read as
+                                               // 32-bit words at any bit offset, hence the zero word behind bin 160
     uint8_t  adv[kBins + 3];                   // ml(f) - ml(f-1): filters completed before bin f (0 for f = 0)
-    uint8_t  lo[kMaxW];                        // phase 3: warp w produces partial sums of filters lo[w] .. hi[w]
-    uint8_t  hi[kMaxW];                        //          (hi may exceed n_mels - 1; lo > hi: warp has no bins)
+    // phase 3: warp w OWNS filters lo[w] .. hi[w] (lo > hi: none) and walks every bin that feeds one of
+    // them, [b0[w], b1[w]): the bins whose lower filter is lo - 1 .. hi.  The walk delivers a sum for every
+    // filter m0[w] .. m1[w] = ml(b0) .. ml(b1 - 1) + 1 (m0 > m1: none); those of lo - 1 and hi + 1 are
+    // incomplete and belong to the neighbours.
+    uint8_t  lo[kMaxW], hi[kMaxW];
+    uint8_t  b0[kMaxW], b1[kMaxW];
+    uint8_t  m0[kMaxW], m1[kMaxW];
     // any other basis: filter m is the row [lo, lo + cnt) of the caller's device matrix
     uint32_t row[kMaxMels];                    // lo | cnt << 8
     int      n_mels;
@@ -137,7 +143,7 @@ struct BwdTab {                                // backward kernel parameter, per
 };
 // shared-memory image: the per-step constants of the algorithm, then the parameter above
 struct alignas(16) StepEnt { uint32_t f[5]; float sn[5]; float cs[5]; uint32_t pad_; };     // 64 B
-struct alignas(16) FwdSmem { StepEnt step[17]; float2 w[kBins]; uint8_t hmask[kGroups + 4]; uint8_t adv[kBins + 3]; uint32_t row[kMaxMels]; };
+struct alignas(16) FwdSmem { StepEnt step[17]; float2 w[kBins]; uint8_t hmask[kGroups + 8]; uint8_t adv[kBins + 3]; uint32_t row[kMaxMels]; };
 struct alignas(16) BwdSmem { StepEnt step[17]; float w[17][5][4]; uint32_t d[17][5][2]; };
 constexpr int kTabBytesFwd = (int)((sizeof(FwdSmem) + 15) / 16 * 16);
 constexpr int kTabBytesBwd = (int)((sizeof(BwdSmem) + 15) / 16 * 16);
@@ -149,14 +155,12 @@ template <bool BWD> struct TabBytes { static constexpr int value = BWD ? kTabByt
 // the table copy's barrier (8), pad (8) | raw buffer
 constexpr int kCtlBytes = 48;
 constexpr int kRawBytes_ = (kTile + 1) * 164 * 4;
-constexpr int smem_bytes(bool bwd) { return kScratchBytes + (bwd ? kTabBytesBwd : kTabBytesFwd) + kCtlBytes + kRawBytes_; }
+// backward: + the tile's dE rows (up to kDeSmemRows mel rows x 32 frames), see stage_de()
+constexpr int kDeSmemRows = 48;
+constexpr int kDeSmemBytes = kDeSmemRows * 32 * 4;
+constexpr int smem_bytes(bool bwd) { return kScratchBytes + (bwd ? kTabBytesBwd : kTabBytesFwd) + kCtlBytes + kRawBytes_ + (bwd ? kDeSmemBytes : 0); }
 // the device-resident image of both shared-memory tables (aas_lmfb_plan_upload): forward, then backward
 constexpr int kTabBlobBytes = kTabBytesFwd + kTabBytesBwd;
-
-// phase 3: warp w of W walks the 8-bin groups [p3_g0, p3_g1); the last warp also takes bin 160
-LMFB_CX int p3_per(int W) { return (kGroups + W - 1) / W; }
-LMFB_CX int p3_g0(int W, int w) { return w * p3_per(W) < kGroups ? w * p3_per(W) : kGroups; }
-LMFB_CX int p3_g1(int W, int w) { return (w + 1) * p3_per(W) < kGroups ? (w + 1) * p3_per(W) : kGroups; }
 
 LMFB_CX int slot_of_packed(int j) {            // j in [0,160): packed-sample index -> PFA input slot
     return ((3 * (j % 5)) % 5) * 32 + ((13 * (j & 31)) & 31);
@@ -167,7 +171,7 @@ LMFB_CX int bin_of(int k2, int k1) { return (96 * k1 + 65 * k2) % 160; }
 // pass 2: the first 32 floats of slot row f (row f = columns f mod 32 of sub-transform f / 32 is
 // one of the rows the producing step has just consumed); bin 160 has a row of its own behind the slots
 LMFB_CX int p_off(int f) { return f * kRow; }
-// float offset of partial-sum row r of phase 3 (walk): second 32 floats of slot row 1 + r
+// float offset of sum row r of phase 3 (walk): second 32 floats of slot row 1 + r
 LMFB_CX int e_off(int r) { return (1 + r) * kRow + kTile; }
 
 // 'reflect' padding index (numpy semantics, any offset, length >= 1)
@@ -253,6 +257,22 @@ __device__ __forceinline__ void mbar_arrive_tx(uint64_t* bar, unsigned bytes) {
 #else
 static inline void bulk_row(void* dst, const void* src, unsigned bytes, uint64_t*) { memcpy(dst, src, bytes); }
 static inline void mbar_arrive_tx(uint64_t*, unsigned) {}
+#endif
+
+#ifdef __CUDACC__
+// backward: the tile's dE rows (n_mels x 32 frames, 5 KB for 40 mels) straight into shared memory with 4-byte
+// asynchronous copies; pass 2 re-reads every row eight times, and with three 67 KB tiles per SM only 26 KB
+// of L1 are left to catch those re-reads (measured on 256 x 10 s: backward 0.2053 -> 0.2021 ms).
+// Rows w, w + W, ...; `de` = this lane's (clamped) column of row 0.
+template <int W>
+__device__ __forceinline__ void stage_de(int w, int lane, const float* __restrict__ de, unsigned sem_bytes, int n_mels,
+                                         float* __restrict__ de_s) {
+#pragma unroll 4
+    for (int m = w; m < n_mels; m += W)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(de_s + m * 32 + lane)),
+                     "l"(at_row(de, (uint32_t)m, sem_bytes)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
 struct StageLane {                      // per-lane constants of the slot map (used by the adjoint staging)
@@ -503,7 +523,7 @@ LMFB_HD void tables_fill(FwdSmem* sm, const FwdTab& tab, int tid, int nthreads) 
     if (tab.walkable) {
         copy_words(reinterpret_cast<uint32_t*>(sm->w), reinterpret_cast<const uint32_t*>(tab.w), 2 * kBins, tid, nthreads);
         copy_words(reinterpret_cast<uint32_t*>(sm->hmask), reinterpret_cast<const uint32_t*>(tab.hmask),
-                   (kGroups + 4 + kBins + 3) / 4, tid, nthreads);                // hmask and adv are adjacent in both structs
+                   (kGroups + 8 + kBins + 3) / 4, tid, nthreads);                // hmask and adv are adjacent in both structs
     } else {
         copy_words(sm->row, tab.row, kMaxMels, tid, nthreads);
     }
@@ -567,7 +587,17 @@ LMFB_HD void load_masks(const StepEnt& se, const float* __restrict__ mr, const f
 // 200 instructions that need nothing from global memory) run while these loads are in flight.
 // de1 = dE + one row.
 LMFB_HD void load_d(const uint32_t (*drow)[2], const float* __restrict__ dE, const float* __restrict__ de1,
-                    unsigned sem_bytes, StepD& in) {
+                    unsigned sem_bytes, StepD& in, const float* __restrict__ de_s = nullptr) {
+    if (de_s) {                                              // the tile's dE rows are in shared memory (this lane's column)
+#pragma unroll
+        for (int k1 = 0; k1 < 5; ++k1) {
+            const float* pf = de_s + drow[k1][0] * 32u;
+            const float* pp = de_s + drow[k1][1] * 32u;
+            in.d0[k1] = pf[0]; in.d1[k1] = pf[32];
+            in.d0[5 + k1] = pp[0]; in.d1[5 + k1] = pp[32];
+        }
+        return;
+    }
 #pragma unroll
     for (int k1 = 0; k1 < 5; ++k1) {
         const uint32_t df = drow[k1][0], dp = drow[k1][1];
@@ -586,9 +616,9 @@ LMFB_HD void load_d(const uint32_t (*drow)[2], const float* __restrict__ dE, con
 template <int MASK, bool BWD, bool GW, class SM>
 LMFB_HD void pass2_step(int k2, float2* __restrict__ col, float* __restrict__ pl, const SM& sm, const StepMasks& in,
                         const float* __restrict__ dE, const float* __restrict__ de1, unsigned sem_bytes, unsigned msf_bytes,
-                        float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
+                        float* __restrict__ gr, float* __restrict__ gi, bool inrow, const float* __restrict__ de_s = nullptr) {
     StepD d;
-    if constexpr (BWD && MASK != kStftOut) load_d(sm.d[k2], dE, de1, sem_bytes, d);
+    if constexpr (BWD && MASK != kStftOut) load_d(sm.d[k2], dE, de1, sem_bytes, d, de_s);
     const int kb = (32 - k2) & 31;
     const float2* ca = col + k2 * kPitch;
     const float2* cb = col + kb * kPitch;
@@ -776,7 +806,7 @@ template <int W, int MASK, bool BWD, int AHEAD, bool GW, class SM>
 LMFB_HD void fft_pass2(int w, float2* __restrict__ col, float* __restrict__ pl, const SM& sm, MaskSets<AHEAD>& ms,
                        const float* __restrict__ mr, const float* __restrict__ mi,
                        const float* __restrict__ dE, unsigned sem_bytes, unsigned msf_bytes,
-                       float* __restrict__ gr, float* __restrict__ gi, bool inrow) {
+                       float* __restrict__ gr, float* __restrict__ gi, bool inrow, const float* __restrict__ de_s = nullptr) {
     const float* de1 = at_row(dE, 1u, sem_bytes);
     constexpr int R = AHEAD + 1;                            // register sets in rotation
 #pragma unroll 1
@@ -787,19 +817,24 @@ LMFB_HD void fft_pass2(int w, float2* __restrict__ col, float* __restrict__ pl, 
             if (k <= 16) {
                 const int kn = k + AHEAD * W;               // the step AHEAD later goes to set (i + AHEAD) mod R
                 if (kn <= 16) load_masks<MASK, BWD, GW>(sm.step[kn], mr, mi, msf_bytes, ms.m[(i + AHEAD) % R]);
-                pass2_step<MASK, BWD, GW>(k, col, pl, sm, ms.m[i], dE, de1, sem_bytes, msf_bytes, gr, gi, inrow);
+                pass2_step<MASK, BWD, GW>(k, col, pl, sm, ms.m[i], dE, de1, sem_bytes, msf_bytes, gr, gi, inrow, de_s);
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 3 (forward).  A: warp w walks its range of bins in ascending order with two running sums
-// (filters ml(f), ml(f)+1); when the band moves on, the finished sum goes to this warp's partial
-// rows.  A warp writes every row lo[w] .. hi[w] of its own set exactly once (row index = filter +
-// 2w, so the sets of neighbouring warps, which share at most two filters, never collide).
-// B (after a block barrier): filter m = sum of the partial rows of the warps whose range covers
-// m, then log1p + store.
+// phase 3 (forward).  Every warp OWNS a run of whole filters (FwdTab::lo .. hi, a cost-balanced
+// partition made on the host) and walks, in ascending order with two running sums (filters ml(f),
+// ml(f) + 1), every bin that feeds one of them; when the band moves on, the finished sum goes to a
+// row of the warp's own.  Neighbouring warps both walk the bins between their two border filters
+// (one inter-centre interval: ~10 % more bins in total), which buys: no partial sums, no block barrier
+// between the walk and the log1p -- a lane reads back only what it wrote itself -- and one
+// shared-memory load per filter in the finish.  (History: bins dealt in equal shares, partial sums
+// in W row sets, a barrier, and a finish that added up to W partial rows per filter: 4.2 k warp
+// instructions per tile and 8 % of the kernel's stall samples on that barrier.)
+// Rows: filter m of warp w is slot row 1 + 2w + m (second half): the row sets of neighbouring warps,
+// which overlap by the two border filters, never collide.
 //   out : out + n*stride_n + t (row m at + m*som); inrow: t < Tmax; valid: t < T_i
 // ---------------------------------------------------------------------------------------
 struct Walk { float acc0, acc1; float* cur; };
@@ -831,84 +866,103 @@ LMFB_HD void walk_bin_multi(Walk& wk, float p, float2 wgt, unsigned adv) {
     wk.acc1 = fmaf(wgt.y, p, wk.acc1);
 }
 
-template <int W>
-LMFB_HD void phase3_walk(int w, float* __restrict__ pl, const FwdSmem& sm, const FwdTab& tab) {
-    const int g0 = p3_g0(W, w), g1 = p3_g1(W, w);
-    const bool last = w == W - 1;
-    if (g0 >= g1 && !last) return;
+// hand-over bits of the eight bins f .. f + 7 (bit i: the band moves on before bin f + i)
+LMFB_HD unsigned hand_bits(const uint8_t* hmask, int f) {
+    const uint32_t* hb = reinterpret_cast<const uint32_t*>(hmask);
+    const unsigned long long two = ((unsigned long long)hb[(f >> 5) + 1] << 32) | hb[f >> 5];
+    return (unsigned)(two >> (f & 31)) & 0xffu;
+}
+
+// the walk over this warp's bins; leaves a sum in row er + m * kRow for every filter m0 .. m1
+LMFB_HD void phase3_walk(int w, const float* __restrict__ pl, float* __restrict__ er, const FwdSmem& sm, const FwdTab& tab) {
+    const int b0 = tab.b0[w], b1 = tab.b1[w];
+    if (b0 >= b1) return;
     Walk wk;
     wk.acc0 = wk.acc1 = 0.0f;
-    wk.cur = pl + e_off(2 * w) + (int)tab.lo[w] * kRow;
-    const float* pp = pl + g0 * 8 * kRow;
-    const float2* wp = sm.w + g0 * 8;
+    wk.cur = er + (int)tab.m0[w] * kRow;
     if (!tab.multi) {
         // eight bins at a time: all sixteen loads of a group are in flight before the hand-over
         // chain starts.  (A piece-by-piece walk with counted loops and no per-bin predicates
         // was measured: 20 % fewer instructions in this phase, but twice its duration -- short dependent
         // load -> FMA loops leave a warp nothing to overlap; what a phase costs is its latency.)
+        const float* pp = pl + b0 * kRow;
+        const float2* wp = sm.w + b0;
+        int f = b0;
 #pragma unroll 1
-        for (int g = g0; g < g1; ++g) {
+        for (; f + 8 <= b1; f += 8) {
             float p[8]; float2 wg[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { p[i] = pp[i * kRow]; wg[i] = wp[i]; }
-            unsigned hm = sm.hmask[g];
-            if (g == g0) hm &= ~1u;                        // nothing is complete before the warp's first bin
+            unsigned hm = hand_bits(sm.hmask, f);
+            if (f == b0) hm &= ~1u;                        // nothing is complete before the warp's first bin
 #pragma unroll
             for (int i = 0; i < 8; ++i) walk_bin(wk, p[i], wg[i], (hm >> i) & 1u);
             pp += 8 * kRow; wp += 8;
         }
-        if (last) walk_bin(wk, pl[p_off(kBins - 1)], sm.w[kBins - 1], g1 > g0 && (sm.hmask[kGroups] & 1u));
+        if (f < b1) {                                      // the last 1 .. 7 bins
+            const int rem = b1 - f;
+            float p[7]; float2 wg[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                p[i] = 0.0f; wg[i] = make_float2(0.0f, 0.0f);
+                if (i < rem) { p[i] = pp[i * kRow]; wg[i] = wp[i]; }
+            }
+            unsigned hm = hand_bits(sm.hmask, f);
+            if (f == b0) hm &= ~1u;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) if (i < rem) walk_bin(wk, p[i], wg[i], (hm >> i) & 1u);
+        }
     } else {
 #pragma unroll 1
-        for (int f = g0 * 8; f < g1 * 8; ++f) walk_bin_multi(wk, pl[f * kRow], sm.w[f], f == g0 * 8 ? 0u : sm.adv[f]);
-        if (last) walk_bin_multi(wk, pl[p_off(kBins - 1)], sm.w[kBins - 1], g1 > g0 ? sm.adv[kBins - 1] : 0u);
+        for (int f = b0; f < b1; ++f) walk_bin_multi(wk, pl[f * kRow], sm.w[f], f == b0 ? 0u : sm.adv[f]);
     }
     sts_if_noalias(wk.cur, wk.acc0, true);
     sts_if_noalias(wk.cur + kRow, wk.acc1, true);
 }
 
-template <int W>
-LMFB_HD float finish_sum(const float* __restrict__ pl, const FwdTab& tab, int m) {
-    float e = 0.0f;
-#pragma unroll
-    for (int wi = 0; wi < W; ++wi)
-        if (m >= (int)tab.lo[wi] && m <= (int)tab.hi[wi]) e += pl[e_off(2 * wi) + m * kRow];
-    return e;
+// the sum of filter m as the walk of this warp left it (filters no bin of the walk reached are empty)
+LMFB_HD float walked_sum(const float* __restrict__ er, int m, int m0, int m1) {
+    return (m >= m0 && m <= m1) ? er[m * kRow] : 0.0f;
 }
 
 template <int W>
-LMFB_HD void phase3_finish(int w, const float* __restrict__ pl, const FwdTab& tab,
-                           float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid,
-                           bool first = true, bool last = true) {
-    const int n_mels = tab.n_mels;
-    const int per = (n_mels + W - 1) / W;
-    const int m_lo = w * per, m_hi = m_lo + per < n_mels ? m_lo + per : n_mels;
+LMFB_HD void phase3_own(int w, float* __restrict__ pl, const FwdSmem& sm, const FwdTab& tab,
+                        float* __restrict__ out, unsigned som_bytes, bool inrow, bool valid,
+                        bool first = true, bool last = true) {
+    float* er = pl + e_off(2 * w);
+    phase3_walk(w, pl, er, sm, tab);
+#ifdef __CUDACC__
+    asm volatile("" ::: "memory");                         // the rows are written behind the optimiser's back (sts_if_noalias)
+#endif
+    const int m_lo = tab.lo[w], m_end = (int)tab.hi[w] + 1;
+    const int m0 = tab.m0[w], m1 = tab.m1[w];
+    if (m_lo >= m_end) return;
     float* op = at_row(out, (uint32_t)m_lo, som_bytes);
     if (first && last) {
         // single channel (the common case): four filters in flight -- the log1p chains are what this
-        // phase waits for
+        // part waits for
         int m = m_lo;
 #pragma unroll 1
-        for (; m + 4 <= m_hi; m += 4) {
+        for (; m + 4 <= m_end; m += 4) {
             float e[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) e[i] = finish_sum<W>(pl, tab, m + i);
+            for (int i = 0; i < 4; ++i) e[i] = walked_sum(er, m + i, m0, m1);
 #pragma unroll
             for (int i = 0; i < 4; ++i) e[i] = valid ? log1pf(e[i]) : 0.0f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) { st_if(op, e[i], inrow); op = at_row(op, 1u, som_bytes); }
         }
 #pragma unroll 1
-        for (; m < m_hi; ++m) {
-            const float e = finish_sum<W>(pl, tab, m);
+        for (; m < m_end; ++m) {
+            const float e = walked_sum(er, m, m0, m1);
             st_if(op, valid ? log1pf(e) : 0.0f, inrow);
             op = at_row(op, 1u, som_bytes);
         }
         return;
     }
 #pragma unroll 1
-    for (int m = m_lo; m < m_hi; ++m) {
-        float e = finish_sum<W>(pl, tab, m);
+    for (int m = m_lo; m < m_end; ++m) {
+        float e = walked_sum(er, m, m0, m1);
         if (!first) e += inrow ? *op : 0.0f;                 // multi-channel: partial sums of E travel through `out`
         const float y = last ? (valid ? log1pf(e) : 0.0f) : e;
         st_if(op, y, inrow);

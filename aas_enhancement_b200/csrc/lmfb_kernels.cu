@@ -167,6 +167,8 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
     uint64_t* raw_bar  = clc_bar + 1;
     uint64_t* tab_bar  = clc_bar + 2;
     float*    raw      = reinterpret_cast<float*>(reinterpret_cast<char*>(clc_resp) + kCtlBytes);
+    float*    de_buf   = raw + kRawBytes / 4;                  // backward: the tile's dE rows
+    const bool de_smem = BWD && MASK != kStftOut && tab.n_mels <= kDeSmemRows;
 #ifdef LMFB_TIMELINE
     unsigned long long gt_entry;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_entry));
@@ -208,7 +210,8 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         const long long mrow = (long long)u.n * a.msn + (long long)u.ch * kBins * a.msf;
         if (LMFB_NEEDS_MASK_R(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_r + mrow, a.msf, kBins, u.t0, a.tmax);
         if (LMFB_NEEDS_MASK_I(MASK, BWD, GW)) prefetch_rows_l2(threadIdx.x, kTile * W, a.mask_i + mrow, a.msf, kBins, u.t0, a.tmax);
-        if (BWD && MASK != kStftOut) prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)u.n * n_mels * som, som, n_mels, u.t0, a.tmax);
+        if (BWD && MASK != kStftOut && !de_smem)
+            prefetch_rows_l2(threadIdx.x, kTile * W, a.dE + (long long)u.n * n_mels * som, som, n_mels, u.t0, a.tmax);
     };
 
     int cur_tile = (int)blockIdx.x, cur_ch = 0;              // only these two cross the passes; a unit is decoded where it is used
@@ -297,6 +300,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
         float* po = a.out + row_nm;
         LMFB_OPAQUE(mr); LMFB_OPAQUE(mi); LMFB_OPAQUE(de); LMFB_OPAQUE(gr); LMFB_OPAQUE(gi); LMFB_OPAQUE(po);
 
+        if (BWD && de_smem) stage_de<W>(w, lane, de, som_bytes, n_mels, de_buf);
         mbar_wait(raw_bar, raw_phase);              // this unit's rows have landed
         raw_phase ^= 1u;
         LMFB_TICK(1);
@@ -309,6 +313,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
             for (int i = 0; i <= AHEAD; ++i) ms.m[i].vr[0] = valid ? 0.5f : 0.0f;
         }
         LMFB_TICK(3);
+        if (BWD && de_smem) cp_async_wait_all();
         __syncthreads();                            // the scratch is complete, the raw buffer is free
         LMFB_TICK(4);
 
@@ -333,7 +338,8 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
             }
         }
 
-        fft_pass2<W, MASK, BWD, AHEAD, GW>(w, col, pl, sm, ms, mr, mi, de, som_bytes, msf_bytes, gr, gi, inrow);
+        fft_pass2<W, MASK, BWD, AHEAD, GW>(w, col, pl, sm, ms, mr, mi, de, som_bytes, msf_bytes, gr, gi, inrow,
+                                           (BWD && de_smem) ? de_buf + lane : nullptr);
         if constexpr (BWD && GW) {                  // gradient into the waveform: adjoint pass 1, overlap-add
             static_assert(!(GW && I16), "an int16 wave takes no gradient");
             StageLane sl;
@@ -350,10 +356,7 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
             __syncthreads();
             LMFB_TICK(6);
             if (tab.walkable) {
-                phase3_walk<W>(w, pl, sm, tab);
-                __syncthreads();
-                LMFB_TICK(5);                   // (overwrites the pass-2 end stamp: phase 3 split A | B)
-                phase3_finish<W>(w, pl, tab, po, som_bytes, inrow, valid, cur.ch == 0, last_ch);
+                phase3_own<W>(w, pl, sm, tab, po, som_bytes, inrow, valid, cur.ch == 0, last_ch);
             } else {
                 phase3_gather<W>(w, pl, sm, n_mels, a.mel, po, som_bytes, inrow, valid, cur.ch == 0, last_ch);
             }

@@ -44,18 +44,52 @@ inline void build_fwd_tab(const float* mel, int n_mels, FwdTab* out, int* ml_out
     }
 }
 
-// forward phase 3 (walk) with W warps: warp w walks the 8-bin groups [p3_g0(W, w), p3_g1(W, w)), the last
-// warp also bin 160, and produces partial sums for filters lo[w] .. hi[w] = ml(first bin) ..
-// ml(last bin) + 1
+// forward phase 3 with W warps: the filters are dealt to the warps as W contiguous runs, warp w OWNS
+// filters lo[w] .. hi[w] and walks every bin that feeds one of them (the bins whose lower filter is
+// lo - 1 .. hi; ml is non-decreasing, so they are one range [b0, b1)).  The partition minimises the
+// largest per-warp cost, cost = kP3CostBin per walked bin + kP3CostFilter per owned filter (log1p +
+// store): the low filters of a mel basis have one or two bins each, the high ones ten and more.
+#ifndef LMFB_P3_COST_BIN
+#  define LMFB_P3_COST_BIN 8
+#endif
+#ifndef LMFB_P3_COST_FILTER
+#  define LMFB_P3_COST_FILTER 40
+#endif
+constexpr int kP3CostBin = LMFB_P3_COST_BIN, kP3CostFilter = LMFB_P3_COST_FILTER;
+
 inline void set_warp_ranges(FwdTab* tab, const int* ml, int warps) {
     if (warps < 1) warps = 1;
     if (warps > kMaxW) warps = kMaxW;
-    for (int w = 0; w < kMaxW; ++w) {
-        int b0 = p3_g0(warps, w) * 8, b1 = p3_g1(warps, w) * 8;              // bins [b0, b1)
-        if (w >= warps) b0 = b1 = 0;
-        if (w == warps - 1) { if (b0 >= b1) b0 = kBins - 1; b1 = kBins; }
-        tab->lo[w] = (uint8_t)(b0 < b1 ? ml[b0] : 255);
-        tab->hi[w] = (uint8_t)(b0 < b1 ? ml[b1 - 1] + 1 : 0);
+    const int M = tab->n_mels;
+    int below[kMaxMels + 2];                                  // below[m] = bins whose lower filter is < m
+    for (int m = 0; m <= M + 1; ++m) {
+        below[m] = 0;
+        for (int f = 0; f < kBins; ++f) if (ml[f] < m) ++below[m];
+    }
+    auto cost = [&](int a, int b) {                           // filters a .. b (inclusive), a <= b
+        return kP3CostBin * (below[b + 1] - below[a > 0 ? a - 1 : 0]) + kP3CostFilter * (b - a + 1);
+    };
+    // best[k][j]: filters [0, j) in k runs (runs may be empty), smallest possible largest cost
+    static thread_local int best[kMaxW + 1][kMaxMels + 1], cut[kMaxW + 1][kMaxMels + 1];
+    for (int j = 0; j <= M; ++j) { best[0][j] = j == 0 ? 0 : 0x3fffffff; cut[0][j] = 0; }
+    for (int k = 1; k <= warps; ++k)
+        for (int j = 0; j <= M; ++j) {
+            best[k][j] = best[k - 1][j]; cut[k][j] = j;       // run k empty
+            for (int i = 0; i < j; ++i) {
+                const int c = cost(i, j - 1), v = best[k - 1][i] > c ? best[k - 1][i] : c;
+                if (v < best[k][j]) { best[k][j] = v; cut[k][j] = i; }
+            }
+        }
+    int end = M;
+    for (int w = kMaxW - 1; w >= 0; --w) {
+        int a = 1, b = 0;                                     // none
+        if (w < warps) { a = cut[w + 1][end]; b = end - 1; end = a; }
+        tab->lo[w] = (uint8_t)a; tab->hi[w] = (uint8_t)b;
+        int b0 = 0, b1 = 0;
+        if (a <= b) { b0 = below[a > 0 ? a - 1 : 0]; b1 = below[b + 1]; }
+        tab->b0[w] = (uint8_t)b0; tab->b1[w] = (uint8_t)b1;
+        tab->m0[w] = (uint8_t)(b0 < b1 ? ml[b0] : 1);
+        tab->m1[w] = (uint8_t)(b0 < b1 ? ml[b1 - 1] + 1 : 0);
     }
 }
 

@@ -71,17 +71,10 @@ void emu_tile(const float* wave_row, int len, int t0, const float* window, bool 
         for (int w = 0; w < W; ++w)
             for (int lane = 0; lane < 32; ++lane) {
                 const int t = t0 + lane;
-                if (tab.walkable) phase3_walk<W>(w, reinterpret_cast<float*>(S.data()) + lane, sm, tab);
-                else phase3_gather<W>(w, reinterpret_cast<float*>(S.data()) + lane, sm, tab.n_mels, mel_dev,
-                                      out + t, som * 4u, t < tmax, t < T, first_ch, last_ch);
+                float* pl = reinterpret_cast<float*>(S.data()) + lane;
+                if (tab.walkable) phase3_own<W>(w, pl, sm, tab, out + t, som * 4u, t < tmax, t < T, first_ch, last_ch);
+                else phase3_gather<W>(w, pl, sm, tab.n_mels, mel_dev, out + t, som * 4u, t < tmax, t < T, first_ch, last_ch);
             }
-        if (tab.walkable)
-            for (int w = 0; w < W; ++w)
-                for (int lane = 0; lane < 32; ++lane) {
-                    const int t = t0 + lane;
-                    phase3_finish<W>(w, reinterpret_cast<float*>(S.data()) + lane, tab, out + t, som * 4u, t < tmax, t < T,
-                                     first_ch, last_ch);
-                }
     }
 }
 
