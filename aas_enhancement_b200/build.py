@@ -1,10 +1,21 @@
 """In-tree build of the C-ABI CUDA library (plain nvcc, no torch headers).
 
     python -m aas_enhancement_b200.build          # -> aas_enhancement_b200/libaas_lmfb.so
+
+The K1 kernels sit at the 128-register cap (three thread blocks of five warps per SM), and whether the
+default ones come out of the compiler WITHOUT a stack frame depends on how nvcc partitions this one
+translation unit: `--split-compile N` (parallel optimisation of the kernels) and the single-module
+build give different register allocations for the same source, and `--split-compile` is not even
+reproducible run to run.  A kernel with a stack frame needs local memory set up at launch (measured:
++1.6 us per step on the 30 x 6 s workload) and spills in the tile loop (measured: 3 % on 256 x 10 s).
+So the build CHECKS what it got: it reads ptxas' resource report, sums the stack frames of the hot
+kernels, and tries the next partitioning until the eight-warp kernels have none and the five-warp ones at most 16
+bytes (or keeps the best one seen).
 """
 from __future__ import annotations
 
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -16,7 +27,11 @@ DEPS = [SRC, os.path.join(HERE, "csrc", "lmfb_core.cuh"), os.path.join(HERE, "cs
 LIB = os.path.join(HERE, "libaas_lmfb.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "--split-compile", "0"]      # (the kernels are optimised in parallel)
+              "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# partitionings tried in turn (threads of --split-compile; 1 = the single-module build, deterministic)
+SPLITS = (8, 6, 4, 1)
+# the kernels every default call launches: lmfb_k1<reim, fwd|bwd, 5 warps x 3 | 8 warps x 2, no wave gradient, fp32 wave>
+HOT = ["lmfb_k1ILi1ELb%dELi%dELi%dELb0ELb0E" % (b, w, c) for b in (0, 1) for (w, c) in ((5, 3), (8, 2))]
 
 
 def find_nvcc() -> str:
@@ -33,16 +48,64 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
+def stack_report(ptxas_log: str) -> dict:
+    """{kernel: (stack frame bytes, registers)} from `ptxas -v` output."""
+    out, cur = {}, None
+    for line in ptxas_log.splitlines():
+        m = re.search(r"Compiling entry function '(\S+)'", line)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.search(r"(\d+) bytes stack frame", line)
+        if m and cur:
+            out[cur] = [int(m.group(1)), 0]
+            continue
+        m = re.search(r"Used (\d+) registers", line)
+        if m and cur and cur in out:
+            out[cur][1] = int(m.group(1))
+    return out
+
+
+def hot_stack_bytes(report: dict) -> int:
+    """Stack bytes of the hot kernels; those of the small-launch shape (8 warps), where the launch overhead of a
+    kernel with local memory is a visible share of the step, count a thousandfold."""
+    return sum(v[0] * (1000 if "ELi8ELi2E" in k else 1) for k, v in report.items() if any(h in k for h in HOT))
+
+
+GOOD_ENOUGH = 16      # a few scalars spilled once per tile in a five-warp kernel: not measurable
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    extra = os.environ.get("AAS_LMFB_NVCC_EXTRA", "").split()      # e.g. -DLMFB_ONLY_W3 for quick experiments
-    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", LIB]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    extra = os.environ.get("AAS_LMFB_NVCC_EXTRA", "").split()      # e.g. -DLMFB_ONLY_W5 for quick experiments
+    splits = [int(x) for x in os.environ.get("AAS_LMFB_SPLITS", "").split(",") if x] or list(SPLITS)
+    best = None                                                    # (stack bytes, path, log, split)
+    for i, split in enumerate(splits):
+        tmp = LIB + ".try%d" % i
+        cmd = [find_nvcc()] + NVCC_FLAGS + (["--split-compile", str(split)] if split != 1 else []) + extra + [SRC, "-o", tmp]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout)
+        rep = stack_report(res.stdout)
+        score = hot_stack_bytes(rep)
+        if verbose:
+            print("split-compile %d: stack frames of the hot kernels: %d bytes" % (split, score))
+        if best is None or score < best[0]:
+            if best is not None:
+                os.remove(best[1])
+            best = (score, tmp, res.stdout, split)
+        else:
+            os.remove(tmp)
+        if score <= GOOD_ENOUGH:
+            break
+    os.replace(best[1], LIB)
     if verbose:
-        print(res.stdout)
+        rep = stack_report(best[2])
+        for k in sorted(rep):
+            if any(h in k for h in HOT):
+                print("  %s: %d registers, %d bytes stack" % (k[:60], rep[k][1], rep[k][0]))
+        print("kept the --split-compile %d build" % best[3])
     return LIB
 
 

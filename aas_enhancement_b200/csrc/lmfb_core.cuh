@@ -319,11 +319,14 @@ LMFB_HD void stage_raw(int w, int lane, const void* __restrict__ wave_row_, int 
         if (lane == 0) {
             const Sample* src = wave_row + (long long)(t0 - 1 + w) * kHop;
             float* dst = raw + w * kRawPitch;
-            constexpr int kMine = (kTile + 1 + W - 1) / W;    // rows w, w + W, ... (the last may not exist)
+            // rows w, w + W, ...: kAll of them in every warp, one more in the first kMore warps (spelled out: left
+            // as `if (w + i * W < 33)` the tests fold, or not, with the optimiser's knowledge of the warp index)
+            constexpr int kAll = (kTile + 1) / W, kMore = (kTile + 1) % W;
 #pragma unroll
-            for (int i = 0; i < kMine; ++i)
-                if (w + i * W < kTile + 1) bulk_row(dst + i * W * kRawPitch, src + i * W * kHop, kRowBytes, bar);
-            mbar_arrive_tx(bar, (unsigned)(((kTile + 1 - w + W - 1) / W) * kRowBytes));
+            for (int i = 0; i < kAll; ++i) bulk_row(dst + i * W * kRawPitch, src + i * W * kHop, kRowBytes, bar);
+            const bool more = w < kMore;
+            if (more) bulk_row(dst + kAll * W * kRawPitch, src + kAll * W * kHop, kRowBytes, bar);
+            mbar_arrive_tx(bar, (unsigned)((kAll + (more ? 1 : 0)) * kRowBytes));
         }
         return;
     }
