@@ -423,6 +423,17 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
+__device__ __forceinline__ void block_sum2(double& a, double& b, double (*red)[2]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();                       // protect red[] from the previous use
+    if ((threadIdx.x & 31) == 0) { red[w][0] = a; red[w][1] = b; }
+    __syncthreads();
+    a = b = 0.0;
+    for (int i = 0; i < nw; ++i) { a += red[i][0]; b += red[i][1]; }
+}
+
 __device__ __forceinline__ int frames_of(const int32_t* lengths, int n, int tmax, long long wave_len) {
     int len = lengths[n];
     if (wave_len > 0 && (long long)len > wave_len) len = (int)wave_len;
@@ -621,6 +632,11 @@ cmvn_bwd_rows(const float* __restrict__ z, const float* __restrict__ stats,
     float* eb = dE + (long long)row * tmax;
     float g[KMAX], zz[KMAX];
     float sg = 0.0f, sgz = 0.0f;
+    float c1 = 0.0f, kk = 0.0f, mean = 0.0f, rstd = 1.0f;
+    if (mode != 0 && T > 0) {                       // fetched with the row, not behind the reductions
+        mean = stats[2 * (long long)row];
+        rstd = stats[2 * (long long)row + 1];
+    }
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         const int t = lane + 32 * k;
@@ -629,11 +645,8 @@ cmvn_bwd_rows(const float* __restrict__ z, const float* __restrict__ stats,
         sg += g[k];
         sgz = fmaf(g[k], zz[k], sgz);
     }
-    float c1 = 0.0f, kk = 0.0f, mean = 0.0f, rstd = 1.0f;
     if (mode != 0 && T > 0) {
         const double sg_d = warp_sum((double)sg), sgz_d = warp_sum((double)sgz);
-        mean = stats[2 * (long long)row];
-        rstd = stats[2 * (long long)row + 1];
         const double sigma = 1.0 / (double)rstd - (double)eps;
         c1 = (float)(sg_d / (double)T);
         kk = (float)(sgz_d / ((double)(T - 1) * sigma));
@@ -721,7 +734,7 @@ __global__ void __launch_bounds__(kRowThreads)
 cmvn_bwd_block(const float* __restrict__ z, const float* __restrict__ stats,
                const float* __restrict__ grad_out, float* __restrict__ dE,
                const int32_t* __restrict__ lengths, int n_mels, int tmax, float eps, int mode, long long wave_len) {
-    __shared__ double red[kRowThreads / 32];
+    __shared__ double red[kRowThreads / 32][2];
     const int row = blockIdx.x;
     const int n = row / n_mels;
     const int T = frames_of(lengths, n, tmax, wave_len);
@@ -730,6 +743,11 @@ cmvn_bwd_block(const float* __restrict__ z, const float* __restrict__ stats,
     float* eb = dE + (long long)row * tmax;
     float g[K], zz[K];
     float sg = 0.0f, sgz = 0.0f;
+    float c1 = 0.0f, kk = 0.0f, mean = 0.0f, rstd = 1.0f;
+    if (mode != 0 && T > 0) {                          // fetched with the row, not behind the reductions
+        mean = stats[2 * (long long)row];
+        rstd = stats[2 * (long long)row + 1];
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int t = threadIdx.x + kRowThreads * k;
@@ -738,13 +756,10 @@ cmvn_bwd_block(const float* __restrict__ z, const float* __restrict__ stats,
         sg += g[k];
         sgz = fmaf(g[k], zz[k], sgz);
     }
-    float c1 = 0.0f, kk = 0.0f, mean = 0.0f, rstd = 1.0f;
     if (mode != 0) {                                   // block-uniform
-        const double sg_d = block_sum((double)sg, red);
-        const double sgz_d = block_sum((double)sgz, red);
+        double sg_d = (double)sg, sgz_d = (double)sgz;
+        block_sum2(sg_d, sgz_d, red);                  // both sums behind one pair of barriers
         if (T > 0) {
-            mean = stats[2 * (long long)row];
-            rstd = stats[2 * (long long)row + 1];
             const double sigma = 1.0 / (double)rstd - (double)eps;
             c1 = (float)(sg_d / (double)T);
             kk = (float)(sgz_d / ((double)(T - 1) * sigma));
