@@ -174,7 +174,9 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_entry));
 #endif
     const int lane = threadIdx.x & 31;
-    const int w    = threadIdx.x >> 5;
+    // (through a shuffle from lane 0: the optimiser then knows that the warp index is the same in all lanes and
+    // keeps what is derived from it -- the operands of the bulk copies, table rows -- in uniform registers)
+    const int w    = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     // The range of the warp index decides how much of the per-warp dealing (rows of the staging, sub-transforms,
     // pass-2 steps) folds at compile time.  The optimiser derives it from __launch_bounds__ in some builds and
     // not in others (same source: parallel vs single-module compilation of this file gave 4,800 vs 4,896 vs

@@ -48,7 +48,8 @@ inline void build_fwd_tab(const float* mel, int n_mels, FwdTab* out, int* ml_out
 // filters lo[w] .. hi[w] and walks every bin that feeds one of them (the bins whose lower filter is
 // lo - 1 .. hi; ml is non-decreasing, so they are one range [b0, b1)).  The partition minimises the
 // largest per-warp cost, cost = kP3CostBin per walked bin + kP3CostFilter per owned filter (log1p +
-// store): the low filters of a mel basis have one or two bins each, the high ones ten and more.
+// store, done four filters at a time): the low filters of a mel basis have one or two bins each, the
+// high ones ten and more.
 #ifndef LMFB_P3_COST_BIN
 #  define LMFB_P3_COST_BIN 8
 #endif
@@ -67,7 +68,7 @@ inline void set_warp_ranges(FwdTab* tab, const int* ml, int warps) {
         for (int f = 0; f < kBins; ++f) if (ml[f] < m) ++below[m];
     }
     auto cost = [&](int a, int b) {                           // filters a .. b (inclusive), a <= b
-        return kP3CostBin * (below[b + 1] - below[a > 0 ? a - 1 : 0]) + kP3CostFilter * (b - a + 1);
+        return kP3CostBin * (below[b + 1] - below[a > 0 ? a - 1 : 0]) + kP3CostFilter * ((b - a + 4) / 4 * 4);   // (log1p in groups of four)
     };
     // best[k][j]: filters [0, j) in k runs (runs may be empty), smallest possible largest cost
     static thread_local int best[kMaxW + 1][kMaxMels + 1], cut[kMaxW + 1][kMaxMels + 1];
