@@ -38,9 +38,14 @@ fd = LMFBFrontEnd(mel_basis=np.random.RandomState(2).rand(40, 161) * 0.02, mask_
 mr, mi = masks(); z, _ = fd(torch.from_numpy(b["wave"]).cuda(), lengths, mr, mi); z.backward(g); print("dense", float(z.abs().sum()))
 wg = torch.from_numpy(b["wave"]).cuda().requires_grad_(True)
 mr, mi = masks(); z, _ = fe(wg, lengths, mr, mi); z.backward(g); print("grad_wave", float(wg.grad.abs().sum()))
+# rows of 813 frames: the block-per-row CMVN kernels (two sums behind one pair of barriers)
+bl = _synth.make_batch(2, 130000, seed=7, ragged=True)
+mrl = torch.from_numpy(bl["mask_r"]).cuda().requires_grad_(True); mil = torch.from_numpy(bl["mask_i"]).cuda().requires_grad_(True)
+z, _ = fe(torch.from_numpy(bl["wave"]).cuda(), torch.from_numpy(bl["lengths"]).cuda(), mrl, mil)
+z.backward(torch.from_numpy(bl["grad_out"]).cuda()); print("long rows", float(z.abs().sum()), float(mrl.grad.abs().sum()))
 torch.cuda.synchronize()
 PY
 for tool in memcheck racecheck; do
   echo "== $tool"
-  timeout 600 compute-sanitizer --tool $tool --kernel-regex kns=lmfb_k1 python /tmp/san.py 2>&1 | grep -v "^=========     at\|^=========     by\|Host Frame\|Saved host" | tail -25 | tee gpurun_out/sanitize_$tool.txt
+  timeout 600 compute-sanitizer --tool $tool --kernel-regex 'kns=lmfb_k1|cmvn_' python /tmp/san.py 2>&1 | grep -v "^=========     at\|^=========     by\|Host Frame\|Saved host" | tail -25 | tee gpurun_out/sanitize_$tool.txt
 done
