@@ -151,6 +151,22 @@ __device__ __forceinline__ void decode_unit(const K1Args& a, int tile, int ch_fw
 
 // (Which warps take the 17 mod W longer shares of pass 2 does not matter: giving them to the highest warp
 // indices instead of the lowest was measured, 0.4385 vs 0.4345 ms per step on 256 x 10 s.)
+// Measured and rejected in this kernel (256 x 10 s step, ms; builds with and without each change compared back
+// to back on the same box, each twice):
+//   * half steps for the self-paired columns 0 and 16 of pass 2 (one 5-point DFT, three outputs; the 17 steps
+//     then weigh 3 | 3 | 3 | 3.55 | 3.55 on five warps and 2 .. 2.1 on eight), tested inside the step loop and
+//     peeled in front of it: 0.4465 vs 0.4345, and 24.8 vs 22.8 us for the eight-warp forward on 30 x 6 s.
+//     Less work, and slower, in every build tried;
+//   * the next tile's FFT in registers BEFORE the barrier that frees the scratch (warps that finish a tile early
+//     start their next FFT instead of waiting; needs two answer slots for the launch-control unit and the dE
+//     staging behind that barrier): forward unchanged (0.1848 vs 0.1845), backward 0.2094 vs 0.1951.  With
+//     three thread blocks per SM the stall samples on a block barrier are not idle issue slots;
+//   * step constants and mel weights read from constant memory with the (now warp-uniform) step index instead
+//     of from the shared-memory image: forward 0.1950 vs 0.1846, backward 0.1992 vs 0.1931;
+//   * tile index and utterance length made warp-uniform with a shuffle (like the warp index): no change;
+//   * a 16-instruction log1p for non-negative arguments (2 atanh(x / (2 + x)) below 1/2, hardware log2 above)
+//     in place of log1pf (31 instructions, a tenth of the forward kernel's): 0.4135 - 0.4183 vs 0.4158 - 0.4163;
+//     the phase is bound by its dependent chains, not by issue slots.
 template <int MASK, bool BWD, int W, int CTAS, bool GW = false, bool I16 = false>
 __global__ void __launch_bounds__(kTile * W, CTAS)
 lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf<BWD>::Param tab) {
@@ -410,7 +426,11 @@ lmfb_k1(const __grid_constant__ K1Args a, const __grid_constant__ typename TabOf
 // Programmatic dependent launch of the second kernel of a call (CMVN behind K1, K1 behind the CMVN
 // gradient, its prologue + staging + pass 1 ahead of griddepcontrol.wait) was measured too, inside the
 // CUDA graph of the benchmark: 55.6 vs 54.9 us per step on 30 x 6 s, 0.4329 vs 0.4326 ms on 256 x 10 s:
-// nothing, as in round 1.)
+// nothing, as in round 1.
+// Block-per-row kernels with 16-byte accesses (head / aligned float4 body / tail, two float4 per thread for
+// 1,001 frames) were measured as well: forward 24.9 vs 20.8 us, backward 37.2 vs 33.1 us on 256 x 10 s -- a
+// quarter of the load instructions, but also a quarter of the bytes in flight per SM (4 KB per block of 128
+// threads against 16 KB for four warps holding a row each).)
 constexpr int kRowThreads = 128;
 
 __device__ __forceinline__ double block_sum(double v, double* red) {

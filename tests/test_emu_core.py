@@ -178,6 +178,27 @@ def _tables(emu, mel, warps=4):
     return fwd, bwd, walkable.value, banded.value
 
 
+def test_phase3_filter_partition(emu):
+    """Forward phase 3: the filters are dealt to the warps as contiguous runs that cover every filter exactly
+    once (mel_band.hpp: set_warp_ranges), whatever the basis and the number of warps."""
+    for n_mels in (40, 23, 64, 80, 128, 2):
+        mel = np.ascontiguousarray(orc.mel_filterbank(n_mels=n_mels) if n_mels > 2 else
+                                   np.stack([np.linspace(1, 0, 161), np.linspace(0, 1, 161)]), dtype=np.float32)
+        for warps in (1, 2, 3, 4, 5, 6, 8):
+            fwd = np.zeros_like(mel); bwd = np.zeros_like(mel)
+            walkable = ctypes.c_int(-1); banded = ctypes.c_int(-1)
+            lohi = np.zeros(16, np.int32)
+            assert emu.emu_mel_tables(mel.ctypes.data, n_mels, warps, fwd.ctypes.data, bwd.ctypes.data,
+                                      ctypes.byref(walkable), ctypes.byref(banded), lohi.ctypes.data) == 0
+            owned = []
+            for w in range(8):
+                lo, hi = int(lohi[2 * w]), int(lohi[2 * w + 1])
+                if w >= warps:
+                    assert lo > hi                       # warps that do not exist own nothing
+                owned += list(range(lo, hi + 1))
+            assert owned == list(range(n_mels)), (n_mels, warps, lohi)
+
+
 def test_mel_tables_reproduce_the_basis(emu):
     """The forward tables (walk or rows) and the backward (d, d+1) table, expanded back into dense
     matrices, are the basis itself: triangular filterbanks are walkable + banded, anything else is generic."""
