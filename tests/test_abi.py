@@ -115,3 +115,28 @@ def test_default_mel_and_window_match_oracle(lib):
     from aas_enhancement_b200 import slaney_mel_basis, hamming_window
     assert np.abs(slaney_mel_basis() - orc.mel_filterbank()).max() < 1e-15
     assert np.abs(hamming_window() - orc.hamming_window()).max() == 0
+
+
+def test_build_reads_the_stack_frames_of_the_hot_kernels():
+    """aas_enhancement_b200/build.py keeps a build only if ptxas reports no stack frame for the kernels every
+    default call launches (a kernel with local memory costs launch time and spills in the tile loop)."""
+    from aas_enhancement_b200 import build as b
+    log = "\n".join([
+        "ptxas info    : Compiling entry function '_ZN8aas_lmfb7lmfb_k1ILi1ELb0ELi5ELi3ELb0ELb0EEEvNS_6K1ArgsENS_5TabOfIXT0_EE5ParamE' for 'sm_100a'",
+        "ptxas info    : Function properties for _ZN8aas_lmfb7lmfb_k1ILi1ELb0ELi5ELi3ELb0ELb0EEEvNS_6K1ArgsENS_5TabOfIXT0_EE5ParamE",
+        "    16 bytes stack frame, 12 bytes spill stores, 16 bytes spill loads",
+        "ptxas info    : Used 128 registers, used 1 barriers, 16 bytes cumulative stack size",
+        "ptxas info    : Compiling entry function '_ZN8aas_lmfb7lmfb_k1ILi1ELb1ELi8ELi2ELb0ELb0EEEvNS_6K1ArgsENS_5TabOfIXT0_EE5ParamE' for 'sm_100a'",
+        "    8 bytes stack frame, 8 bytes spill stores, 8 bytes spill loads",
+        "ptxas info    : Used 128 registers, used 1 barriers",
+        "ptxas info    : Compiling entry function '_ZN8aas_lmfb7lmfb_k1ILi1ELb1ELi4ELi3ELb1ELb0EEEvNS_6K1ArgsENS_5TabOfIXT0_EE5ParamE' for 'sm_100a'",
+        "    64 bytes stack frame, 60 bytes spill stores, 60 bytes spill loads",
+        "ptxas info    : Used 168 registers, used 1 barriers",
+    ])
+    rep = b.stack_report(log)
+    assert len(rep) == 3
+    assert [v for k, v in rep.items() if "ELi5ELi3ELb0ELb0E" in k] == [[16, 128]]
+    # five-warp kernel: 16 bytes; eight-warp kernel: 8 bytes, weighted a thousandfold; the wave-gradient kernel is not a hot one
+    assert b.hot_stack_bytes(rep) == 16 + 8 * 1000
+    assert b.hot_stack_bytes(b.stack_report(log.replace("    8 bytes stack", "    0 bytes stack"))) <= b.GOOD_ENOUGH
+    assert b.SPLITS[0] == 1                      # the reproducible single-module build is tried first
